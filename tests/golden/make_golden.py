@@ -1,0 +1,162 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference sources.
+
+Runs only in the build container (needs /root/reference).  TensorFlow is absent there,
+so the reference files are executed against oracle/tf1_shim.py (a TF1-API emulation on
+torch CPU, fp32) -- see that file's header for what this does and does not pin.
+Gradients are torch autograd over the reference's own op sequence, i.e. what
+`tf.gradients` would assemble from the same graph.
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import tf1_shim as tf  # noqa: E402
+
+REF = os.environ.get('DVSG_REFERENCE', '/root/reference')
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def smooth_image(rng, b, h, w, c):
+    """Band-limited frames in [0,1]: low-frequency sinusoids + 1% noise."""
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing='ij')
+    im = np.zeros((b, h, w, c), np.float64)
+    for bi in range(b):
+        for ci in range(c):
+            for _ in range(4):
+                fx, fy = rng.uniform(-1, 1, 2) / 12.0
+                im[bi, :, :, ci] += np.sin(2 * np.pi * (fx * xx + fy * yy) + rng.uniform(0, 6.28))
+    im = (im - im.min()) / (im.max() - im.min())
+    return (0.99 * im + 0.01 * rng.random(im.shape)).astype(np.float32)
+
+
+def mesh(n_rows, n_cols, b):
+    xs = np.linspace(-1, 1, n_cols)
+    ys = np.linspace(-1, 1, n_rows)
+    gx, gy = np.meshgrid(xs, ys)
+    m = np.stack([gx.reshape(-1), gy.reshape(-1)], 1).astype(np.float32)
+    return np.tile(m[None], (b, 1, 1))
+
+
+def tt(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def run_tps(fn, u, coord, second, out_size, g_out, g_x, g_y, dtype):
+    tf.set_float(dtype)
+    u_t = tt(u).to(dtype).requires_grad_(True)
+    s_t = tt(second).to(dtype).requires_grad_(True)
+    c_t = tt(coord).to(dtype)
+    out, x, y = fn(u_t, c_t, s_t, list(out_size))
+    loss = (out * tt(g_out).to(dtype)).sum() + (x * tt(g_x).to(dtype)).sum() + (y * tt(g_y).to(dtype)).sum()
+    loss.backward()
+    tf.set_float(torch.float32)
+    return [v.detach().numpy() for v in (out, x, y, u_t.grad, s_t.grad)]
+
+
+def tps_cases(rng):
+    ref_tps = tf.load_reference(os.path.join(REF, 'ThinPlateSpline.py'), 'ref_ThinPlateSpline')
+    ref_tps2 = tf.load_reference(os.path.join(REF, 'ThinPlateSpline2.py'), 'ref_ThinPlateSpline2')
+    cases = {}
+    specs = [
+        # name,           B, H,  W,  C, mesh,   out_size, amplitude, variant
+        ('tps_4x4',       2, 24, 32, 3, (4, 4), (24, 32), 0.10, 1),
+        ('tps_5x5',       2, 18, 20, 3, (5, 5), (18, 20), 0.10, 1),
+        ('tps_4x4_big',   1, 36, 52, 3, (4, 4), (36, 52), 0.35, 1),   # samples far outside the frame
+        ('tps_resize',    2, 16, 20, 2, (3, 3), (12, 10), 0.05, 1),   # out_size != in size, C=2
+        ('tps2_4x4',      2, 20, 28, 3, (4, 4), (20, 28), 0.10, 2),
+        ('tps_8x8',       1, 20, 24, 1, (8, 8), (20, 24), 0.03, 1),   # N=67 > one warp
+    ]
+    for name, b, h, w, c, (mr, mc), osz, amp, variant in specs:
+        u = smooth_image(rng, b, h, w, c)
+        coord = mesh(mr, mc, b)
+        vec = rng.uniform(-amp, amp, coord.shape).astype(np.float32)
+        second = vec if variant == 1 else (coord + vec).astype(np.float32)
+        fn = ref_tps.ThinPlateSpline if variant == 1 else ref_tps2.ThinPlateSpline2
+        n_out = b * osz[0] * osz[1]
+        g_out = rng.standard_normal((b, osz[0], osz[1], c)).astype(np.float32)
+        g_x = (rng.standard_normal(n_out) * 0.1).astype(np.float32)
+        g_y = (rng.standard_normal(n_out) * 0.1).astype(np.float32)
+        out, x, y, gu, gs = run_tps(fn, u, coord, second, osz, g_out, g_x, g_y, torch.float32)
+        out64, x64, y64, gu64, gs64 = run_tps(fn, u, coord, second, osz, g_out, g_x, g_y, torch.float64)
+        cases[name] = dict(u=u, coord=coord, second=second, out_size=np.array(osz), variant=np.array(variant),
+                           g_out=g_out, g_x=g_x, g_y=g_y, out=out, x=x, y=y, grad_u=gu, grad_second=gs,
+                           out64=out64, x64=x64, y64=y64, grad_u64=gu64, grad_second64=gs64)
+    # validity mask: all-ones image (model.py:82,85)
+    b, h, w = 1, 24, 32
+    coord = mesh(4, 4, b)
+    vec = rng.uniform(-0.15, 0.15, coord.shape).astype(np.float32)
+    ones = np.ones((b, h, w, 3), np.float32)
+    out, x, y = ref_tps.ThinPlateSpline(tt(ones), tt(coord), tt(vec), [h, w])
+    cases['tps_mask'] = dict(u=ones, coord=coord, second=vec, out_size=np.array([h, w]), variant=np.array(1),
+                             out=out.numpy(), x=x.numpy(), y=y.numpy())
+    return cases
+
+
+def sampler_cases(rng):
+    st = tf.load_reference(os.path.join(REF, 'spatial_transformer.py'), 'ref_spatial_transformer')
+    fl = tf.load_reference(os.path.join(REF, 'warp_with_optical_flow.py'), 'ref_warp_with_optical_flow')
+    cases = {}
+    # B1
+    cases['meshgrid'] = dict(out_size=np.array([7, 9]), grid=st._meshgrid([7, 9]).numpy(),
+                             out_size2=np.array([288, 512]), grid2=st._meshgrid([288, 512]).numpy()[::97].copy())
+    # B2 / B3: C = 18 is the only live call (model.py:160-164); coordinates reach far outside
+    for name, b, h, w, c, osz in [('bilinear_c18', 2, 14, 18, 18, (14, 18)), ('bilinear_c3', 2, 15, 21, 3, (9, 13))]:
+        im = smooth_image(rng, b, h, w, c)
+        n = b * osz[0] * osz[1]
+        x = rng.uniform(-1.3, 1.3, n).astype(np.float32)
+        y = rng.uniform(-1.3, 1.3, n).astype(np.float32)
+        x[:8] = [-1.0, 1.0, -1.0 - 2.0 / (w - 1), 1.0 + 2.0 / (w - 1), 0.0, -5.0, 5.0, 1.0]
+        y[:8] = [-1.0, 1.0, 0.0, 0.0, 1.0 + 2.0 / (h - 1), 0.3, -0.3, -1.0]
+        g = rng.standard_normal((n, c)).astype(np.float32)
+        im_t, x_t, y_t = tt(im).requires_grad_(True), tt(x).requires_grad_(True), tt(y).requires_grad_(True)
+        out = st._interpolate(im_t, x_t, y_t, list(osz), 'bilinear')
+        (out * tt(g)).sum().backward()
+        cases[name] = dict(im=im, x=x, y=y, out_size=np.array(osz), g_out=g, out=out.detach().numpy(),
+                           grad_im=im_t.grad.numpy(), grad_x=x_t.grad.numpy(), grad_y=y_t.grad.numpy())
+    # N2: projective / affine transformers on top of B2
+    b, h, w, c = 2, 12, 16, 18
+    im = smooth_image(rng, b, h, w, c)
+    theta = (rng.uniform(-1, 1, (b, 8)) * np.array([0.1, 0.1, 0.5, 0.1, 0.1, 0.5, 0.1, 0.1])
+             + np.array([1.0, 0, 0, 0, 1.0, 0, 0, 0])).astype(np.float32)          # model.py:161-163
+    pt = st.ProjectiveTransformer([h, w])
+    cases['projective'] = dict(im=im, theta=theta, out_size=np.array([h, w]),
+                               out=pt.transform(tt(im), tt(theta)).numpy())
+    theta6 = (rng.uniform(-0.2, 0.2, (b, 6)) + np.array([1.0, 0, 0, 0, 1.0, 0])).astype(np.float32)
+    at = st.AffineTransformer([h, w])
+    cases['affine'] = dict(im=im, theta=theta6, out_size=np.array([h, w]),
+                           out=at.transform(tt(im), tt(theta6)).numpy())
+    # C1
+    for name, b, h, w, c, amp in [('flow_small', 2, 16, 24, 3, 2.0), ('flow_large', 1, 18, 22, 3, 12.0)]:
+        im = smooth_image(rng, b, h, w, c)
+        flow = rng.uniform(-amp, amp, (b, h, w, 2)).astype(np.float32)
+        flow[0, 0, 0] = [-1.0, -1.0]
+        flow[0, 0, 1] = [0.0, 0.0]
+        flow[0, 1, 0] = [w + 3.0, 0.5]
+        g = rng.standard_normal((b, h, w, c)).astype(np.float32)
+        im_t, f_t = tt(im).requires_grad_(True), tt(flow).requires_grad_(True)
+        out = fl.tf_warp(im_t, f_t, h, w)
+        (out * tt(g)).sum().backward()
+        cases[name] = dict(im=im, flow=flow, g_out=g, out=out.detach().numpy(),
+                           grad_im=im_t.grad.numpy(), grad_flow=f_t.grad.numpy())
+    return cases
+
+
+def main():
+    rng = np.random.default_rng(20261018)
+    allc = {}
+    allc.update(tps_cases(rng))
+    allc.update(sampler_cases(rng))
+    for name, arrays in allc.items():
+        path = os.path.join(OUT, name + '.npz')
+        np.savez_compressed(path, **arrays)
+        print('%-16s %8.1f KB' % (name, os.path.getsize(path) / 1024.0))
+
+
+if __name__ == '__main__':
+    main()

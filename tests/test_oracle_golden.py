@@ -1,0 +1,92 @@
+"""CPU: the NumPy oracle against golden vectors produced by the UNMODIFIED reference sources
+(executed over oracle/tf1_shim.py -- see tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import dvsg_oracle as O
+from conftest import load_golden
+
+TPS_CASES = ['tps_4x4', 'tps_5x5', 'tps_4x4_big', 'tps_resize', 'tps2_4x4', 'tps_8x8']
+# fp32 noise of the coefficient solve grows with the system's condition number
+COORD_TOL = {'tps_8x8': 1e-4}
+
+
+@pytest.mark.parametrize('name', TPS_CASES)
+def test_tps_forward(name):
+    g = load_golden(name)
+    fn = O.thin_plate_spline if int(g['variant']) == 1 else O.thin_plate_spline2
+    out, x, y = fn(g['u'], g['coord'], g['second'], g['out_size'])
+    tol = COORD_TOL.get(name, 2e-5)
+    assert out.shape == g['out'].shape and out.dtype == np.float32
+    assert np.abs(x - g['x']).max() <= tol
+    assert np.abs(y - g['y']).max() <= tol
+    # frames are tiny (<= 52 px wide), so coordinate noise maps to << 1e-4 in pixel values
+    assert np.abs(out - g['out']).max() <= 1e-4
+    # both fp32 evaluations sit equally close to the fp64 run of the same reference graph
+    assert np.abs(x - g['x64']).max() <= 2 * max(np.abs(g['x'] - g['x64']).max(), 1e-6)
+
+
+@pytest.mark.parametrize('name', TPS_CASES)
+def test_tps_sampler_stage_is_bit_exact_on_identical_coordinates(name):
+    """A4 given the golden x, y: integer corners, weights and blend are pure IEEE ops."""
+    g = load_golden(name)
+    oh, ow = (int(v) for v in g['out_size'])
+    out = O.tps_interpolate(g['u'], g['x'], g['y'], oh, ow).reshape(g['out'].shape)
+    np.testing.assert_array_equal(out, g['out'])
+
+
+@pytest.mark.parametrize('name', ['tps_4x4', 'tps_5x5', 'tps_4x4_big', 'tps_resize', 'tps_8x8'])
+def test_tps_backward_stages(name):
+    """A5 stage by stage on the golden coordinates (gradients are discontinuous across
+    sampling-cell boundaries, so they are compared on identical x, y)."""
+    g = load_golden(name)
+    oh, ow = (int(v) for v in g['out_size'])
+    g_im, gx, gy = O.tps_interpolate_bwd(g['u'], g['x'], g['y'], oh, ow, g['g_out'])
+    scale = np.abs(g['grad_u']).max()
+    assert np.abs(g_im - g['grad_u']).max() <= 1e-5 * scale + 1e-6
+    g_t = O.tps_grid_bwd(g['coord'], oh, ow, gx + g['g_x'], gy + g['g_y'])
+    _, w_inv = O.tps_solve(g['coord'], g['coord'] + g['second'], return_inverse=True)
+    g_vec = O.tps_solve_bwd(w_inv, g_t)
+    ref = g['grad_second']
+    assert np.abs(g_vec - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_tps_mask_all_ones_image():
+    g = load_golden('tps_mask')
+    out, _, _ = O.thin_plate_spline(g['u'], g['coord'], g['second'], g['out_size'])
+    assert np.abs(out - g['out']).max() <= 1e-6
+    assert out.max() <= 1.0 + 1e-6 and out.min() >= -1e-5
+
+
+def test_st_meshgrid_exact():
+    g = load_golden('meshgrid')
+    np.testing.assert_array_equal(O.st_meshgrid(g['out_size']), g['grid'])
+    np.testing.assert_array_equal(O.st_meshgrid(g['out_size2'])[::97], g['grid2'])
+
+
+@pytest.mark.parametrize('name', ['bilinear_c18', 'bilinear_c3'])
+def test_bilinear_interp(name):
+    g = load_golden(name)
+    out = O.bilinear_interp(g['im'], g['x'], g['y'], g['out_size'])
+    np.testing.assert_array_equal(out, g['out'])
+    g_im, gx, gy = O.bilinear_interp_bwd(g['im'], g['x'], g['y'], g['out_size'], g['g_out'])
+    assert np.abs(g_im - g['grad_im']).max() <= 2e-6
+    assert np.abs(gx - g['grad_x']).max() <= 1e-6 * np.abs(g['grad_x']).max() + 1e-6
+    assert np.abs(gy - g['grad_y']).max() <= 1e-6 * np.abs(g['grad_y']).max() + 1e-6
+
+
+def test_projective_and_affine_transformers():
+    g = load_golden('projective')
+    assert np.abs(O.projective_transform(g['im'], g['theta'], g['out_size']) - g['out']).max() <= 1e-5
+    g = load_golden('affine')
+    assert np.abs(O.affine_transform(g['im'], g['theta'], g['out_size']) - g['out']).max() <= 1e-5
+
+
+@pytest.mark.parametrize('name', ['flow_small', 'flow_large'])
+def test_tf_warp(name):
+    g = load_golden(name)
+    h, w = g['im'].shape[1:3]
+    np.testing.assert_array_equal(O.tf_warp(g['im'], g['flow'], h, w), g['out'])
+    g_im, g_flow = O.tf_warp_bwd(g['im'], g['flow'], h, w, g['g_out'])
+    assert np.abs(g_im - g['grad_im']).max() <= 2e-6
+    assert np.abs(g_flow - g['grad_flow']).max() <= 2e-6
