@@ -1,0 +1,141 @@
+// api.cu -- library-level pieces of the C ABI: version, thread-local error string, launch
+// bookkeeping, and the host-buffer pipeline (H2D -> solve -> fused warp -> D2H).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "dvsg_common.cuh"
+
+namespace dvsg {
+
+static thread_local char t_err[512] = "";
+static thread_local long long t_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { t_launches += n; }
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return DVSG_ERR_CUDA;
+    }
+    return DVSG_OK;
+}
+
+}  // namespace dvsg
+
+using namespace dvsg;
+
+extern "C" int dvsg_version(void) { return 100; }   // 0.1.0
+extern "C" const char* dvsg_last_error(void) { return t_err; }
+extern "C" long long dvsg_launch_count(void) { return t_launches; }
+
+// ---- host-buffer pipeline ------------------------------------------------------------------
+// eval.py:106-110 feeds every frame from host memory and reads the warped frame back.  This
+// object is that call for a batch of frames: chunks of frames rotate through n_slots device
+// staging slots, each slot on its own stream, so chunk i's kernels overlap chunk i+1's H2D
+// copy and chunk i-1's D2H copy (two copy engines + SMs busy at once).
+struct dvsg_host_pipeline {
+    int device, H, W, C, pn, fpc, n_slots;
+    size_t frame_elems;
+    float* d_coord;                 // [pn, 2] shared mesh
+    std::vector<cudaStream_t> streams;
+    std::vector<float*> d_in, d_out, d_vec, d_T;
+};
+
+#define DVSG_CUDA(call)                                                   \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) {                                          \
+            set_error("%s: %s", #call, cudaGetErrorString(e_));           \
+            return DVSG_ERR_CUDA;                                         \
+        }                                                                 \
+    } while (0)
+
+extern "C" int dvsg_host_pipeline_create(dvsg_host_pipeline** out, int device, int H, int W, int C, int pn,
+                                         int frames_per_chunk, int n_slots) {
+    DVSG_REQUIRE(out && H > 0 && W > 0 && C > 0 && pn >= 3 && frames_per_chunk > 0 && n_slots > 0 && n_slots <= 16,
+                 "host_pipeline_create: bad argument");
+    DVSG_REQUIRE(pn + 3 <= 32, "host_pipeline_create: meshes above 29 control points are not supported by the host pipeline");
+    DVSG_CUDA(cudaSetDevice(device));
+    dvsg_host_pipeline* p = new dvsg_host_pipeline();
+    p->device = device; p->H = H; p->W = W; p->C = C; p->pn = pn; p->fpc = frames_per_chunk; p->n_slots = n_slots;
+    p->frame_elems = (size_t)H * W * C;
+    p->d_coord = nullptr;
+    *out = p;
+    DVSG_CUDA(cudaMalloc(&p->d_coord, (size_t)pn * 2 * sizeof(float)));
+    for (int s = 0; s < n_slots; ++s) {
+        cudaStream_t st;
+        float *a = nullptr, *b = nullptr, *v = nullptr, *t = nullptr;
+        DVSG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        p->streams.push_back(st);
+        DVSG_CUDA(cudaMalloc(&a, p->frame_elems * frames_per_chunk * sizeof(float)));
+        p->d_in.push_back(a);
+        DVSG_CUDA(cudaMalloc(&b, p->frame_elems * frames_per_chunk * sizeof(float)));
+        p->d_out.push_back(b);
+        DVSG_CUDA(cudaMalloc(&v, (size_t)frames_per_chunk * pn * 2 * sizeof(float)));
+        p->d_vec.push_back(v);
+        DVSG_CUDA(cudaMalloc(&t, (size_t)frames_per_chunk * 2 * (pn + 3) * sizeof(float)));
+        p->d_T.push_back(t);
+    }
+    return DVSG_OK;
+}
+
+extern "C" void dvsg_host_pipeline_destroy(dvsg_host_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (auto s : p->streams) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (auto q : p->d_in) cudaFree(q);
+    for (auto q : p->d_out) cudaFree(q);
+    for (auto q : p->d_vec) cudaFree(q);
+    for (auto q : p->d_T) cudaFree(q);
+    cudaFree(p->d_coord);
+    delete p;
+}
+
+__global__ void add_mesh_kernel(const float* __restrict__ coord, float* __restrict__ vec, int n, int per_frame) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vec[i] = __fadd_rn(coord[i % per_frame], vec[i]);   // coord + vector, ThinPlateSpline.py:161
+}
+
+extern "C" int dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, const float* coord_host,
+                                  const float* vector_host, float* out_host, int B) {
+    DVSG_REQUIRE(p && B >= 0, "host_tps_warp: bad argument");
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(U_host && coord_host && vector_host && out_host, "host_tps_warp: null pointer");
+    DVSG_CUDA(cudaSetDevice(p->device));
+    const size_t fe = p->frame_elems;
+    const int pn = p->pn;
+    DVSG_CUDA(cudaMemcpyAsync(p->d_coord, coord_host, (size_t)pn * 2 * sizeof(float), cudaMemcpyHostToDevice, p->streams[0]));
+    DVSG_CUDA(cudaStreamSynchronize(p->streams[0]));
+    int chunk = 0;
+    for (int f0 = 0; f0 < B; f0 += p->fpc, ++chunk) {
+        const int s = chunk % p->n_slots;
+        const int nf = B - f0 < p->fpc ? B - f0 : p->fpc;
+        cudaStream_t st = p->streams[s];   // stream order serialises reuse of slot s
+        DVSG_CUDA(cudaMemcpyAsync(p->d_in[s], U_host + (size_t)f0 * fe, fe * nf * sizeof(float), cudaMemcpyHostToDevice, st));
+        DVSG_CUDA(cudaMemcpyAsync(p->d_vec[s], vector_host + (size_t)f0 * pn * 2, (size_t)nf * pn * 2 * sizeof(float),
+                                  cudaMemcpyHostToDevice, st));
+        const int n = nf * pn * 2;
+        add_mesh_kernel<<<(n + 255) / 256, 256, 0, st>>>(p->d_coord, p->d_vec[s], n, pn * 2);
+        count_launch();
+        int rc = check_launch("add_mesh_kernel");
+        if (rc) return rc;
+        rc = dvsg_tps_solve(p->d_coord, 0, p->d_vec[s], p->d_T[s], nf, pn, nullptr, 0, st);
+        if (rc) return rc;
+        rc = dvsg_tps_warp_fwd(p->d_in[s], p->d_coord, 0, p->d_T[s], p->d_out[s], nullptr, nullptr, nullptr, nf, p->H, p->W,
+                               p->C, p->H, p->W, pn, 0, st);
+        if (rc) return rc;
+        DVSG_CUDA(cudaMemcpyAsync(out_host + (size_t)f0 * fe, p->d_out[s], fe * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    for (auto st : p->streams) DVSG_CUDA(cudaStreamSynchronize(st));
+    return DVSG_OK;
+}

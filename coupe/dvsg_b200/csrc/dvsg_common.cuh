@@ -1,0 +1,76 @@
+// dvsg_common.cuh -- error plumbing, launch bookkeeping and the sm_100a PTX wrappers
+// (mbarrier + 1-D bulk async copies, i.e. the non-tensor TMA path: SASS UBLKCP).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../../include/dvsg_warp.h"
+
+namespace dvsg {
+
+// ---- host-side error state (thread-local) ---------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);   // cudaGetLastError -> DVSG_ERR_CUDA
+
+#define DVSG_REQUIRE(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            ::dvsg::set_error(__VA_ARGS__);     \
+            return DVSG_ERR_INVALID;            \
+        }                                       \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#if defined(__CUDACC__)
+// ---- device-side PTX wrappers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (16-B aligned addresses, size % 16 == 0), completion on mbar
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+// shared -> global bulk copy, tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// single MUFU.LG2 (t is never denormal on this path: t >= 1e-6)
+__device__ __forceinline__ float lg2_approx(float t) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+#endif  // __CUDACC__
+
+}  // namespace dvsg

@@ -1,0 +1,275 @@
+// tps_solve.cu -- K1: batched TPS coefficient solve (and its backward w.r.t. the targets).
+//
+// Replaces _solve_system (ThinPlateSpline.py:143-166): W = [[P, R], [0, P^T]] with
+// R_ij = d2_ij * log(d2_ij + 1e-6), T = (W^-1 @ pad(target))^T.
+//
+// The matrix ENTRIES are formed in fp32 exactly as the reference forms them (so the system
+// solved is the reference's system); the elimination runs in fp64 with partial pivoting and
+// the coefficients are rounded to fp32 once at the end.  The reference's own fp32
+// inverse-then-multiply carries ~cond(W)*eps of noise (2e-6 for a 4x4 mesh, 1.6e-3 for
+// 16x16 -- SURVEY.md H4); the fp64 elimination removes this kernel's share of that noise
+// at no measurable cost (the kernel is latency-bound).
+//
+//   N = pn+3 <= 32 : one warp per frame, augmented [A | rhs] in shared memory, lane i owns
+//                    row i; pivot search with warp shuffles.
+//   N  > 32        : one CTA per DISTINCT system (1 when the mesh is shared by the batch --
+//                    SURVEY.md H6) runs Gauss-Jordan on [W | I] in a global-memory workspace,
+//                    then a second kernel applies W^-1 (or its transpose) to every frame.
+#include <float.h>
+
+#include "dvsg_common.cuh"
+#include "sampler_math.cuh"
+
+namespace dvsg {
+
+constexpr int SOLVE_WARPS = 4;
+constexpr int SMALL_N = 32;
+constexpr int SMALL_LD = SMALL_N + 2 + 1;   // odd row pitch (doubles): lane-per-row access is conflict-free
+
+// W_ij in fp32, reference op order (ThinPlateSpline.py:147-158).  i, j in [0, N).
+__device__ __forceinline__ float tps_w_entry(const float* __restrict__ c, int pn, int i, int j) {
+    if (i < pn) {
+        if (j == 0) return 1.0f;
+        if (j == 1) return c[2 * i];
+        if (j == 2) return c[2 * i + 1];
+        const int k = j - 3;
+        // reduce_sum(square(p_i - p_k)) over (1, x, y): the leading term is exactly 0
+        const float d2 = tps_d2(c[2 * i], c[2 * i + 1], c[2 * k], c[2 * k + 1]);
+        return DVSG_MUL(d2, logf(DVSG_ADD(d2, 1e-6f)));
+    }
+    if (j < 3) return 0.0f;
+    const int r = i - pn, k = j - 3;
+    return r == 0 ? 1.0f : c[2 * k + (r - 1)];
+}
+
+// rhs layout: TRANSPOSED == false : forward,  A = W,   rhs = pad(target)   -> T[b][c][i]
+//             TRANSPOSED == true  : backward, A = W^T, rhs = grad_T^T      -> grad_target[b][i][c], i < pn
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) tps_solve_warp_kernel(const float* __restrict__ coord, long long coord_stride,
+                                                                          const float* __restrict__ rhs_in, float* __restrict__ out,
+                                                                          int B, int pn) {
+    __shared__ double s_a[SOLVE_WARPS][SMALL_N * SMALL_LD];
+    __shared__ float s_c[SOLVE_WARPS][2 * SMALL_N];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * SOLVE_WARPS + w;
+    if (b >= B) return;
+    const int N = pn + 3, NC = N + 2;
+    double* a = s_a[w];
+    float* c = s_c[w];
+    const float* cb = coord + (size_t)b * coord_stride;
+    for (int i = lane; i < 2 * pn; i += 32) c[i] = cb[i];
+    __syncwarp();
+    // build [A | rhs]; lane = column here (coalesced smem writes), rows sequential
+    for (int i = 0; i < N; ++i) {
+        for (int j = lane; j < NC; j += 32) {
+            double v;
+            if (j < N) {
+                v = TRANSPOSED ? (double)tps_w_entry(c, pn, j, i) : (double)tps_w_entry(c, pn, i, j);
+            } else {
+                const int cc = j - N;
+                if (TRANSPOSED) v = (double)rhs_in[((size_t)b * 2 + cc) * N + i];                   // grad_T[b][cc][i]
+                else v = i < pn ? (double)rhs_in[((size_t)b * pn + i) * 2 + cc] : 0.0;              // pad(target)
+            }
+            a[i * SMALL_LD + j] = v;
+        }
+    }
+    __syncwarp();
+    // Gauss-Jordan with partial pivoting; lane i owns row i
+    for (int k = 0; k < N; ++k) {
+        double mag = (lane >= k && lane < N) ? fabs(a[lane * SMALL_LD + k]) : -1.0;
+        int piv = lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double om = __shfl_xor_sync(0xffffffffu, mag, off);
+            const int op = __shfl_xor_sync(0xffffffffu, piv, off);
+            if (om > mag || (om == mag && op < piv)) { mag = om; piv = op; }
+        }
+        if (piv != k) {   // swap rows k and piv, lanes over columns
+            for (int j = lane; j < NC; j += 32) {
+                const double t = a[k * SMALL_LD + j];
+                a[k * SMALL_LD + j] = a[piv * SMALL_LD + j];
+                a[piv * SMALL_LD + j] = t;
+            }
+        }
+        __syncwarp();
+        const double inv = 1.0 / a[k * SMALL_LD + k];
+        const double f = (lane < N && lane != k) ? a[lane * SMALL_LD + k] : 0.0;
+        __syncwarp();
+        if (lane < N) {
+            if (lane == k) {
+                for (int j = k; j < NC; ++j) a[k * SMALL_LD + j] *= inv;
+            }
+        }
+        __syncwarp();
+        if (lane < N && lane != k) {
+            for (int j = k; j < NC; ++j) a[lane * SMALL_LD + j] -= f * a[k * SMALL_LD + j];
+        }
+        __syncwarp();
+    }
+    // solution X[i][cc] = a[i][N+cc]
+    if (TRANSPOSED) {
+        for (int i = lane; i < 2 * pn; i += 32) out[(size_t)b * pn * 2 + i] = (float)a[(i >> 1) * SMALL_LD + N + (i & 1)];
+    } else {
+        for (int i = lane; i < 2 * N; i += 32) out[(size_t)b * 2 * N + i] = (float)a[(i % N) * SMALL_LD + N + (i / N)];
+    }
+}
+
+// ---- large systems: W^-1 into a global workspace, one CTA per distinct system ---------------
+constexpr int INV_THREADS = 1024;
+
+__global__ void __launch_bounds__(INV_THREADS) tps_inverse_kernel(const float* __restrict__ coord, long long coord_stride, int pn,
+                                                                  double* __restrict__ work /* [nsys][N][2N] */, int* __restrict__ status) {
+    extern __shared__ double s_buf[];   // pivot row (2N) + factor column (N)
+    __shared__ double s_red[32];
+    __shared__ int s_redi[32];
+    __shared__ int s_piv;
+    const int N = pn + 3, M = 2 * N;
+    const int tid = threadIdx.x;
+    const float* c = coord + (size_t)blockIdx.x * coord_stride;
+    double* a = work + (size_t)blockIdx.x * N * M;
+    double* s_row = s_buf;
+    double* s_col = s_buf + M;
+    for (int e = tid; e < N * M; e += INV_THREADS) {
+        const int i = e / M, j = e % M;
+        a[e] = j < N ? (double)tps_w_entry(c, pn, i, j) : (j - N == i ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int k = 0; k < N; ++k) {
+        // pivot search in column k, rows k..N-1
+        double mag = -1.0;
+        int piv = 0x7fffffff;
+        for (int i = k + tid; i < N; i += INV_THREADS) {
+            const double v = fabs(a[(size_t)i * M + k]);
+            if (v > mag) { mag = v; piv = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double om = __shfl_xor_sync(0xffffffffu, mag, off);
+            const int op = __shfl_xor_sync(0xffffffffu, piv, off);
+            if (om > mag || (om == mag && op < piv)) { mag = om; piv = op; }
+        }
+        if ((tid & 31) == 0) { s_red[tid >> 5] = mag; s_redi[tid >> 5] = piv; }
+        __syncthreads();
+        if (tid < 32) {
+            mag = s_red[tid]; piv = s_redi[tid];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double om = __shfl_xor_sync(0xffffffffu, mag, off);
+                const int op = __shfl_xor_sync(0xffffffffu, piv, off);
+                if (om > mag || (om == mag && op < piv)) { mag = om; piv = op; }
+            }
+            if (tid == 0) {
+                s_piv = piv;
+                if (!(mag > 0.0) && status) atomicExch(status, 1);   // singular (tf.matrix_inverse would raise)
+            }
+        }
+        __syncthreads();
+        piv = s_piv;
+        // stage the (scaled) pivot row and the factor column; swap rows k <-> piv on the fly
+        const double inv = 1.0 / a[(size_t)piv * M + k];
+        for (int j = tid; j < M; j += INV_THREADS) s_row[j] = a[(size_t)piv * M + j] * inv;
+        for (int i = tid; i < N; i += INV_THREADS) {
+            const int src = i == k ? piv : (i == piv ? k : i);     // row that will live at i after the swap
+            s_col[i] = i == k ? 0.0 : a[(size_t)src * M + k];
+        }
+        __syncthreads();
+        if (piv != k) {
+            for (int j = tid; j < M; j += INV_THREADS) a[(size_t)piv * M + j] = a[(size_t)k * M + j];
+        }
+        __syncthreads();
+        for (int e = tid; e < N * M; e += INV_THREADS) {
+            const int i = e / M, j = e % M;
+            a[e] = i == k ? s_row[j] : a[e] - s_col[i] * s_row[j];
+        }
+        __syncthreads();
+    }
+}
+
+// forward : T[b][c][i]           = sum_{j<pn} Winv[i][j]     * target[b][j][c]
+// backward: grad_target[b][j][c] = sum_{i<N}  Winv[i][j]     * grad_T[b][c][i]     (j < pn)
+template <bool TRANSPOSED>
+__global__ void tps_apply_kernel(const double* __restrict__ work, int shared_sys, const float* __restrict__ rhs,
+                                 float* __restrict__ out, int B, int pn) {
+    const int N = pn + 3, M = 2 * N;
+    const int n_out = TRANSPOSED ? pn : N;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * n_out) return;
+    const int b = (int)(gid / n_out), o = (int)(gid % n_out);
+    const double* winv = work + (size_t)(shared_sys ? 0 : b) * N * M + N;   // right half of [I | W^-1]
+    double a0 = 0.0, a1 = 0.0;
+    if (TRANSPOSED) {
+        for (int i = 0; i < N; ++i) {
+            const double w = winv[(size_t)i * M + o];
+            a0 += w * (double)rhs[((size_t)b * 2 + 0) * N + i];
+            a1 += w * (double)rhs[((size_t)b * 2 + 1) * N + i];
+        }
+        out[((size_t)b * pn + o) * 2 + 0] = (float)a0;
+        out[((size_t)b * pn + o) * 2 + 1] = (float)a1;
+    } else {
+        for (int j = 0; j < pn; ++j) {
+            const double w = winv[(size_t)o * M + j];
+            a0 += w * (double)rhs[((size_t)b * pn + j) * 2 + 0];
+            a1 += w * (double)rhs[((size_t)b * pn + j) * 2 + 1];
+        }
+        out[((size_t)b * 2 + 0) * N + o] = (float)a0;
+        out[((size_t)b * 2 + 1) * N + o] = (float)a1;
+    }
+}
+
+static size_t big_workspace_bytes(int B, int pn, long long stride) {
+    const size_t N = (size_t)pn + 3;
+    const size_t nsys = stride == 0 ? 1 : (size_t)B;
+    return nsys * N * 2 * N * sizeof(double) + 256;   // + status word, kept 256-B apart
+}
+
+template <bool TRANSPOSED>
+static int solve_impl(const float* coord, long long stride, const float* rhs, float* out, int B, int pn, void* ws,
+                      size_t ws_bytes, cudaStream_t st, const char* what) {
+    DVSG_REQUIRE(B >= 0 && pn >= 3, "%s: need B >= 0 and at least 3 control points (got B=%d pn=%d)", what, B, pn);
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(coord && rhs && out, "%s: null pointer", what);
+    DVSG_REQUIRE(stride == 0 || stride >= 2LL * pn, "%s: coord stride %lld < 2*pn", what, stride);
+    const int N = pn + 3;
+    if (N <= SMALL_N) {
+        tps_solve_warp_kernel<TRANSPOSED><<<(B + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, st>>>(coord, stride, rhs, out, B, pn);
+        count_launch();
+        return check_launch("tps_solve_warp_kernel");
+    }
+    DVSG_REQUIRE(N <= 2048, "%s: %d control points exceed the supported maximum 2045", what, pn);
+    const size_t need = big_workspace_bytes(B, pn, stride);
+    if (!ws || ws_bytes < need) {
+        set_error("%s: workspace of %zu bytes required, %zu given", what, need, ws_bytes);
+        return DVSG_ERR_WORKSPACE;
+    }
+    DVSG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7u) == 0, "%s: workspace must be 8-byte aligned", what);
+    const int nsys = stride == 0 ? 1 : B;
+    double* work = reinterpret_cast<double*>(ws);
+    tps_inverse_kernel<<<nsys, INV_THREADS, (size_t)3 * N * sizeof(double), st>>>(coord, stride, pn, work, nullptr);
+    count_launch();
+    int rc = check_launch("tps_inverse_kernel");
+    if (rc) return rc;
+    const long long n_out = (long long)B * (TRANSPOSED ? pn : N);
+    tps_apply_kernel<TRANSPOSED><<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(work, stride == 0, rhs, out, B, pn);
+    count_launch();
+    return check_launch("tps_apply_kernel");
+}
+
+}  // namespace dvsg
+
+using namespace dvsg;
+
+extern "C" size_t dvsg_tps_solve_workspace_bytes(int B, int pn, long long coord_batch_stride) {
+    if (pn + 3 <= SMALL_N || B <= 0) return 0;
+    return big_workspace_bytes(B, pn, coord_batch_stride);
+}
+
+extern "C" int dvsg_tps_solve(const float* coord, long long coord_batch_stride, const float* target, float* T, int B, int pn,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    return solve_impl<false>(coord, coord_batch_stride, target, T, B, pn, workspace, workspace_bytes, (cudaStream_t)stream, "tps_solve");
+}
+
+extern "C" int dvsg_tps_solve_bwd(const float* coord, long long coord_batch_stride, const float* grad_T, float* grad_target,
+                                  int B, int pn, void* workspace, size_t workspace_bytes, void* stream) {
+    return solve_impl<true>(coord, coord_batch_stride, grad_T, grad_target, B, pn, workspace, workspace_bytes, (cudaStream_t)stream,
+                            "tps_solve_bwd");
+}

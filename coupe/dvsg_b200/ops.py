@@ -1,0 +1,346 @@
+"""Host-side operators over the C ABI: shape checks, buffer allocation, autograd wiring.
+
+Each public function here is the eager, CUDA-backed equivalent of one group of TF ops in
+the reference; the drop-in modules (ThinPlateSpline.py, spatial_transformer.py,
+warp_with_optical_flow.py) only rename these to the reference's signatures.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._tensors import as_cuda_f32, out_hw, ptr, stream_ptr
+
+_workspaces = {}   # (device index) -> cached uint8 workspace for large TPS systems
+
+
+def _workspace(device, nbytes):
+    if nbytes == 0:
+        return None
+    key = device.index
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _as_mesh(coord, like):
+    """coord -> fp32 CUDA tensor WITHOUT materialising a batch-stride-0 (expanded) view."""
+    if not isinstance(coord, torch.Tensor):
+        if not hasattr(coord, '__dlpack__'):
+            raise TypeError('coord: expected a torch.Tensor or a DLPack-capable array, got %s' % type(coord).__name__)
+        coord = torch.from_dlpack(coord)
+    if not coord.is_cuda:
+        raise ValueError('coord: tensor lives on %s -- this path runs on CUDA only (no CPU fallback)' % coord.device)
+    if coord.device != like.device:
+        raise ValueError('coord: device %s differs from %s' % (coord.device, like.device))
+    return coord if coord.dtype == torch.float32 else coord.float()
+
+
+def _mesh_args(coord, B, pn_expected=None):
+    """coord [B,pn,2] (dense) or [pn,2] / batch-stride-0 view (one mesh shared by the batch,
+    as model.py:68 builds it) -> (contiguous tensor, batch stride in floats, pn)."""
+    if coord.dim() == 2:
+        coord = coord.unsqueeze(0).expand(B, -1, -1)
+    if coord.dim() != 3 or coord.shape[2] != 2 or coord.shape[0] != B:
+        raise ValueError('coord must have shape [B, num_point, 2] with B=%d, got %s' % (B, tuple(coord.shape)))
+    pn = coord.shape[1]
+    if pn_expected is not None and pn != pn_expected:
+        raise ValueError('coord has %d control points, expected %d' % (pn, pn_expected))
+    if B > 0 and coord.stride(0) == 0:
+        return coord[0].contiguous(), 0, pn
+    return coord.contiguous(), pn * 2, pn
+
+
+# ---- K1 ------------------------------------------------------------------------------------
+def tps_solve(coord, target):
+    """_solve_system (ThinPlateSpline.py:143-166) -> T [B, 2, pn+3]."""
+    lib = _lib.load()
+    target = as_cuda_f32(target, 'target')
+    B = target.shape[0]
+    coord = _as_mesh(coord, target)
+    cbuf, cstride, pn = _mesh_args(coord, B)
+    if tuple(target.shape) != (B, pn, 2):
+        raise ValueError('target must have shape [B, num_point, 2], got %s' % (tuple(target.shape),))
+    if pn < 3:
+        raise ValueError('TPS needs at least 3 control points, got %d' % pn)
+    T = torch.empty((B, 2, pn + 3), dtype=torch.float32, device=target.device)
+    nbytes = lib.dvsg_tps_solve_workspace_bytes(B, pn, cstride)
+    ws = _workspace(target.device, nbytes)
+    with torch.cuda.device(target.device):
+        rc = lib.dvsg_tps_solve(ptr(cbuf), cstride, ptr(target), ptr(T), B, pn, ptr(ws), nbytes, stream_ptr(target.device))
+    _lib.check(rc, 'dvsg_tps_solve')
+    return T
+
+
+def tps_solve_bwd(coord, grad_T):
+    lib = _lib.load()
+    grad_T = as_cuda_f32(grad_T, 'grad_T')
+    B, _, N = grad_T.shape
+    cbuf, cstride, pn = _mesh_args(coord, B, N - 3)
+    g = torch.empty((B, pn, 2), dtype=torch.float32, device=grad_T.device)
+    nbytes = lib.dvsg_tps_solve_workspace_bytes(B, pn, cstride)
+    ws = _workspace(grad_T.device, nbytes)
+    with torch.cuda.device(grad_T.device):
+        rc = lib.dvsg_tps_solve_bwd(ptr(cbuf), cstride, ptr(grad_T), ptr(g), B, pn, ptr(ws), nbytes, stream_ptr(grad_T.device))
+    _lib.check(rc, 'dvsg_tps_solve_bwd')
+    return g
+
+
+# ---- K2+K3 / K4 ------------------------------------------------------------------------------
+def tps_warp_fwd(U, coord, T, out_size, want_grid=True, want_mask=False, flags=0):
+    lib = _lib.load()
+    B, H, W, C = U.shape
+    oh, ow = out_hw(out_size)
+    cbuf, cstride, pn = _mesh_args(coord, B, T.shape[2] - 3)
+    dev = U.device
+    out = torch.empty((B, oh, ow, C), dtype=torch.float32, device=dev)
+    x = torch.empty(B * oh * ow, dtype=torch.float32, device=dev) if want_grid else None
+    y = torch.empty(B * oh * ow, dtype=torch.float32, device=dev) if want_grid else None
+    mask = torch.empty((B, oh, ow), dtype=torch.float32, device=dev) if want_mask else None
+    with torch.cuda.device(dev):
+        rc = lib.dvsg_tps_warp_fwd(ptr(U), ptr(cbuf), cstride, ptr(T), ptr(out), ptr(x), ptr(y), ptr(mask),
+                                   B, H, W, C, oh, ow, pn, flags, stream_ptr(dev))
+    _lib.check(rc, 'dvsg_tps_warp_fwd')
+    return out, x, y, mask
+
+
+def tps_warp_bwd(U, coord, T, out_size, grad_out, grad_x=None, grad_y=None, need_grad_U=True, want_grid_grad=False):
+    lib = _lib.load()
+    B, H, W, C = U.shape
+    oh, ow = out_hw(out_size)
+    cbuf, cstride, pn = _mesh_args(coord, B, T.shape[2] - 3)
+    dev = U.device
+    grad_out = as_cuda_f32(grad_out, 'grad_out', like=U)
+    gx_in = as_cuda_f32(grad_x, 'grad_x', like=U) if grad_x is not None else None
+    gy_in = as_cuda_f32(grad_y, 'grad_y', like=U) if grad_y is not None else None
+    if (gx_in is None) != (gy_in is None):
+        z = torch.zeros(B * oh * ow, dtype=torch.float32, device=dev)
+        gx_in = z if gx_in is None else gx_in
+        gy_in = z if gy_in is None else gy_in
+    gU = torch.zeros_like(U) if need_grad_U else None
+    gT = torch.empty((B, 2, pn + 3), dtype=torch.float32, device=dev)
+    gxs = torch.empty(B * oh * ow, dtype=torch.float32, device=dev) if want_grid_grad else None
+    gys = torch.empty(B * oh * ow, dtype=torch.float32, device=dev) if want_grid_grad else None
+    with torch.cuda.device(dev):
+        rc = lib.dvsg_tps_warp_bwd(ptr(U), ptr(cbuf), cstride, ptr(T), ptr(grad_out), ptr(gx_in), ptr(gy_in), ptr(gU),
+                                   ptr(gT), ptr(gxs), ptr(gys), B, H, W, C, oh, ow, pn, stream_ptr(dev))
+    _lib.check(rc, 'dvsg_tps_warp_bwd')
+    return gU, gT, gxs, gys
+
+
+class _TpsWarp(torch.autograd.Function):
+    """(U, target) -> (output, x, y) with coord a constant, as in every reference call site
+    (model.py:62-68)."""
+
+    @staticmethod
+    def forward(ctx, U, coord, target, out_size, want_grid):
+        T = tps_solve(coord, target)
+        out, x, y, _ = tps_warp_fwd(U, coord, T, out_size, want_grid=want_grid)
+        ctx.save_for_backward(U, coord, T)
+        ctx.out_size = out_size
+        ctx.want_grid = want_grid
+        if not want_grid:
+            x, y = out.new_empty(0), out.new_empty(0)
+            ctx.mark_non_differentiable(x, y)
+        return out, x, y
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_x, grad_y):
+        U, coord, T = ctx.saved_tensors
+        if not ctx.want_grid:
+            grad_x = grad_y = None
+        need_U = ctx.needs_input_grad[0]
+        need_t = ctx.needs_input_grad[2]
+        gU, gT, _, _ = tps_warp_bwd(U, coord, T, ctx.out_size, grad_out.contiguous(), grad_x, grad_y, need_grad_U=need_U)
+        g_target = tps_solve_bwd(coord, gT) if need_t else None
+        return gU, None, g_target, None, None
+
+
+def thin_plate_spline(U, coord, target, out_size, want_grid=True):
+    U = as_cuda_f32(U, 'U')
+    if U.dim() != 4:
+        raise ValueError('U must have shape [num_batch, height, width, num_channels], got %s' % (tuple(U.shape),))
+    coord = _as_mesh(coord, U)
+    target = as_cuda_f32(target, 'target', like=U)
+    if coord.requires_grad:
+        raise NotImplementedError('gradient w.r.t. the control-point positions is not implemented: every reference '
+                                  'call site passes a constant mesh (model.py:62-68)')
+    out, x, y = _TpsWarp.apply(U, coord, target, tuple(out_hw(out_size)), bool(want_grid))
+    return (out, x, y) if want_grid else (out, None, None)
+
+
+def thin_plate_spline_with_mask(U, coord, target, out_size, want_grid=True):
+    """N1: the image warp and the warp of an all-ones image (model.py:82,85,121)
+    from ONE pass.  Inference-style (no autograd through the mask, matching the reference where the
+    mask only gates losses)."""
+    U = as_cuda_f32(U, 'U')
+    target = as_cuda_f32(target, 'target', like=U)
+    coord = _as_mesh(coord, U)
+    T = tps_solve(coord, target)
+    out, x, y, mask = tps_warp_fwd(U, coord, T, out_hw(out_size), want_grid=want_grid, want_mask=True)
+    return out, mask.unsqueeze(-1).expand(-1, -1, -1, U.shape[3]), x, y
+
+
+# ---- K5 --------------------------------------------------------------------------------------
+class _Bilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, im, x, y, out_size):
+        lib = _lib.load()
+        B, H, W, C = im.shape
+        oh, ow = out_size
+        out = torch.empty((B * oh * ow, C), dtype=torch.float32, device=im.device)
+        with torch.cuda.device(im.device):
+            rc = lib.dvsg_bilinear_fwd(ptr(im), ptr(x), ptr(y), ptr(out), B, H, W, C, oh, ow, 0, stream_ptr(im.device))
+        _lib.check(rc, 'dvsg_bilinear_fwd')
+        ctx.save_for_backward(im, x, y)
+        ctx.out_size = out_size
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        im, x, y = ctx.saved_tensors
+        B, H, W, C = im.shape
+        oh, ow = ctx.out_size
+        grad_out = grad_out.contiguous()
+        g_im = torch.zeros_like(im) if ctx.needs_input_grad[0] else None
+        need_xy = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        gx = torch.empty_like(x) if need_xy else None
+        gy = torch.empty_like(y) if need_xy else None
+        with torch.cuda.device(im.device):
+            rc = lib.dvsg_bilinear_bwd(ptr(im), ptr(x), ptr(y), ptr(grad_out), ptr(g_im), ptr(gx), ptr(gy),
+                                       B, H, W, C, oh, ow, stream_ptr(im.device))
+        _lib.check(rc, 'dvsg_bilinear_bwd')
+        return g_im, gx, gy, None
+
+
+def bilinear_interp(im, x, y, out_size):
+    im = as_cuda_f32(im, 'im')
+    if im.dim() != 4:
+        raise ValueError('im must have shape [batch, height, width, channels], got %s' % (tuple(im.shape),))
+    oh, ow = out_hw(out_size)
+    x = as_cuda_f32(x, 'x', like=im).reshape(-1)
+    y = as_cuda_f32(y, 'y', like=im).reshape(-1)
+    n = im.shape[0] * oh * ow
+    if x.numel() != n or y.numel() != n:
+        raise ValueError('x and y must hold batch*out_height*out_width = %d coordinates, got %d and %d' % (n, x.numel(), y.numel()))
+    return _Bilinear.apply(im, x, y, (oh, ow))
+
+
+# ---- K6 --------------------------------------------------------------------------------------
+class _FlowWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, im, flow):
+        lib = _lib.load()
+        B, H, W, C = im.shape
+        out = torch.empty_like(im)
+        with torch.cuda.device(im.device):
+            rc = lib.dvsg_flow_warp_fwd(ptr(im), ptr(flow), ptr(out), B, H, W, C, 0, stream_ptr(im.device))
+        _lib.check(rc, 'dvsg_flow_warp_fwd')
+        ctx.save_for_backward(im, flow)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        im, flow = ctx.saved_tensors
+        B, H, W, C = im.shape
+        grad_out = grad_out.contiguous()
+        g_im = torch.zeros_like(im) if ctx.needs_input_grad[0] else None
+        g_flow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(im.device):
+            rc = lib.dvsg_flow_warp_bwd(ptr(im), ptr(flow), ptr(grad_out), ptr(g_im), ptr(g_flow), B, H, W, C, stream_ptr(im.device))
+        _lib.check(rc, 'dvsg_flow_warp_bwd')
+        return g_im, g_flow
+
+
+def flow_warp(im, flow, out_height, out_width):
+    im = as_cuda_f32(im, 'im')
+    flow = as_cuda_f32(flow, 'flow', like=im)
+    if im.dim() != 4:
+        raise ValueError('im must have shape [batch, height, width, channels], got %s' % (tuple(im.shape),))
+    B, H, W, _ = im.shape
+    if tuple(flow.shape) != (B, H, W, 2):
+        raise ValueError('flow must have shape [batch, height, width, 2] matching im, got %s' % (tuple(flow.shape),))
+    if (int(out_height), int(out_width)) != (H, W):
+        # the reference builds its gather base from out_height*out_width while x, y come from im's
+        # own size (warp_with_optical_flow.py:107,148): any other value is ill-formed there too
+        raise ValueError('tf_warp requires out_height, out_width == im height, width (%d, %d)' % (H, W))
+    return _FlowWarp.apply(im, flow)
+
+
+# ---- B1 / N2 ---------------------------------------------------------------------------------
+def st_meshgrid(out_size, device=None):
+    lib = _lib.load()
+    oh, ow = out_hw(out_size)
+    device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    grid = torch.empty(3 * oh * ow, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = lib.dvsg_st_meshgrid(ptr(grid), oh, ow, stream_ptr(device))
+    _lib.check(rc, 'dvsg_st_meshgrid')
+    return grid
+
+
+def homography_warp(inp, theta, out_size, projective, want_grid=False):
+    lib = _lib.load()
+    inp = as_cuda_f32(inp, 'inp')
+    B, H, W, C = inp.shape
+    nt = 8 if projective else 6
+    theta = as_cuda_f32(theta, 'theta', like=inp).reshape(B, nt)
+    oh, ow = out_hw(out_size)
+    out = torch.empty((B, oh, ow, C), dtype=torch.float32, device=inp.device)
+    x = torch.empty(B * oh * ow, dtype=torch.float32, device=inp.device) if want_grid else None
+    y = torch.empty(B * oh * ow, dtype=torch.float32, device=inp.device) if want_grid else None
+    with torch.cuda.device(inp.device):
+        rc = lib.dvsg_homography_warp_fwd(ptr(inp), ptr(theta), 1 if projective else 0, ptr(out), ptr(x), ptr(y),
+                                          B, H, W, C, oh, ow, stream_ptr(inp.device))
+    _lib.check(rc, 'dvsg_homography_warp_fwd')
+    return (out, x, y) if want_grid else out
+
+
+# ---- host-buffer pipeline --------------------------------------------------------------------
+class HostPipeline(object):
+    """ThinPlateSpline on HOST buffers: H2D, solve, fused warp and D2H overlapped across
+    `n_slots` staging slots (the e2e path measured by bench.py)."""
+
+    def __init__(self, H, W, C, pn, frames_per_chunk=8, n_slots=3, device=None):
+        lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.shape = (H, W, C)
+        self.pn = pn
+        h = ctypes.c_void_p()
+        rc = lib.dvsg_host_pipeline_create(ctypes.byref(h), self.device, H, W, C, pn, frames_per_chunk, n_slots)
+        if rc != 0:
+            if h.value:
+                lib.dvsg_host_pipeline_destroy(h)
+            _lib.check(rc, 'dvsg_host_pipeline_create')
+        self._h = h
+
+    def thin_plate_spline(self, U_host, coord_host, vector_host, out_host=None):
+        """U_host [B,H,W,C], coord_host [pn,2], vector_host [B,pn,2]: CPU fp32 contiguous torch
+        tensors (pinned for full PCIe bandwidth).  Returns out_host."""
+        lib = _lib.load()
+        for name, t in (('U', U_host), ('coord', coord_host), ('vector', vector_host)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError('%s must be a contiguous fp32 CPU tensor' % name)
+        B = U_host.shape[0]
+        if tuple(U_host.shape[1:]) != self.shape or tuple(coord_host.shape) != (self.pn, 2) or tuple(vector_host.shape) != (B, self.pn, 2):
+            raise ValueError('shape mismatch with the pipeline configuration')
+        if out_host is None:
+            out_host = torch.empty_like(U_host, pin_memory=U_host.is_pinned())
+        rc = lib.dvsg_host_tps_warp(self._h, U_host.data_ptr(), coord_host.data_ptr(), vector_host.data_ptr(), out_host.data_ptr(), B)
+        _lib.check(rc, 'dvsg_host_tps_warp')
+        return out_host
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            _lib.load().dvsg_host_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,142 @@
+/*
+ * dvsg_warp.h -- C ABI of the B200-native (sm_100a) frame-warping hot path of DVSG.
+ *
+ * The reference (posgraph/coupe.DVSG) has no FFI: its boundary for this path is a set of
+ * plain Python functions built from stock TensorFlow ops.  Each entry point below replaces
+ * the group of TF ops named in its comment (file:line relative to the reference tree);
+ * the Python modules under coupe/dvsg_b200/ keep the reference's function signatures and
+ * bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - all tensors are fp32, contiguous, NHWC for images; indices are int32 internally;
+ *   - every pointer is a DEVICE pointer owned by the caller (no hidden allocation, no
+ *     hidden host<->device copy) except in the dvsg_host_* pipeline, which takes HOST
+ *     pointers and a caller-created pipeline object that owns its staging buffers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work
+ *     is enqueued on it and the call returns without synchronising;
+ *   - return value: 0 on success, negative DVSG_ERR_* otherwise; dvsg_last_error()
+ *     returns a thread-local message for the last failing call on this thread;
+ *   - the library is stateless and re-entrant (one host thread per GPU is the intended
+ *     multi-GPU driving model; frames shard independently, no collective).
+ */
+#ifndef DVSG_WARP_H_
+#define DVSG_WARP_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVSG_OK               0
+#define DVSG_ERR_INVALID     (-1)   /* bad shape / null pointer / misaligned argument   */
+#define DVSG_ERR_CUDA        (-2)   /* a CUDA runtime call or kernel launch failed       */
+#define DVSG_ERR_WORKSPACE   (-3)   /* caller-provided workspace too small               */
+#define DVSG_ERR_UNSUPPORTED (-4)   /* valid request outside the implemented envelope    */
+
+/* flags for dvsg_tps_warp_fwd / dvsg_bilinear_fwd / dvsg_flow_warp_fwd */
+#define DVSG_FLAG_FORCE_DIRECT 1    /* use the direct-gather kernel even when the
+                                       shared-memory-staged kernel is applicable          */
+
+int         dvsg_version(void);
+const char* dvsg_last_error(void);
+/* number of kernels this library has launched on the calling thread (bench bookkeeping) */
+long long   dvsg_launch_count(void);
+
+/* ---- K1: TPS coefficient solve -------------------------------------------------------
+ * Replaces _solve_system: ThinPlateSpline.py:143-166 (tf.matrix_inverse :159, tf.matmul
+ * :163) and ThinPlateSpline2.py:142-165.
+ *   coord  [B, pn, 2] control points (x, y); coord_batch_stride in floats between frames
+ *          (pn*2 for a dense batch, 0 = one mesh shared by every frame);
+ *   target [B, pn, 2] right-hand side: coord+vector (ThinPlateSpline.py:161) or the
+ *          absolute targets (ThinPlateSpline2.py:160);
+ *   T      [B, 2, pn+3] out; coefficient order (1, x, y, rbf_1..rbf_pn) as the grid rows of
+ *          ThinPlateSpline.py:110.
+ * The system matrix entries are formed in fp32 in the reference's op order; the
+ * elimination itself runs in fp64 (partial pivoting) and T is rounded to fp32.
+ * pn+3 <= 32: one warp per frame, no workspace.  Larger systems: one CTA per distinct
+ * system inverts it into `workspace` (see dvsg_tps_solve_workspace_bytes).            */
+size_t dvsg_tps_solve_workspace_bytes(int B, int pn, long long coord_batch_stride);
+int dvsg_tps_solve(const float* coord, long long coord_batch_stride, const float* target,
+                   float* T, int B, int pn, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* Backward of K1 w.r.t. the right-hand side (the only gradient the reference's callers
+ * need, coord being a constant: model.py:62-68):  grad_target = (W^-T grad_T^T)[:pn].   */
+int dvsg_tps_solve_bwd(const float* coord, long long coord_batch_stride, const float* grad_T,
+                       float* grad_target, int B, int pn, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- K2+K3: fused TPS grid generation + bilinear gather ------------------------------
+ * Replaces _meshgrid (ThinPlateSpline.py:92-111), tf.matmul(T, grid) (:129) and
+ * _interpolate (:30-90) -- the [B, pn+3, h*w] basis is never materialised.
+ *   U [B,H,W,C] source; out [B,oh,ow,C];
+ *   x_out, y_out: optional (may be NULL) flat [B*oh*ow] normalised sampling coordinates,
+ *          the 2nd/3rd return values of ThinPlateSpline (:170);
+ *   mask_out: optional [B,oh,ow] -- the warp of an all-ones image (model.py:82,85,121),
+ *          i.e. the sum of the four bilinear weights in add_n order.                   */
+int dvsg_tps_warp_fwd(const float* U, const float* coord, long long coord_batch_stride,
+                      const float* T, float* out, float* x_out, float* y_out, float* mask_out,
+                      int B, int H, int W, int C, int oh, int ow, int pn, int flags,
+                      void* stream);
+
+/* ---- K4: backward of K2+K3 (TF autodiff of ThinPlateSpline.py:48-89,129) -------------
+ *   grad_out [B,oh,ow,C]; grad_x_in / grad_y_in: optional upstream gradients on the
+ *   returned x, y (surf loss, trainer.py:363-386);
+ *   grad_U [B,H,W,C]: accumulated into with atomics -- the caller zero-fills it (or
+ *          passes NULL to skip the image gradient);
+ *   grad_T [B,2,pn+3]: overwritten (may be NULL);
+ *   grad_xs / grad_ys: optional flat [B*oh*ow] total gradient w.r.t. x_s, y_s.          */
+int dvsg_tps_warp_bwd(const float* U, const float* coord, long long coord_batch_stride,
+                      const float* T, const float* grad_out, const float* grad_x_in,
+                      const float* grad_y_in, float* grad_U, float* grad_T, float* grad_xs,
+                      float* grad_ys, int B, int H, int W, int C, int oh, int ow, int pn,
+                      void* stream);
+
+/* ---- K5: generic bilinear sampler -----------------------------------------------------
+ * Replaces bilinear_interp (spatial_transformer.py:496-563): 1-px zero padding,
+ * (W-1)/2 scaling, coordinate clip.  x, y flat [B*oh*ow] normalised; out [B,oh,ow,C].    */
+int dvsg_bilinear_fwd(const float* im, const float* x, const float* y, float* out,
+                      int B, int H, int W, int C, int oh, int ow, int flags, void* stream);
+/* grad_im is accumulated into (caller zero-fills; NULL to skip); grad_x, grad_y
+ * overwritten (NULL to skip).                                                          */
+int dvsg_bilinear_bwd(const float* im, const float* x, const float* y, const float* grad_out,
+                      float* grad_im, float* grad_x, float* grad_y,
+                      int B, int H, int W, int C, int oh, int ow, void* stream);
+
+/* ---- K6: dense optical-flow warp -------------------------------------------------------
+ * Replaces tf_warp (warp_with_optical_flow.py:96-176).  flow [B,H,W,2], channel 0 = dx,
+ * 1 = dy in pixels; out [B,H,W,C].                                                     */
+int dvsg_flow_warp_fwd(const float* im, const float* flow, float* out,
+                       int B, int H, int W, int C, int flags, void* stream);
+int dvsg_flow_warp_bwd(const float* im, const float* flow, const float* grad_out,
+                       float* grad_im, float* grad_flow, int B, int H, int W, int C,
+                       void* stream);
+
+/* ---- B1 / N2: spatial_transformer grids -------------------------------------------------
+ * dvsg_st_meshgrid replaces _meshgrid (spatial_transformer.py:460-482): grid [3*oh*ow].
+ * dvsg_homography_warp_fwd fuses ProjectiveTransformer._transform (:423-452, theta [B,8],
+ * div_no_nan) or AffineTransformer._transform (:73-91, theta [B,6]) with bilinear_interp;
+ * `projective` selects which.  x_out / y_out optional.                                  */
+int dvsg_st_meshgrid(float* grid, int oh, int ow, void* stream);
+int dvsg_homography_warp_fwd(const float* im, const float* theta, int projective, float* out,
+                             float* x_out, float* y_out, int B, int H, int W, int C,
+                             int oh, int ow, void* stream);
+
+/* ---- host-buffer pipeline (end-to-end path: H2D, solve, warp, D2H) ----------------------
+ * The call a host-side user of ThinPlateSpline(U, coord, vector, out_size) makes when the
+ * frames live in host memory (eval.py:106-110 feeds numpy through feed_dict every frame).
+ * Frames are cut into chunks that move through `n_slots` device staging slots on separate
+ * streams so that H2D, kernels and D2H overlap.  Host buffers should be pinned.        */
+typedef struct dvsg_host_pipeline dvsg_host_pipeline;
+int  dvsg_host_pipeline_create(dvsg_host_pipeline** out, int device, int H, int W, int C,
+                               int pn, int frames_per_chunk, int n_slots);
+void dvsg_host_pipeline_destroy(dvsg_host_pipeline* p);
+/* U_host [B,H,W,C], coord_host [pn,2] (shared mesh) , vector_host [B,pn,2],
+ * out_host [B,H,W,C]; blocks until out_host is complete.                               */
+int  dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, const float* coord_host,
+                        const float* vector_host, float* out_host, int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVSG_WARP_H_ */

@@ -1,0 +1,311 @@
+"""GPU parity tests, forward path -- every call goes through the C ABI (ctypes) via the
+drop-in modules.  Oracle = oracle/dvsg_oracle.py; golden vectors = unmodified reference
+sources run over the TF1 shim (tests/golden/make_golden.py).
+
+Stated tolerances (fp32):
+  * integer sample corners, bilinear weights and the blend: BIT-EXACT given identical x, y
+    (the kernel's own x, y output is fed to the oracle's sampler stage);
+  * TPS sampling coordinates x, y (normalised): max-abs <= 2e-5 for meshes up to 5x5 --
+    the reference's own fp32 inverse-then-multiply carries ~3e-6 of noise (fp64 run of the
+    same graph, tests/golden/*.npz x64), MUFU.LG2 adds ~1e-6;
+  * warped pixels: max-abs <= 1e-4 on band-limited [0,1] frames.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import smooth_flow, smooth_image, tiled_mesh
+from oracle import dvsg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+FORCE_DIRECT = 1
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def run_tps(u, coord, second, out_size, variant=1, flags=0, want_mask=False):
+    """Through ops (so the staged/direct kernel can be selected with flags)."""
+    from coupe.dvsg_b200 import ops
+    U, C_, S = cu(u), cu(coord), cu(second)
+    target = C_ + S if variant == 1 else S
+    T = ops.tps_solve(C_, target)
+    out, x, y, mask = ops.tps_warp_fwd(U, C_, T, tuple(int(v) for v in out_size), want_grid=True, want_mask=want_mask, flags=flags)
+    torch.cuda.synchronize()
+    res = [out.cpu().numpy(), x.cpu().numpy(), y.cpu().numpy(), T.cpu().numpy()]
+    if want_mask:
+        res.append(mask.cpu().numpy())
+    return res
+
+
+TPS_GOLDEN = ['tps_4x4', 'tps_5x5', 'tps_4x4_big', 'tps_resize', 'tps2_4x4', 'tps_8x8']
+
+
+@pytest.mark.parametrize('flags', [0, FORCE_DIRECT], ids=['staged', 'direct'])
+@pytest.mark.parametrize('name', TPS_GOLDEN)
+def test_tps_forward_vs_golden(name, flags):
+    g = load_golden(name)
+    out, x, y, T = run_tps(g['u'], g['coord'], g['second'], g['out_size'], int(g['variant']), flags)
+    tol = 1e-4 if name == 'tps_8x8' else 2e-5
+    ex, ey = np.abs(x - g['x']).max(), np.abs(y - g['y']).max()
+    print('%s coord err vs fp32 golden %.2e %.2e, vs fp64 %.2e (golden fp32 vs fp64 %.2e)' %
+          (name, ex, ey, np.abs(x - g['x64']).max(), np.abs(g['x'] - g['x64']).max()))
+    assert ex <= tol and ey <= tol
+    assert np.abs(out - g['out']).max() <= 1e-4
+    # the sampler stage (index, weights, blend) is bit-exact on the kernel's own coordinates
+    oh, ow = (int(v) for v in g['out_size'])
+    ref = O.tps_interpolate(g['u'], x, y, oh, ow).reshape(out.shape)
+    np.testing.assert_array_equal(out, ref)
+
+
+@pytest.mark.parametrize('name', ['tps_4x4', 'tps_5x5', 'tps2_4x4'])
+def test_dropin_signature_matches_reference(name):
+    """ThinPlateSpline(U, coord, vector, out_size) -> (output, x, y), called as model.py:81 does."""
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline as stn
+    from coupe.dvsg_b200.ThinPlateSpline2 import ThinPlateSpline2
+    g = load_golden(name)
+    fn = stn if int(g['variant']) == 1 else ThinPlateSpline2
+    out, x, y = fn(cu(g['u']), cu(g['coord']), cu(g['second']), [int(v) for v in g['out_size']])
+    assert out.shape == g['out'].shape and x.shape == g['x'].shape and y.shape == g['y'].shape
+    assert np.abs(out.cpu().numpy() - g['out']).max() <= 1e-4
+    out2, x2, y2 = fn(cu(g['u']), cu(g['coord']), cu(g['second']), [int(v) for v in g['out_size']], return_grid=False)
+    assert x2 is None and y2 is None
+    np.testing.assert_array_equal(out2.cpu().numpy(), out.cpu().numpy())
+
+
+@pytest.mark.parametrize('n,tol32,tol64', [(4, 2e-5, 2e-6), (5, 2e-5, 2e-6), (8, 2e-3, 5e-6), (16, 0.2, 2e-4)])
+def test_tps_solve_coefficients(n, tol32, tol64):
+    """K1 against the fp32 oracle (the reference's arithmetic: noise grows with cond(W), H4)
+    and against the fp64 run of the same algorithm (what both approximate)."""
+    from coupe.dvsg_b200 import ops
+    rng = np.random.default_rng(n)
+    B = 3
+    coord = tiled_mesh(n, n, B)
+    vec = rng.uniform(-0.1, 0.1, coord.shape).astype(np.float32)
+    target = (coord + vec).astype(np.float32)
+    T = ops.tps_solve(cu(coord), cu(target)).cpu().numpy()
+    T32 = O.tps_solve(coord, target)
+    T64 = O.tps_solve(coord.astype(np.float64), target.astype(np.float64), dtype=np.float64)
+    e32, e64 = np.abs(T - T32).max(), np.abs(T - T64).max()
+    print('mesh %dx%d: |T - fp32 oracle| %.2e, |T - fp64| %.2e, |fp32 oracle - fp64| %.2e' % (n, n, e32, e64, np.abs(T32 - T64).max()))
+    assert e32 <= tol32 and e64 <= tol64
+    # shared-mesh (batch stride 0) path gives the same coefficients
+    Ts = ops.tps_solve(cu(coord[0]).unsqueeze(0).expand(B, -1, -1), cu(target)).cpu().numpy()
+    assert np.abs(Ts - T).max() <= 1e-6
+
+
+def test_tps_identity_and_affine_known_answers():
+    from coupe.dvsg_b200 import ops
+    coord = tiled_mesh(4, 4, 1)
+    T = ops.tps_solve(cu(coord), cu(coord)).cpu().numpy()
+    expect = np.zeros_like(T)
+    expect[0, 0, 1] = expect[0, 1, 2] = 1.0
+    assert np.abs(T - expect).max() < 1e-6
+    a = np.array([[1.1, 0.2], [-0.15, 0.9]], np.float32)
+    off = np.array([0.05, -0.07], np.float32)
+    T = ops.tps_solve(cu(coord), cu(coord @ a.T + off)).cpu().numpy()
+    assert np.abs(T[0, :, 3:]).max() < 1e-6 and np.abs(T[0, :, 0] - off).max() < 1e-6 and np.abs(T[0, :, 1:3] - a).max() < 1e-6
+
+
+@pytest.mark.parametrize('shape', [(2, 288, 512, 3, 4), (2, 288, 512, 3, 5), (1, 37, 53, 3, 4), (2, 40, 64, 1, 3), (1, 33, 48, 18, 4)])
+@pytest.mark.parametrize('flags', [0, FORCE_DIRECT], ids=['staged', 'direct'])
+def test_tps_forward_vs_oracle_seeded(shape, flags):
+    b, h, w, c, m = shape
+    rng = np.random.default_rng(h * 1000 + w + m)
+    u = smooth_image(rng, b, h, w, c)
+    coord = tiled_mesh(m, m, b)
+    vec = rng.uniform(-0.1, 0.1, coord.shape).astype(np.float32)
+    out, x, y, T = run_tps(u, coord, vec, (h, w), 1, flags)
+    r_out, r_x, r_y = O.thin_plate_spline(u, coord, vec, (h, w))
+    ex = max(np.abs(x - r_x).max(), np.abs(y - r_y).max())
+    eo = np.abs(out - r_out).max()
+    xp, yp, x0, x1, y0, y1 = O.tps_sample_indices(x, y, h, w)
+    _, _, rx0, _, ry0, _ = O.tps_sample_indices(r_x, r_y, h, w)
+    flips = float(np.mean((x0 != rx0) | (y0 != ry0)))
+    print('%s coord err %.2e  pixel err %.2e  corner flips vs oracle coords %.4f%%' % (shape, ex, eo, 100 * flips))
+    assert ex <= 2e-5 and eo <= 1e-4
+    np.testing.assert_array_equal(out, O.tps_interpolate(u, x, y, h, w).reshape(out.shape))
+
+
+def test_staged_and_direct_kernels_agree_bitwise_at_720p():
+    """Full-size property: the shared-memory-staged kernel and the direct-gather kernel perform
+    the same arithmetic, so their outputs are identical bit for bit (white-noise frames)."""
+    from coupe.dvsg_b200 import ops
+    torch.manual_seed(0)
+    B, H, W = 4, 720, 1280
+    U = torch.rand((B, H, W, 3), device=DEV)
+    coord = cu(tiled_mesh(4, 4, 1)[0]).unsqueeze(0).expand(B, -1, -1)
+    vec = (torch.rand((B, 16, 2), device=DEV) - 0.5) * 0.2
+    T = ops.tps_solve(coord, coord + vec)
+    a = ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True, want_mask=True)
+    b = ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True, want_mask=True, flags=FORCE_DIRECT)
+    for p, q in zip(a, b):
+        assert torch.equal(p, q)
+    # shard invariance: per-frame results do not depend on what else is in the batch
+    c = ops.tps_warp_fwd(U[2:].contiguous(), coord[2:], T[2:].contiguous(), (H, W), want_grid=False)
+    assert torch.equal(c[0], a[0][2:])
+    # large offsets: footprints that do not fit the staging buffer take the in-kernel fallback
+    vec2 = (torch.rand((B, 16, 2), device=DEV) - 0.5) * 1.6
+    T2 = ops.tps_solve(coord, coord + vec2)
+    a2 = ops.tps_warp_fwd(U, coord, T2, (H, W), want_grid=False)
+    b2 = ops.tps_warp_fwd(U, coord, T2, (H, W), want_grid=False, flags=FORCE_DIRECT)
+    assert torch.equal(a2[0], b2[0])
+
+
+def test_mask_output_equals_warp_of_ones():
+    """N1: mask_out == ThinPlateSpline(ones_like(U), ...) (model.py:82,85), exactly."""
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline, ThinPlateSplineWithMask
+    g = load_golden('tps_mask')
+    U = cu(smooth_image(np.random.default_rng(0), 1, 24, 32, 3))
+    out, mask, x, y = ThinPlateSplineWithMask(U, cu(g['coord']), cu(g['second']), [24, 32])
+    ones_out, _, _ = ThinPlateSpline(torch.ones_like(U), cu(g['coord']), cu(g['second']), [24, 32])
+    assert torch.equal(mask.contiguous(), ones_out)
+    assert np.abs(ones_out.cpu().numpy() - g['out']).max() <= 1e-5
+    plain, _, _ = ThinPlateSpline(U, cu(g['coord']), cu(g['second']), [24, 32])
+    assert torch.equal(out, plain)
+
+
+@pytest.mark.parametrize('name', ['bilinear_c18', 'bilinear_c3'])
+def test_bilinear_interp_vs_golden_bit_exact(name):
+    from coupe.dvsg_b200.spatial_transformer import _interpolate
+    g = load_golden(name)
+    out = _interpolate(cu(g['im']), cu(g['x']), cu(g['y']), [int(v) for v in g['out_size']], 'bilinear')
+    assert tuple(out.shape) == g['out'].shape
+    np.testing.assert_array_equal(out.cpu().numpy(), g['out'])
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 96, 3), (1, 45, 67, 3), (2, 30, 40, 18), (1, 288, 512, 3)])
+def test_bilinear_interp_vs_oracle_bit_exact(shape):
+    from coupe.dvsg_b200.spatial_transformer import bilinear_interp
+    from coupe.dvsg_b200 import _lib, ops
+    b, h, w, c = shape
+    rng = np.random.default_rng(sum(shape))
+    im = rng.random(shape, dtype=np.float32)
+    oh, ow = h, w
+    x = rng.uniform(-1.2, 1.2, b * oh * ow).astype(np.float32)
+    y = rng.uniform(-1.2, 1.2, b * oh * ow).astype(np.float32)
+    # a smooth part so that the staged path sees compact footprints too
+    gx, gy = np.meshgrid(np.linspace(-1, 1, ow), np.linspace(-1, 1, oh))
+    half = b * oh * ow // 2
+    x[:half] = (np.tile(gx.reshape(-1), b)[:half] * 1.05 + 0.01).astype(np.float32)
+    y[:half] = (np.tile(gy.reshape(-1), b)[:half] * 0.95 - 0.02).astype(np.float32)
+    ref = O.bilinear_interp(im, x, y, (oh, ow))
+    out = bilinear_interp(cu(im), cu(x), cu(y), [oh, ow])
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    lib = _lib.load()
+    out2 = torch.empty_like(out)
+    I, X, Y = cu(im), cu(x), cu(y)
+    rc = lib.dvsg_bilinear_fwd(I.data_ptr(), X.data_ptr(), Y.data_ptr(), out2.data_ptr(), b, h, w, c, oh, ow, FORCE_DIRECT, 0)
+    assert rc == 0
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out2.cpu().numpy(), ref)
+    del ops
+
+
+@pytest.mark.parametrize('name', ['flow_small', 'flow_large'])
+def test_tf_warp_vs_golden_bit_exact(name):
+    from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+    g = load_golden(name)
+    h, w = g['im'].shape[1:3]
+    out = tf_warp(cu(g['im']), cu(g['flow']), h, w)
+    np.testing.assert_array_equal(out.cpu().numpy(), g['out'])
+
+
+@pytest.mark.parametrize('shape', [(2, 128, 192, 3), (1, 51, 75, 3), (1, 40, 44, 5)])
+def test_tf_warp_vs_oracle_bit_exact(shape):
+    from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+    b, h, w, c = shape
+    rng = np.random.default_rng(sum(shape))
+    im = rng.random(shape, dtype=np.float32)
+    flow = smooth_flow(rng, b, h, w)
+    flow[0, :3, :3] = [[[-2.0, -2.0]] * 3, [[0.0, 0.0]] * 3, [[w + 1.0, h + 1.0]] * 3]
+    out = tf_warp(cu(im), cu(flow), h, w)
+    np.testing.assert_array_equal(out.cpu().numpy(), O.tf_warp(im, flow, h, w))
+
+
+def test_tf_warp_1080p_properties():
+    """Full-size (cfg4 frame shape) properties: zero flow is the identity, an integer shift moves
+    pixels exactly, staged == direct bitwise."""
+    from coupe.dvsg_b200 import _lib
+    from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+    torch.manual_seed(1)
+    B, H, W = 2, 1080, 1920
+    im = torch.rand((B, H, W, 3), device=DEV)
+    assert torch.equal(tf_warp(im, torch.zeros((B, H, W, 2), device=DEV), H, W), im)
+    flow = torch.zeros((B, H, W, 2), device=DEV)
+    flow[..., 0] = 3.0
+    flow[..., 1] = -2.0
+    out = tf_warp(im, flow, H, W)
+    assert torch.equal(out[:, 2:, :-3], im[:, :-2, 3:])
+    assert out[:, :2].abs().max() == 0 and out[:, :, -3:].abs().max() == 0
+    flow = (torch.rand((B, H, W, 2), device=DEV) - 0.5) * 16
+    a = tf_warp(im, flow, H, W)
+    b = torch.empty_like(a)
+    rc = _lib.load().dvsg_flow_warp_fwd(im.data_ptr(), flow.data_ptr(), b.data_ptr(), B, H, W, 3, FORCE_DIRECT, 0)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+
+def test_st_meshgrid_and_transformers_vs_golden():
+    from coupe.dvsg_b200.spatial_transformer import AffineTransformer, ProjectiveTransformer, _meshgrid
+    g = load_golden('meshgrid')
+    np.testing.assert_array_equal(_meshgrid([int(v) for v in g['out_size']]).cpu().numpy(), g['grid'])
+    np.testing.assert_array_equal(_meshgrid([int(v) for v in g['out_size2']]).cpu().numpy()[::97], g['grid2'])
+    g = load_golden('projective')
+    pt = ProjectiveTransformer([int(v) for v in g['out_size']])
+    out = pt.transform(cu(g['im']), cu(g['theta']))
+    assert np.abs(out.cpu().numpy() - g['out']).max() <= 1e-5
+    np.testing.assert_array_equal(out.cpu().numpy(), O.projective_transform(g['im'], g['theta'], g['out_size']))
+    xs, ys = pt._transform(cu(g['im']), cu(g['theta']))
+    rx, ry = O.projective_grid(g['theta'], g['out_size'])
+    np.testing.assert_array_equal(xs.cpu().numpy(), rx)
+    g = load_golden('affine')
+    out = AffineTransformer([int(v) for v in g['out_size']]).transform(cu(g['im']), cu(g['theta']))
+    assert np.abs(out.cpu().numpy() - g['out']).max() <= 1e-5
+
+
+def test_empty_and_ragged_inputs():
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline
+    from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+    coord = cu(tiled_mesh(4, 4, 1)[0])
+    out, x, y = ThinPlateSpline(torch.zeros((0, 8, 8, 3), device=DEV), coord.unsqueeze(0).expand(0, -1, -1),
+                                torch.zeros((0, 16, 2), device=DEV), [8, 8])
+    assert out.shape == (0, 8, 8, 3) and x.numel() == 0
+    out = tf_warp(torch.zeros((0, 8, 8, 3), device=DEV), torch.zeros((0, 8, 8, 2), device=DEV), 8, 8)
+    assert out.shape == (0, 8, 8, 3)
+    # 1x1 output and 1-pixel-wide frames: linspace degenerates to the single value -1
+    u = torch.rand((1, 5, 1, 3), device=DEV)
+    out, x, y = ThinPlateSpline(u, coord.unsqueeze(0), torch.zeros((1, 16, 2), device=DEV), [1, 1])
+    r_out, r_x, r_y = O.thin_plate_spline(u.cpu().numpy(), coord.cpu().numpy()[None], np.zeros((1, 16, 2), np.float32), (1, 1))
+    assert np.abs(out.cpu().numpy() - r_out).max() <= 1e-5 and abs(float(x[0]) - r_x[0]) <= 1e-5
+
+
+def test_errors_are_loud():
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline
+    from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+    coord = cu(tiled_mesh(4, 4, 2))
+    with pytest.raises(ValueError):
+        ThinPlateSpline(torch.zeros((2, 8, 8, 3), device=DEV), coord, torch.zeros((2, 9, 2), device=DEV), [8, 8])
+    with pytest.raises(ValueError):
+        ThinPlateSpline(torch.zeros((2, 8, 8, 3)), coord, torch.zeros((2, 16, 2), device=DEV), [8, 8])
+    with pytest.raises(ValueError):
+        tf_warp(torch.zeros((1, 8, 8, 3), device=DEV), torch.zeros((1, 8, 8, 2), device=DEV), 4, 4)
+
+
+def test_host_pipeline_matches_device_path():
+    from coupe.dvsg_b200 import ops
+    rng = np.random.default_rng(11)
+    B, H, W = 7, 48, 64
+    u = smooth_image(rng, B, H, W, 3)
+    mesh = tiled_mesh(4, 4, 1)[0]
+    vec = rng.uniform(-0.1, 0.1, (B, 16, 2)).astype(np.float32)
+    pipe = ops.HostPipeline(H, W, 3, 16, frames_per_chunk=2, n_slots=3, device=0)
+    out_h = pipe.thin_plate_spline(torch.from_numpy(u).pin_memory(), torch.from_numpy(mesh), torch.from_numpy(vec))
+    pipe.close()
+    out_d, _, _, _ = run_tps(u, np.tile(mesh[None], (B, 1, 1)), vec, (H, W))
+    np.testing.assert_array_equal(out_h.numpy(), out_d)
