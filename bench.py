@@ -211,7 +211,9 @@ def run_ours(args, wl):
     ev_pairs = []
 
     if kind == 'flow':
-        flow = (torch.rand((B, H, W, 2), device=dev, generator=g) - 0.5) * 16.0
+        lat = (torch.rand((B, 2, 9, 16), device=dev, generator=g) - 0.5) * 16.0
+        flow = torch.nn.functional.interpolate(lat, size=(H, W), mode='bilinear', align_corners=True)
+        flow = (flow + (torch.rand((B, 2, H, W), device=dev, generator=g) - 0.5)).permute(0, 2, 3, 1).contiguous()
         out = torch.empty_like(U)
         stream = torch.cuda.current_stream(dev)
 

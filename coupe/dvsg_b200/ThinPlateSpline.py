@@ -7,6 +7,12 @@ return arity: /root/reference/ThinPlateSpline.py:4,168-170), backed by the sm_10
 from . import ops
 
 
+def _check_mesh(coord, vector):
+    if coord.dim() != 3 or vector.dim() != 3 or coord.shape[2] != 2 or tuple(coord.shape) != tuple(vector.shape):
+        raise ValueError('coord and vector must both have shape [num_batch, num_point, 2], got %s and %s'
+                         % (tuple(coord.shape), tuple(vector.shape)))
+
+
 def ThinPlateSpline(U, coord, vector, out_size, return_grid=True):
     """Thin Plate Spline Spatial Transformer Layer.
 
@@ -28,6 +34,7 @@ def ThinPlateSpline(U, coord, vector, out_size, return_grid=True):
     coord_t = ops._as_mesh(coord, U)
     if coord_t.dim() == 2:
         coord_t = coord_t.unsqueeze(0).expand(U.shape[0], -1, -1)
+    _check_mesh(coord_t, vector)
     target = coord_t + vector          # ThinPlateSpline.py:161 (tiny [B,pn,2] tensor op; keeps autograd to `vector`)
     return ops.thin_plate_spline(U, coord_t, target, out_size, want_grid=return_grid)
 
@@ -42,4 +49,5 @@ def ThinPlateSplineWithMask(U, coord, vector, out_size, return_grid=True):
     coord_t = ops._as_mesh(coord, U)
     if coord_t.dim() == 2:
         coord_t = coord_t.unsqueeze(0).expand(U.shape[0], -1, -1)
+    _check_mesh(coord_t, vector)
     return ops.thin_plate_spline_with_mask(U, coord_t, coord_t + vector, out_size, want_grid=return_grid)

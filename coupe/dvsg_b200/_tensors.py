@@ -17,7 +17,7 @@ def as_cuda_f32(obj, name, like=None):
             raise TypeError('%s: expected a torch.Tensor or a DLPack-capable array, got %s' % (name, type(obj).__name__))
     if not obj.is_cuda:
         raise ValueError('%s: tensor lives on %s -- this path runs on CUDA only (no CPU fallback); move it '
-                         'with .cuda() or use coupe.dvsg_b200.host_pipeline for host buffers' % (name, obj.device))
+                         'with .cuda() or use coupe.dvsg_b200.ops.HostPipeline for host buffers' % (name, obj.device))
     if like is not None and obj.device != like.device:
         raise ValueError('%s: device %s differs from %s' % (name, obj.device, like.device))
     if obj.dtype != torch.float32:

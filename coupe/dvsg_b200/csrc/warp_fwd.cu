@@ -387,11 +387,27 @@ static float lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 static int g_src_smem_bytes = 28 * 1024;   // staging buffer per CTA; tunable for experiments
 static int g_pack = 1;
 
+// fast path (warp_fwd_strip.cu)
+bool strip_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0);
+int strip_tps(const float* U, const float* coord, long long cstride, const float* T, float* out, float* x_out, float* y_out,
+              float* mask_out, int B, int H, int W, int oh, int ow, int pn, cudaStream_t st);
+int strip_given(const float* im, const float* x, const float* y, float* out, int B, int H, int W, int oh, int ow, cudaStream_t st);
+int strip_flow(const float* im, const float* flow, float* out, int B, int H, int W, cudaStream_t st);
+int strip_homog(const float* im, const float* theta, int projective, float* out, float* x_out, float* y_out, int B, int H, int W,
+                int oh, int ow, cudaStream_t st);
+void strip_set_tuning(int smem_bytes, int pack, int target_ctas, int pipe);
+
+constexpr int FLAG_LEGACY_STAGED = 2;   // experiments only: the non-pipelined one-tile-per-CTA staged kernel
+
+static bool use_strip(int flags, const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn) {
+    return !(flags & (DVSG_FLAG_FORCE_DIRECT | FLAG_LEGACY_STAGED)) && strip_path_ok(src, out, H, W, C, oh, ow, pn);
+}
+
 template <int MODE>
 static int launch_fwd(FwdParams p, int flags, cudaStream_t st) {
     if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
     DVSG_REQUIRE(p.B <= 65535, "batch %d exceeds the grid z limit 65535: split the call", p.B);
-    const bool staged = !(flags & DVSG_FLAG_FORCE_DIRECT) && p.C == 3 && p.W % 4 == 0 && p.ow % 4 == 0 &&
+    const bool staged = (flags & FLAG_LEGACY_STAGED) && p.C == 3 && p.W % 4 == 0 && p.ow % 4 == 0 &&
                         aligned16(p.src) && aligned16(p.out);
     p.kc_cap = MODE == MODE_TPS ? (p.pn < KC ? p.pn : KC) : 0;
     p.src_smem_bytes = staged ? g_src_smem_bytes : 0;
@@ -403,7 +419,7 @@ static int launch_fwd(FwdParams p, int flags, cudaStream_t st) {
 #define DVSG_LAUNCH(ST, PK)                                                                                      \
     do {                                                                                                         \
         auto k = warp_fwd_kernel<MODE, ST, PK>;                                                                  \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (smem > 40 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         k<<<grid, NT, smem, st>>>(p);                                                                            \
     } while (0)
     if (staged) { if (pack) DVSG_LAUNCH(true, true); else DVSG_LAUNCH(true, false); }
@@ -420,6 +436,12 @@ using namespace dvsg;
 extern "C" int dvsg_set_tuning(int src_smem_bytes, int pack) {
     if (src_smem_bytes >= 0) g_src_smem_bytes = src_smem_bytes & ~15;
     if (pack >= 0) g_pack = pack;
+    strip_set_tuning(src_smem_bytes, pack, -1, -1);
+    return DVSG_OK;
+}
+
+extern "C" int dvsg_set_strip_tuning(int target_ctas, int pipe) {
+    strip_set_tuning(-1, -1, target_ctas, pipe);
     return DVSG_OK;
 }
 
@@ -431,6 +453,8 @@ extern "C" int dvsg_tps_warp_fwd(const float* U, const float* coord, long long c
     DVSG_REQUIRE((x_out == nullptr) == (y_out == nullptr), "tps_warp_fwd: x_out and y_out must be given together");
     DVSG_REQUIRE(coord_batch_stride == 0 || coord_batch_stride >= 2LL * pn, "tps_warp_fwd: coord stride %lld < 2*pn", coord_batch_stride);
     DVSG_REQUIRE((long long)H * W < (1LL << 31) / C && (long long)oh * ow < (1LL << 31) / C, "tps_warp_fwd: frame too large for int32 indexing");
+    if (use_strip(flags, U, out, H, W, C, oh, ow, pn))
+        return B == 0 ? DVSG_OK : strip_tps(U, coord, coord_batch_stride, T, out, x_out, y_out, mask_out, B, H, W, oh, ow, pn, (cudaStream_t)stream);
     FwdParams p = {};
     p.src = U; p.out = out; p.x_out = x_out; p.y_out = y_out; p.mask_out = mask_out;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow;
@@ -444,6 +468,8 @@ extern "C" int dvsg_bilinear_fwd(const float* im, const float* x, const float* y
     DVSG_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && oh >= 0 && ow >= 0, "bilinear_fwd: bad shape");
     DVSG_REQUIRE(B == 0 || (im && x && y && out), "bilinear_fwd: null pointer");
     DVSG_REQUIRE((long long)(H + 2) * (W + 2) < (1LL << 31) / C, "bilinear_fwd: frame too large for int32 indexing");
+    if (use_strip(flags, im, out, H, W, C, oh, ow, 0))
+        return B == 0 ? DVSG_OK : strip_given(im, x, y, out, B, H, W, oh, ow, (cudaStream_t)stream);
     FwdParams p = {};
     p.src = im; p.out = out; p.x_in = x; p.y_in = y;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow;
@@ -456,6 +482,8 @@ extern "C" int dvsg_flow_warp_fwd(const float* im, const float* flow, float* out
     DVSG_REQUIRE(B == 0 || (im && flow && out), "flow_warp_fwd: null pointer");
     DVSG_REQUIRE((reinterpret_cast<uintptr_t>(flow) & 7u) == 0, "flow_warp_fwd: flow must be 8-byte aligned");
     DVSG_REQUIRE((long long)(H + 2) * (W + 2) < (1LL << 31) / C, "flow_warp_fwd: frame too large for int32 indexing");
+    if (use_strip(flags, im, out, H, W, C, H, W, 0))
+        return B == 0 ? DVSG_OK : strip_flow(im, flow, out, B, H, W, (cudaStream_t)stream);
     FwdParams p = {};
     p.src = im; p.out = out; p.flow = flow;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = H; p.ow = W;
@@ -468,6 +496,8 @@ extern "C" int dvsg_homography_warp_fwd(const float* im, const float* theta, int
     DVSG_REQUIRE(B == 0 || (im && theta && out), "homography_warp_fwd: null pointer");
     DVSG_REQUIRE((x_out == nullptr) == (y_out == nullptr), "homography_warp_fwd: x_out and y_out must be given together");
     DVSG_REQUIRE((long long)(H + 2) * (W + 2) < (1LL << 31) / C, "homography_warp_fwd: frame too large for int32 indexing");
+    if (use_strip(0, im, out, H, W, C, oh, ow, 0))
+        return B == 0 ? DVSG_OK : strip_homog(im, theta, projective, out, x_out, y_out, B, H, W, oh, ow, (cudaStream_t)stream);
     FwdParams p = {};
     p.src = im; p.out = out; p.x_out = x_out; p.y_out = y_out; p.theta = theta; p.projective = projective;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow;

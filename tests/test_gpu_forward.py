@@ -45,7 +45,7 @@ def run_tps(u, coord, second, out_size, variant=1, flags=0, want_mask=False):
 TPS_GOLDEN = ['tps_4x4', 'tps_5x5', 'tps_4x4_big', 'tps_resize', 'tps2_4x4', 'tps_8x8']
 
 
-@pytest.mark.parametrize('flags', [0, FORCE_DIRECT], ids=['staged', 'direct'])
+@pytest.mark.parametrize('flags', [0, FORCE_DIRECT], ids=['strip', 'direct'])
 @pytest.mark.parametrize('name', TPS_GOLDEN)
 def test_tps_forward_vs_golden(name, flags):
     g = load_golden(name)
@@ -77,10 +77,15 @@ def test_dropin_signature_matches_reference(name):
     np.testing.assert_array_equal(out2.cpu().numpy(), out.cpu().numpy())
 
 
-@pytest.mark.parametrize('n,tol32,tol64', [(4, 2e-5, 2e-6), (5, 2e-5, 2e-6), (8, 2e-3, 5e-6), (16, 0.2, 2e-4)])
+@pytest.mark.parametrize('n,tol32,tol64', [(4, 5e-6, 5e-6), (5, 5e-6, 1e-5), (8, 1e-4, 2e-4), (16, 2e-3, 1e-2)])
 def test_tps_solve_coefficients(n, tol32, tol64):
-    """K1 against the fp32 oracle (the reference's arithmetic: noise grows with cond(W), H4)
-    and against the fp64 run of the same algorithm (what both approximate)."""
+    """K1 against the fp32 oracle (the reference's arithmetic) and against the fp64 run of the
+    same algorithm.  The kernel forms the matrix entries in fp32 exactly like the reference, so it
+    solves the reference's system; the distance of BOTH fp32 results to the fp64 run is set by
+    the fp32 rounding of the entries times cond(W) (2e-2 .. 4e4 from 4x4 to 16x16),
+    which is why the stated tolerance grows with the mesh.  Measured on B200 (|T-fp32 oracle|,
+    |T-fp64|, |fp32 oracle-fp64|): 4x4 2.6e-7/2.6e-7/3.0e-7, 5x5 3.1e-7/1.2e-6/1.1e-6,
+    8x8 5.7e-6/2.2e-5/1.7e-5, 16x16 2.5e-4/1.5e-3/1.5e-3."""
     from coupe.dvsg_b200 import ops
     rng = np.random.default_rng(n)
     B = 3
@@ -112,7 +117,7 @@ def test_tps_identity_and_affine_known_answers():
 
 
 @pytest.mark.parametrize('shape', [(2, 288, 512, 3, 4), (2, 288, 512, 3, 5), (1, 37, 53, 3, 4), (2, 40, 64, 1, 3), (1, 33, 48, 18, 4)])
-@pytest.mark.parametrize('flags', [0, FORCE_DIRECT], ids=['staged', 'direct'])
+@pytest.mark.parametrize('flags', [0, FORCE_DIRECT], ids=['strip', 'direct'])
 def test_tps_forward_vs_oracle_seeded(shape, flags):
     b, h, w, c, m = shape
     rng = np.random.default_rng(h * 1000 + w + m)
@@ -126,8 +131,16 @@ def test_tps_forward_vs_oracle_seeded(shape, flags):
     xp, yp, x0, x1, y0, y1 = O.tps_sample_indices(x, y, h, w)
     _, _, rx0, _, ry0, _ = O.tps_sample_indices(r_x, r_y, h, w)
     flips = float(np.mean((x0 != rx0) | (y0 != ry0)))
-    print('%s coord err %.2e  pixel err %.2e  corner flips vs oracle coords %.4f%%' % (shape, ex, eo, 100 * flips))
-    assert ex <= 2e-5 and eo <= 1e-4
+    # The reference sampler is DISCONTINUOUS at the edge of its support: crossing x_pix = W-1 (or 0)
+    # switches from "interpolate pixels W-2, W-1" to "clamped corners whose weights cancel" (~0).
+    # A pixel whose coordinate differs by one fp32 ulp can land on either side, so pixels whose
+    # integer corner differs between the two coordinate sets are excluded from the value tolerance
+    # (they are still covered by the bit-exact sampler check below, on the kernel's own x, y).
+    same = ((x0 == rx0) & (y0 == ry0)).reshape(b, h, w)
+    eo_same = np.abs(out - r_out)[same].max()
+    print('%s coord err %.2e  pixel err %.2e (all) %.2e (same corners)  corner flips vs oracle coords %.4f%%' %
+          (shape, ex, eo, eo_same, 100 * flips))
+    assert ex <= 2e-5 and eo_same <= 1e-4 and flips <= 5e-3
     np.testing.assert_array_equal(out, O.tps_interpolate(u, x, y, h, w).reshape(out.shape))
 
 
@@ -295,6 +308,8 @@ def test_errors_are_loud():
         ThinPlateSpline(torch.zeros((2, 8, 8, 3)), coord, torch.zeros((2, 16, 2), device=DEV), [8, 8])
     with pytest.raises(ValueError):
         tf_warp(torch.zeros((1, 8, 8, 3), device=DEV), torch.zeros((1, 8, 8, 2), device=DEV), 4, 4)
+    with pytest.raises(ValueError):
+        tf_warp(torch.zeros((1, 8, 8, 3), device=DEV), torch.zeros((1, 8, 9, 2), device=DEV), 8, 8)
 
 
 def test_host_pipeline_matches_device_path():
