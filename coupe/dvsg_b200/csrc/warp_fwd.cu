@@ -397,10 +397,25 @@ int strip_homog(const float* im, const float* theta, int projective, float* out,
                 int oh, int ow, cudaStream_t st);
 void strip_set_tuning(int smem_bytes, int pack, int target_ctas, int pipe);
 
+// fast path (warp_fwd_tile.cu): warp-autonomous 32x8 tiles
+bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0);
+int tile_tps(const float* U, const float* coord, long long cstride, const float* T, float* out, float* x_out, float* y_out,
+             float* mask_out, int B, int H, int W, int oh, int ow, int pn, cudaStream_t st);
+int tile_given(const float* im, const float* x, const float* y, float* out, int B, int H, int W, int oh, int ow, cudaStream_t st);
+int tile_flow(const float* im, const float* flow, float* out, int B, int H, int W, cudaStream_t st);
+int tile_homog(const float* im, const float* theta, int projective, float* out, float* x_out, float* y_out, int B, int H, int W,
+               int oh, int ow, cudaStream_t st);
+void tile_set_tuning(int stage_bytes, int target_ctas);
+
 constexpr int FLAG_LEGACY_STAGED = 2;   // experiments only: the non-pipelined one-tile-per-CTA staged kernel
+constexpr int FLAG_STRIP = 4;           // experiments only: the CTA-synchronous strip kernel (warp_fwd_strip.cu)
+
+static bool use_tile(int flags, const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn) {
+    return !(flags & (DVSG_FLAG_FORCE_DIRECT | FLAG_LEGACY_STAGED | FLAG_STRIP)) && tile_path_ok(src, out, H, W, C, oh, ow, pn);
+}
 
 static bool use_strip(int flags, const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn) {
-    return !(flags & (DVSG_FLAG_FORCE_DIRECT | FLAG_LEGACY_STAGED)) && strip_path_ok(src, out, H, W, C, oh, ow, pn);
+    return (flags & FLAG_STRIP) && strip_path_ok(src, out, H, W, C, oh, ow, pn);
 }
 
 template <int MODE>
@@ -440,6 +455,11 @@ extern "C" int dvsg_set_tuning(int src_smem_bytes, int pack) {
     return DVSG_OK;
 }
 
+extern "C" int dvsg_set_tile_tuning(int stage_bytes, int target_ctas) {
+    tile_set_tuning(stage_bytes, target_ctas);
+    return DVSG_OK;
+}
+
 extern "C" int dvsg_set_strip_tuning(int target_ctas, int pipe) {
     strip_set_tuning(-1, -1, target_ctas, pipe);
     return DVSG_OK;
@@ -453,6 +473,8 @@ extern "C" int dvsg_tps_warp_fwd(const float* U, const float* coord, long long c
     DVSG_REQUIRE((x_out == nullptr) == (y_out == nullptr), "tps_warp_fwd: x_out and y_out must be given together");
     DVSG_REQUIRE(coord_batch_stride == 0 || coord_batch_stride >= 2LL * pn, "tps_warp_fwd: coord stride %lld < 2*pn", coord_batch_stride);
     DVSG_REQUIRE((long long)H * W < (1LL << 31) / C && (long long)oh * ow < (1LL << 31) / C, "tps_warp_fwd: frame too large for int32 indexing");
+    if (use_tile(flags, U, out, H, W, C, oh, ow, pn))
+        return B == 0 ? DVSG_OK : tile_tps(U, coord, coord_batch_stride, T, out, x_out, y_out, mask_out, B, H, W, oh, ow, pn, (cudaStream_t)stream);
     if (use_strip(flags, U, out, H, W, C, oh, ow, pn))
         return B == 0 ? DVSG_OK : strip_tps(U, coord, coord_batch_stride, T, out, x_out, y_out, mask_out, B, H, W, oh, ow, pn, (cudaStream_t)stream);
     FwdParams p = {};
@@ -468,6 +490,8 @@ extern "C" int dvsg_bilinear_fwd(const float* im, const float* x, const float* y
     DVSG_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && oh >= 0 && ow >= 0, "bilinear_fwd: bad shape");
     DVSG_REQUIRE(B == 0 || (im && x && y && out), "bilinear_fwd: null pointer");
     DVSG_REQUIRE((long long)(H + 2) * (W + 2) < (1LL << 31) / C, "bilinear_fwd: frame too large for int32 indexing");
+    if (use_tile(flags, im, out, H, W, C, oh, ow, 0))
+        return B == 0 ? DVSG_OK : tile_given(im, x, y, out, B, H, W, oh, ow, (cudaStream_t)stream);
     if (use_strip(flags, im, out, H, W, C, oh, ow, 0))
         return B == 0 ? DVSG_OK : strip_given(im, x, y, out, B, H, W, oh, ow, (cudaStream_t)stream);
     FwdParams p = {};
@@ -482,6 +506,8 @@ extern "C" int dvsg_flow_warp_fwd(const float* im, const float* flow, float* out
     DVSG_REQUIRE(B == 0 || (im && flow && out), "flow_warp_fwd: null pointer");
     DVSG_REQUIRE((reinterpret_cast<uintptr_t>(flow) & 7u) == 0, "flow_warp_fwd: flow must be 8-byte aligned");
     DVSG_REQUIRE((long long)(H + 2) * (W + 2) < (1LL << 31) / C, "flow_warp_fwd: frame too large for int32 indexing");
+    if (use_tile(flags, im, out, H, W, C, H, W, 0))
+        return B == 0 ? DVSG_OK : tile_flow(im, flow, out, B, H, W, (cudaStream_t)stream);
     if (use_strip(flags, im, out, H, W, C, H, W, 0))
         return B == 0 ? DVSG_OK : strip_flow(im, flow, out, B, H, W, (cudaStream_t)stream);
     FwdParams p = {};
@@ -496,7 +522,9 @@ extern "C" int dvsg_homography_warp_fwd(const float* im, const float* theta, int
     DVSG_REQUIRE(B == 0 || (im && theta && out), "homography_warp_fwd: null pointer");
     DVSG_REQUIRE((x_out == nullptr) == (y_out == nullptr), "homography_warp_fwd: x_out and y_out must be given together");
     DVSG_REQUIRE((long long)(H + 2) * (W + 2) < (1LL << 31) / C, "homography_warp_fwd: frame too large for int32 indexing");
-    if (use_strip(0, im, out, H, W, C, oh, ow, 0))
+    if (use_tile(0, im, out, H, W, C, oh, ow, 0))
+        return B == 0 ? DVSG_OK : tile_homog(im, theta, projective, out, x_out, y_out, B, H, W, oh, ow, (cudaStream_t)stream);
+    if (false)
         return B == 0 ? DVSG_OK : strip_homog(im, theta, projective, out, x_out, y_out, B, H, W, oh, ow, (cudaStream_t)stream);
     FwdParams p = {};
     p.src = im; p.out = out; p.x_out = x_out; p.y_out = y_out; p.theta = theta; p.projective = projective;

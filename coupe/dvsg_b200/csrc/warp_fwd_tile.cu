@@ -1,0 +1,502 @@
+// warp_fwd_tile.cu -- the sm_100a fast path of the forward warp (C == 3, 16-B aligned rows).
+//
+// Every WARP is an autonomous pipeline over 32x8-pixel output tiles (lane = column, 8 rows per
+// thread); the four warps of a CTA share only the per-strip TPS tables and never meet at a
+// CTA barrier after the prologue, so warps drift apart and the SM always has some warps in
+// the arithmetic phase while others wait for their source rows:
+//
+//   A  coordinates   TPS basis in packed fp32x2 (FADD2 / FMUL2 / FFMA2), one MUFU.LG2 per
+//                    (pixel, control point), table records of 64 B per control point read
+//                    as shared-memory broadcasts; or flow / given x,y / homography
+//   F  footprint     NaN-propagating FMNMX3 bounding box of the tile's sampling coordinates,
+//                    4 warp REDUX, no shared atomics
+//   L  staging       the footprint's rows -> the warp's private staging buffer with 1-D bulk
+//                    async copies (cp.async.bulk / UBLKCP), completion on the warp's mbarrier
+//   G  gather+blend  four corners from shared memory; weights and add_n in the reference's
+//                    op order with separately rounded products and sums (bit-exact sampler)
+//   S  store         output tile staged in shared memory, written with bulk async stores
+//
+// Three gather variants, chosen per tile (warp-uniform):
+//   interior  every corner of every pixel lies strictly inside the frame: no clamps, corners
+//             are a00, a00+12, a00+pitch, a00+pitch+12; floor and the address arithmetic run
+//             on the FMA/ALU pipes (2^23 magic constants) so the XU pipe only sees the logs
+//   general   staged, full clamp / zero-pad semantics (frame-border tiles)
+//   direct    footprint larger than the staging buffer (or non-finite coordinates): corners
+//             gathered straight from global memory, same arithmetic
+// Nothing but the frames themselves touches HBM: the [B, pn+3, h*w] basis and the sampling
+// grid of the reference never exist (x, y are written only when the caller asks).
+#include "dvsg_common.cuh"
+#include "sampler_math.cuh"
+
+namespace dvsg {
+
+enum { TMODE_TPS = 0, TMODE_GIVEN = 1, TMODE_FLOW = 2, TMODE_HOMOG = 3 };
+
+constexpr int TR = 8;                       // rows per tile = pixels per thread
+constexpr int TC = 32;                      // columns per tile = lanes
+constexpr int TNW = 4;                      // warps per CTA
+constexpr int TNT = TNW * 32;
+constexpr int TKC = 256;                    // control points resident in shared memory
+constexpr int TOUT_BYTES = TR * TC * 12;    // output tile, 3072 B
+constexpr float TLN2 = 0.6931471805599453f;
+constexpr float MAGIC23 = 8388608.0f;       // 2^23: (x + 2^23) - 2^23 = rint(x) for 0 <= x < 2^22
+
+struct TileParams {
+    const float* src;
+    float* out;
+    float* x_out;
+    float* y_out;
+    float* mask_out;
+    int B, H, W, oh, ow;
+    const float* coord;
+    long long coord_stride;
+    const float* T;
+    int pn;
+    float step_x, step_y;
+    const float* x_in;
+    const float* y_in;
+    const float* flow;
+    const float* theta;
+    int projective;
+    int stage_bytes;      // per-warp staging buffer
+    int n_tx, n_ty;       // tiles per strip / strips per frame
+    int segs, seg_len;    // CTAs per strip, tiles per CTA
+};
+
+struct __align__(16) TpsRec {   // one control point, 64 B, read with broadcast LDS.64 / LDS.128
+    float2 npx;   // (-px, -px)
+    float2 pad;
+    float4 cf;    // (cx ln2, cx ln2, cy ln2, cy ln2)
+    float4 dya;   // (y_t(row0 + r) - py)^2, r = 0..3
+    float4 dyb;   // r = 4..7
+};
+
+// ---- small PTX helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float t_lds(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void t_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float min3n(float a, float b, float c) { float r; asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float max3n(float a, float b, float c) { float r; asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float min2n(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float max2n(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float min8n(const float2 (&v)[4]) { return min2n(min3n(v[0].x, v[0].y, v[1].x), min3n(v[1].y, v[2].x, min3n(v[2].y, v[3].x, v[3].y))); }
+__device__ __forceinline__ float max8n(const float2 (&v)[4]) { return max2n(max3n(v[0].x, v[0].y, v[1].x), max3n(v[1].y, v[2].x, max3n(v[2].y, v[3].x, v[3].y))); }
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2dup(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }   // per-lane IEEE a - b
+// ptxas (CUDA 12.9) contracts mul.rn.f32x2 feeding add/fma.rn.f32x2 into one FFMA2 although both carry
+// .rn, which would fuse roundings the reference keeps apart: sums of products use scalar rounded adds.
+__device__ __forceinline__ float2 add2s(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+
+// floor for |x| < 2^22 on the FMA/ALU pipes (F2I / FRND would occupy the XU pipe the logs need)
+__device__ __forceinline__ int floor_small(float x) {
+    const float v = __fadd_rn(x, 12582912.0f);             // 1.5 * 2^23: integer part lands in the mantissa
+    int n = __float_as_int(v) - 0x4B400000;
+    const float nf = __fadd_rn(v, -12582912.0f);
+    return nf > x ? n - 1 : n;
+}
+__device__ __forceinline__ float t_u2f(unsigned v) { return __uint_as_float(0x4B000000u | v) - MAGIC23; }   // v < 2^23, exact
+__device__ __forceinline__ int t_floor_i32(float f) {
+    // floor + the reference's CPU cast semantics (out-of-range / NaN -> INT_MIN)
+    const int v = __float2int_rd(f);
+    return fabsf(f) < 2147483648.0f ? v : (int)0x80000000;
+}
+
+// ---- per-pixel general gather (border tiles and the direct path): full reference semantics --------
+// xp, yp: TPS -> pixel-space coordinate of the A4 sampler; other modes -> clipped+1 coordinate in the
+// zero-padded frame.  STAGED: corners come from the warp's staging buffer (sbase = shared address of
+// frame pixel (0,0) inside it), else from global memory.
+template <int MODE, bool STAGED>
+__device__ __forceinline__ void general_pixel(float xp, float yp, int W, int H, uint32_t sbase, int pitch, const float* __restrict__ srcb,
+                                              float (&o)[3], float& msum) {
+    int x0, x1, y0, y1;
+    float ax0, ax1, ay0, ay1;
+    bool v00 = true, v01 = true, v10 = true, v11 = true;   // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
+    if (MODE == TMODE_TPS) {
+        const int fx = t_floor_i32(xp), fy = t_floor_i32(yp);
+        x0 = min(max(fx, 0), W - 1);
+        x1 = min(max((int)((unsigned)fx + 1u), 0), W - 1);
+        y0 = min(max(fy, 0), H - 1);
+        y1 = min(max((int)((unsigned)fy + 1u), 0), H - 1);
+        ax1 = DVSG_SUB(t_u2f((unsigned)x1), xp); ax0 = DVSG_SUB(xp, t_u2f((unsigned)x0));
+        ay1 = DVSG_SUB(t_u2f((unsigned)y1), yp); ay0 = DVSG_SUB(yp, t_u2f((unsigned)y0));
+    } else {
+        const int qx0 = __float2int_rd(xp), qy0 = __float2int_rd(yp);     // in [0, W+1] / [0, H+1]
+        const int qx1 = min(qx0 + 1, W + 1), qy1 = min(qy0 + 1, H + 1);
+        const float x0f = t_u2f((unsigned)qx0), y0f = t_u2f((unsigned)qy0);
+        ax1 = DVSG_SUB(DVSG_ADD(x0f, 1.0f), xp); ax0 = DVSG_SUB(xp, x0f);
+        ay1 = DVSG_SUB(DVSG_ADD(y0f, 1.0f), yp); ay0 = DVSG_SUB(yp, y0f);
+        const bool vx0 = zp_valid(qx0, W), vx1 = zp_valid(qx1, W), vy0 = zp_valid(qy0, H), vy1 = zp_valid(qy1, H);
+        v00 = vx0 && vy0; v01 = vx1 && vy0; v10 = vx0 && vy1; v11 = vx1 && vy1;
+        x0 = min(max(qx0, 1) - 1, W - 1); x1 = max(min(qx1, W) - 1, 0);   // keep addresses legal
+        y0 = min(max(qy0, 1) - 1, H - 1); y1 = max(min(qy1, H) - 1, 0);
+    }
+    const float w00 = DVSG_MUL(ax1, ay1), w01 = DVSG_MUL(ax0, ay1), w10 = DVSG_MUL(ax1, ay0), w11 = DVSG_MUL(ax0, ay0);
+    if (MODE == TMODE_TPS) msum = DVSG_ADD(DVSG_ADD(DVSG_ADD(w00, w10), w01), w11);   // A4 add_n order
+    float i00[3], i01[3], i10[3], i11[3];
+    if (STAGED) {
+        const uint32_t r0 = sbase + (uint32_t)(y0 * pitch), r1 = sbase + (uint32_t)(y1 * pitch);
+        const uint32_t a00 = r0 + (uint32_t)x0 * 12u, a01 = r0 + (uint32_t)x1 * 12u, a10 = r1 + (uint32_t)x0 * 12u, a11 = r1 + (uint32_t)x1 * 12u;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            i00[ch] = v00 ? t_lds(a00 + 4 * ch) : 0.0f; i01[ch] = v01 ? t_lds(a01 + 4 * ch) : 0.0f;
+            i10[ch] = v10 ? t_lds(a10 + 4 * ch) : 0.0f; i11[ch] = v11 ? t_lds(a11 + 4 * ch) : 0.0f;
+        }
+    } else {
+        const float* a00 = srcb + ((size_t)y0 * W + x0) * 3;
+        const float* a01 = srcb + ((size_t)y0 * W + x1) * 3;
+        const float* a10 = srcb + ((size_t)y1 * W + x0) * 3;
+        const float* a11 = srcb + ((size_t)y1 * W + x1) * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            i00[ch] = v00 ? __ldg(a00 + ch) : 0.0f; i01[ch] = v01 ? __ldg(a01 + ch) : 0.0f;
+            i10[ch] = v10 ? __ldg(a10 + ch) : 0.0f; i11[ch] = v11 ? __ldg(a11 + ch) : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float t00 = DVSG_MUL(w00, i00[ch]), t01 = DVSG_MUL(w01, i01[ch]), t10 = DVSG_MUL(w10, i10[ch]), t11 = DVSG_MUL(w11, i11[ch]);
+        if (MODE == TMODE_TPS) o[ch] = DVSG_ADD(DVSG_ADD(DVSG_ADD(t00, t10), t01), t11);   // ThinPlateSpline.py:89
+        else o[ch] = DVSG_ADD(DVSG_ADD(DVSG_ADD(t00, t01), t10), t11);                       // spatial_transformer.py:562
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long s_mbar[TNW];
+    __shared__ float s_lin[12];
+    __shared__ __align__(16) float s_yt[TR];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.H, W = p.W, oh = p.oh, ow = p.ow;
+    int bid = blockIdx.x;
+    const int seg = bid % p.segs; bid /= p.segs;
+    const int ty = bid % p.n_ty;
+    const int b = bid / p.n_ty;
+    const int row0 = ty * TR;
+    const int t_begin = seg * p.seg_len, t_end = min(t_begin + p.seg_len, p.n_tx);
+
+    unsigned char* w_out = smem + (size_t)warp * (TOUT_BYTES + p.stage_bytes);
+    unsigned char* w_stage = w_out + TOUT_BYTES;
+    const unsigned char* recs = smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes);
+    const uint32_t mbar = smem_u32(&s_mbar[warp]);
+    const uint32_t out_s = smem_u32(w_out), stage_s = smem_u32(w_stage);
+
+    // ---- prologue: mbarriers, per-strip tables (the only CTA barrier of the kernel) ---------------
+    if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    if (tid < TR) s_yt[tid] = lin_coord(min(row0 + tid, oh - 1), p.step_y);
+    if (MODE == TMODE_TPS) {
+        const int N = p.pn + 3;
+        const float* Tb = p.T + (size_t)b * 2 * N;
+        const float* cb = p.coord + (size_t)b * p.coord_stride;
+        if (tid < 6) s_lin[tid] = __ldg(Tb + (tid < 3 ? tid : N + tid - 3));
+        TpsRec* wr = reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes));
+        for (int k = tid; k < p.pn; k += TNT) {
+            const float px = __ldg(cb + 2 * k), py = __ldg(cb + 2 * k + 1);
+            const float cx = __ldg(Tb + 3 + k) * TLN2, cy = __ldg(Tb + N + 3 + k) * TLN2;
+            float d[TR];
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+                const float dy = DVSG_SUB(lin_coord(min(row0 + r, oh - 1), p.step_y), py);
+                d[r] = DVSG_MUL(dy, dy);
+            }
+            TpsRec rec;
+            rec.npx = f2(-px, -px); rec.pad = f2(0.f, 0.f); rec.cf = make_float4(cx, cx, cy, cy);
+            rec.dya = make_float4(d[0], d[1], d[2], d[3]); rec.dyb = make_float4(d[4], d[5], d[6], d[7]);
+            wr[k] = rec;
+        }
+    } else if (MODE == TMODE_HOMOG) {
+        const int nt = p.projective ? 8 : 6;
+        if (tid < 9) s_lin[tid] = tid < nt ? __ldg(p.theta + (size_t)b * nt + tid) : (tid == 8 ? 1.0f : 0.0f);
+    }
+    __syncthreads();
+
+    const float* srcb = p.src + (size_t)b * H * W * 3;
+    const float2 one2 = f2dup(1.0f);
+    unsigned phase = 0;
+    bool out_pending = false;
+
+    for (int t = t_begin + warp; t < t_end; t += TNW) {
+        const int col0 = t * TC;
+        const int col = min(col0 + lane, ow - 1);      // columns / rows past the edge are duplicates of the edge pixel
+        const bool col_ok = col0 + lane < ow;
+
+        // ================= A: coordinates of the thread's 8 pixels =================
+        // XP/YP[j] = rows (2j, 2j+1).  TPS: A4 pixel-space coordinate.  Others: clipped+1 padded-frame coordinate.
+        float2 XP[TR / 2], YP[TR / 2];
+        if (MODE == TMODE_TPS) {
+            const float xt = lin_coord(col, p.step_x);
+            const float bx = fmaf(s_lin[1], xt, s_lin[0]), by = fmaf(s_lin[4], xt, s_lin[3]);
+            const float2 l2 = f2dup(s_lin[2]), l5 = f2dup(s_lin[5]);
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
+                XP[j] = __ffma2_rn(l2, ytp, f2dup(bx));
+                YP[j] = __ffma2_rn(l5, ytp, f2dup(by));
+            }
+            const float2 eps = f2dup(1e-6f);
+            const unsigned char* rp = recs;
+#pragma unroll 4
+            for (int k = 0; k < p.pn; ++k, rp += sizeof(TpsRec)) {
+                const float2 npx = *reinterpret_cast<const float2*>(rp);
+                const float4 cf = *reinterpret_cast<const float4*>(rp + 16);
+                const float4 da = *reinterpret_cast<const float4*>(rp + 32);
+                const float4 db = *reinterpret_cast<const float4*>(rp + 48);
+                // scalar, separately rounded (x_t - px)^2 as in the reference (a packed mul feeding the packed
+                // add below would be contracted into FFMA2 by ptxas); FADD2 takes it as a broadcast operand
+                const float dx = DVSG_ADD(xt, npx.x);
+                const float2 dxx = f2dup(DVSG_MUL(dx, dx));
+                const float2 cfx = f2(cf.x, cf.y), cfy = f2(cf.z, cf.w);
+                const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
+#pragma unroll
+                for (int j = 0; j < TR / 2; ++j) {
+                    const float2 d2 = __fadd2_rn(dxx, dy[j]);
+                    const float2 tt = __fadd2_rn(d2, eps);
+                    const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
+                    XP[j] = __ffma2_rn(cfx, r, XP[j]);
+                    YP[j] = __ffma2_rn(cfy, r, YP[j]);
+                }
+            }
+            if (p.x_out && col_ok) {
+#pragma unroll
+                for (int j = 0; j < TR / 2; ++j) {
+                    const int row = row0 + 2 * j;
+                    const size_t i = ((size_t)b * oh + row) * ow + col;
+                    if (row < oh) { p.x_out[i] = XP[j].x; p.y_out[i] = YP[j].x; }
+                    if (row + 1 < oh) { p.x_out[i + ow] = XP[j].y; p.y_out[i + ow] = YP[j].y; }
+                }
+            }
+            // x_pix = ((x + 1) * W) / 2   (ThinPlateSpline.py:48-49), separately rounded
+            const float2 wf = f2dup((float)W), hf = f2dup((float)H), half2 = f2dup(0.5f);
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                XP[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(XP[j], one2), wf), half2);
+                YP[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(YP[j], one2), hf), half2);
+            }
+        } else {
+            float xs[TR], ys[TR];
+            if (MODE == TMODE_GIVEN || MODE == TMODE_FLOW) {
+#pragma unroll
+                for (int q = 0; q < TR; ++q) {
+                    const int row = min(row0 + q, oh - 1);
+                    const size_t i = ((size_t)b * oh + row) * ow + col;
+                    if (MODE == TMODE_GIVEN) { xs[q] = __ldg(p.x_in + i); ys[q] = __ldg(p.y_in + i); }
+                    else { const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + i); xs[q] = f.x; ys[q] = f.y; }
+                }
+#pragma unroll
+                for (int q = 0; q < TR; ++q) {
+                    if (MODE == TMODE_GIVEN) { xs[q] = zp_pix_from_norm(xs[q], W); ys[q] = zp_pix_from_norm(ys[q], H); }
+                    else { xs[q] = DVSG_ADD((float)col, xs[q]); ys[q] = DVSG_ADD((float)min(row0 + q, oh - 1), ys[q]); }   // warp_with_optical_flow.py:107-120
+                }
+            } else {
+                const float xt = lin_coord(col, p.step_x);
+#pragma unroll
+                for (int q = 0; q < TR; ++q) {
+                    const float yt = s_yt[q];
+                    // rows of theta @ [x_t; y_t; 1], accumulated k = 0,1,2 (spatial_transformer.py:437)
+                    float xn = DVSG_ADD(DVSG_ADD(DVSG_MUL(s_lin[0], xt), DVSG_MUL(s_lin[1], yt)), s_lin[2]);
+                    float yn = DVSG_ADD(DVSG_ADD(DVSG_MUL(s_lin[3], xt), DVSG_MUL(s_lin[4], yt)), s_lin[5]);
+                    if (p.projective) {
+                        const float zn = DVSG_ADD(DVSG_ADD(DVSG_MUL(s_lin[6], xt), DVSG_MUL(s_lin[7], yt)), s_lin[8]);
+                        xn = zn != 0.0f ? DVSG_DIV(xn, zn) : 0.0f;   // tf.div_no_nan, :446-447
+                        yn = zn != 0.0f ? DVSG_DIV(yn, zn) : 0.0f;
+                    }
+                    const int row = row0 + q;
+                    if (p.x_out && col_ok && row < oh) {
+                        const size_t i = ((size_t)b * oh + row) * ow + col;
+                        p.x_out[i] = xn; p.y_out[i] = yn;
+                    }
+                    xs[q] = zp_pix_from_norm(xn, W); ys[q] = zp_pix_from_norm(yn, H);
+                }
+            }
+            // clip to [-1, W] and shift into the zero-padded frame (spatial_transformer.py:517-521)
+            const float wf = (float)W, hf = (float)H;
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                XP[j] = f2(DVSG_ADD(fminf(fmaxf(xs[2 * j], -1.0f), wf), 1.0f), DVSG_ADD(fminf(fmaxf(xs[2 * j + 1], -1.0f), wf), 1.0f));
+                YP[j] = f2(DVSG_ADD(fminf(fmaxf(ys[2 * j], -1.0f), hf), 1.0f), DVSG_ADD(fminf(fmaxf(ys[2 * j + 1], -1.0f), hf), 1.0f));
+            }
+        }
+
+        // ================= F: footprint of the tile (warp-uniform after the REDUX) =================
+        const float xmn = min8n(XP), xmx = max8n(XP), ymn = min8n(YP), ymx = max8n(YP);
+        // finite and small enough for floor_small(); NaN fails every comparison
+        const bool sane = xmn > -4.0e6f && xmx < 4.0e6f && ymn > -4.0e6f && ymx < 4.0e6f;
+        int x_lo = sane ? floor_small(xmn) : -(1 << 30), x_hi = sane ? floor_small(xmx) + 1 : (1 << 30);
+        int y_lo = sane ? floor_small(ymn) : -(1 << 30), y_hi = sane ? floor_small(ymx) + 1 : (1 << 30);
+        x_lo = __reduce_min_sync(0xffffffffu, x_lo); x_hi = __reduce_max_sync(0xffffffffu, x_hi);
+        y_lo = __reduce_min_sync(0xffffffffu, y_lo); y_hi = __reduce_max_sync(0xffffffffu, y_hi);
+        bool interior;
+        int fx_lo, fx_hi, fy_lo, fy_hi;    // real source pixels the tile can touch (inclusive)
+        if (MODE == TMODE_TPS) {
+            interior = x_lo >= 0 && x_hi <= W - 1 && y_lo >= 0 && y_hi <= H - 1;
+            fx_lo = min(max(x_lo, 0), W - 1); fx_hi = min(max(x_hi, 0), W - 1);
+            fy_lo = min(max(y_lo, 0), H - 1); fy_hi = min(max(y_hi, 0), H - 1);
+        } else {
+            // padded-frame corners x0 in [x_lo, x_hi-1], x1 <= x_hi; valid iff 1 <= idx <= W; real pixel = idx - 1
+            interior = x_lo >= 1 && x_hi <= W && y_lo >= 1 && y_hi <= H;
+            fx_lo = max(x_lo, 1) - 1; fx_hi = min(x_hi, W) - 1;
+            fy_lo = max(y_lo, 1) - 1; fy_hi = min(y_hi, H) - 1;
+        }
+        const bool nonempty = fx_lo <= fx_hi && fy_lo <= fy_hi;
+        const int fx0 = fx_lo & ~3;                                          // 4 px = 48 B keeps rows 16-B aligned
+        const int wpx = min(((fx_hi - fx0 + 1) + 3) & ~3, W - fx0);
+        const int nrows = fy_hi - fy_lo + 1;
+        const int pitch = wpx * 12;
+        const bool staged = nonempty && nrows <= 32 && (long long)pitch * nrows <= (long long)p.stage_bytes;
+        // the interior path forms byte offsets as exact fp32 integers below 2^22
+        interior = interior && staged && (long long)(fy_hi + 1) * pitch + (long long)(fx_hi + 2) * 12 < (1LL << 22);
+
+        // ================= L: stage the footprint =================
+        if (staged) {
+            fence_proxy_async_smem();      // earlier generic reads of the staging buffer vs. the async writes
+            if (lane == 0) mbar_arrive_expect_tx(mbar, (unsigned)(pitch * nrows));
+            __syncwarp();
+            if (lane < nrows) bulk_g2s(stage_s + (unsigned)(lane * pitch), srcb + ((size_t)(fy_lo + lane) * W + fx0) * 3, (unsigned)pitch, mbar);
+        }
+        if (out_pending) {                 // the previous tile's bulk stores must have read the output tile
+            if (lane < TR) bulk_wait_read0();
+            __syncwarp();
+            out_pending = false;
+        }
+        if (staged) { mbar_wait(mbar, phase); phase ^= 1u; }
+
+        // ================= G: gather + blend =================
+        const uint32_t sbase = stage_s - (uint32_t)(fy_lo * pitch + fx0 * 12);   // shared address of frame pixel (0,0)
+        const uint32_t obase = out_s + (uint32_t)lane * 12u;
+        const bool want_mask = MODE == TMODE_TPS && p.mask_out != nullptr;
+        if (interior) {
+            // padded-frame modes address real pixel idx-1: fold the -1 into the base
+            const uint32_t ib = MODE == TMODE_TPS ? sbase : sbase - (uint32_t)(pitch + 12);
+            const float2 pitchf = f2dup((float)pitch), twelve = f2dup(12.0f), m23 = f2dup(MAGIC23);
+            const int ioff = (int)ib - 0x4B000000;
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                const float2 xp = XP[j], yp = YP[j];
+                // floor on the FMA/ALU pipes: rint via the 2^23 constant, minus one where it rounded up
+                const float2 rx = __fadd2_rn(__fadd2_rn(xp, m23), f2dup(-MAGIC23));
+                const float2 ry = __fadd2_rn(__fadd2_rn(yp, m23), f2dup(-MAGIC23));
+                const float2 x0f = f2(rx.x > xp.x ? rx.x - 1.0f : rx.x, rx.y > xp.y ? rx.y - 1.0f : rx.y);
+                const float2 y0f = f2(ry.x > yp.x ? ry.x - 1.0f : ry.x, ry.y > yp.y ? ry.y - 1.0f : ry.y);
+                const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
+                const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
+                const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
+                // byte offset y0*pitch + x0*12 as an exact fp32 integer riding on 2^23
+                const float2 offf = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
+                const uint32_t aa = (uint32_t)(__float_as_int(offf.x) + ioff), ab = (uint32_t)(__float_as_int(offf.y) + ioff);
+                const uint32_t ca = aa + (uint32_t)pitch, cb_ = ab + (uint32_t)pitch;
+                if (want_mask) {
+                    const float2 m = add2s(add2s(add2s(w00, w10), w01), w11);
+                    const int row = row0 + 2 * j;
+                    if (col_ok && row < oh) p.mask_out[((size_t)b * oh + row) * ow + col] = m.x;
+                    if (col_ok && row + 1 < oh) p.mask_out[((size_t)b * oh + row + 1) * ow + col] = m.y;
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float2 i00 = f2(t_lds(aa + 4 * ch), t_lds(ab + 4 * ch)), i01 = f2(t_lds(aa + 12 + 4 * ch), t_lds(ab + 12 + 4 * ch));
+                    const float2 i10 = f2(t_lds(ca + 4 * ch), t_lds(cb_ + 4 * ch)), i11 = f2(t_lds(ca + 12 + 4 * ch), t_lds(cb_ + 12 + 4 * ch));
+                    const float2 t00 = __fmul2_rn(w00, i00), t01 = __fmul2_rn(w01, i01), t10 = __fmul2_rn(w10, i10), t11 = __fmul2_rn(w11, i11);
+                    float2 o;
+                    if (MODE == TMODE_TPS) o = add2s(add2s(add2s(t00, t10), t01), t11);   // ThinPlateSpline.py:89
+                    else o = add2s(add2s(add2s(t00, t01), t10), t11);                       // spatial_transformer.py:562
+                    t_sts(obase + (uint32_t)((2 * j) * TC * 12 + 4 * ch), o.x);
+                    t_sts(obase + (uint32_t)((2 * j + 1) * TC * 12 + 4 * ch), o.y);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < TR; ++q) {
+                const float xp = (q & 1) ? XP[q >> 1].y : XP[q >> 1].x, yp = (q & 1) ? YP[q >> 1].y : YP[q >> 1].x;
+                float o[3], msum = 0.0f;
+                if (staged) general_pixel<MODE, true>(xp, yp, W, H, sbase, pitch, srcb, o, msum);
+                else general_pixel<MODE, false>(xp, yp, W, H, 0u, 0, srcb, o, msum);
+                if (want_mask && col_ok && row0 + q < oh) p.mask_out[((size_t)b * oh + row0 + q) * ow + col] = msum;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) t_sts(obase + (uint32_t)(q * TC * 12 + 4 * ch), o[ch]);
+            }
+        }
+
+        // ================= S: output tile -> global with bulk async stores =================
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int vcols = min(TC, ow - col0);
+        if (lane < TR && row0 + lane < oh) {
+            bulk_s2g(p.out + (((size_t)b * oh + row0 + lane) * ow + col0) * 3, out_s + (uint32_t)(lane * TC * 12), (unsigned)vcols * 12u);
+            bulk_commit();
+        }
+        out_pending = true;
+    }
+    if (out_pending && lane < TR) bulk_wait_read0();   // shared memory must outlive the bulk stores' reads
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
+static int g_tile_stage = 6144;            // per-warp staging bytes
+static int g_tile_target_ctas = 148 * 5 * 12;
+
+bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0) {
+    return C == 3 && W % 4 == 0 && ow % 4 == 0 && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
+           (long long)H * W < (1LL << 28) && pn_or_0 <= TKC;
+}
+
+template <int MODE>
+static int launch_tile(TileParams p, cudaStream_t st) {
+    if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
+    p.stage_bytes = g_tile_stage;
+    p.n_tx = (p.ow + TC - 1) / TC;
+    p.n_ty = (p.oh + TR - 1) / TR;
+    const long long strips = (long long)p.B * p.n_ty;
+    // several CTAs per strip when the launch would otherwise be a few waves only; each warp keeps >= 1 tile
+    int segs = 1;
+    if (strips < g_tile_target_ctas) segs = (int)min((long long)max(p.n_tx / TNW, 1), (g_tile_target_ctas + strips - 1) / strips);
+    p.seg_len = (p.n_tx + segs - 1) / segs;
+    p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
+    const long long ctas = strips * p.segs;
+    DVSG_REQUIRE(ctas < (1LL << 31), "tile kernel: %lld CTAs exceed the grid limit: split the batch", ctas);
+    const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)p.pn * sizeof(TpsRec) : 0);
+    auto k = warp_fwd_tile_kernel<MODE>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(unsigned)ctas, TNT, smem, st>>>(p);
+    count_launch();
+    return check_launch("warp_fwd_tile_kernel");
+}
+
+int tile_tps(const float* U, const float* coord, long long cstride, const float* T, float* out, float* x_out, float* y_out,
+             float* mask_out, int B, int H, int W, int oh, int ow, int pn, cudaStream_t st) {
+    TileParams p = {};
+    p.src = U; p.out = out; p.x_out = x_out; p.y_out = y_out; p.mask_out = mask_out;
+    p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow;
+    p.coord = coord; p.coord_stride = cstride; p.T = T; p.pn = pn;
+    p.step_x = tile_lin_step(ow); p.step_y = tile_lin_step(oh);
+    return launch_tile<TMODE_TPS>(p, st);
+}
+
+int tile_given(const float* im, const float* x, const float* y, float* out, int B, int H, int W, int oh, int ow, cudaStream_t st) {
+    TileParams p = {};
+    p.src = im; p.out = out; p.x_in = x; p.y_in = y;
+    p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow;
+    return launch_tile<TMODE_GIVEN>(p, st);
+}
+
+int tile_flow(const float* im, const float* flow, float* out, int B, int H, int W, cudaStream_t st) {
+    TileParams p = {};
+    p.src = im; p.out = out; p.flow = flow;
+    p.B = B; p.H = H; p.W = W; p.oh = H; p.ow = W;
+    return launch_tile<TMODE_FLOW>(p, st);
+}
+
+int tile_homog(const float* im, const float* theta, int projective, float* out, float* x_out, float* y_out, int B, int H, int W,
+               int oh, int ow, cudaStream_t st) {
+    TileParams p = {};
+    p.src = im; p.out = out; p.x_out = x_out; p.y_out = y_out; p.theta = theta; p.projective = projective;
+    p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow;
+    p.step_x = tile_lin_step(ow); p.step_y = tile_lin_step(oh);
+    return launch_tile<TMODE_HOMOG>(p, st);
+}
+
+void tile_set_tuning(int stage_bytes, int target_ctas) {
+    if (stage_bytes >= 0) g_tile_stage = (stage_bytes + 127) & ~127;
+    if (target_ctas > 0) g_tile_target_ctas = target_ctas;
+}
+
+}  // namespace dvsg

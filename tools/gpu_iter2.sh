@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_forward.py -m gpu -q -x --timeout 300 > gpurun_out/pytest_fwd.log 2>&1
+echo "pytest fwd exit $?"; tail -25 gpurun_out/pytest_fwd.log
+timeout 900 python tools/sweep2.py ${1:-all} > gpurun_out/sweep2.log 2>&1; echo "sweep exit $?"; cat gpurun_out/sweep2.log

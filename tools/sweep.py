@@ -107,4 +107,5 @@ def main():
         print('%-52s %8.3f ms  %8.1f GB/s  %5.1f%%' % (name, ms, gbs, 100 * gbs / 6548.2))
 
 
-main()
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""Times the forward kernel variants with CUDA events (tile kernel vs strip / direct) -- run on the GPU box."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from coupe.dvsg_b200 import _lib, ops
+from tools.sweep import timeit, tps_case, smooth_flow, dev
+
+lib = _lib.load()
+res = []
+
+
+def rec(name, ms, px, bpp):
+    gbs = px * bpp / ms / 1e6
+    res.append((name, ms, gbs))
+    print('%-56s %8.3f ms  %8.1f GB/s  %5.1f%%  %7.1f Gpix/s' % (name, ms, gbs, 100 * gbs / 6548.2, px / ms / 1e6), flush=True)
+
+
+def flow_call(im, flow, out, flags):
+    rc = lib.dvsg_flow_warp_fwd(im.data_ptr(), flow.data_ptr(), out.data_ptr(), im.shape[0], im.shape[1], im.shape[2], 3, flags, 0)
+    assert rc == 0, lib.dvsg_last_error()
+
+
+def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    B, H, W = 64, 720, 1280
+    px = B * H * W
+    if only in ('all', 'tps'):
+        for amp in (0.2, 0.04, 0.0):
+            U, coord, T = tps_case(B, H, W, 4, amp)
+            for stage in (5120, 6144, 8192):
+                lib.dvsg_set_tile_tuning(stage, -1)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
+                rec('tps720 4x4 amp=%.2f tile stage=%d' % (amp, stage), ms, px, 24)
+            lib.dvsg_set_tile_tuning(6144, -1)
+            if amp == 0.2:
+                for tc in (148 * 5 * 4, 148 * 5 * 24):
+                    lib.dvsg_set_tile_tuning(6144, tc)
+                    ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
+                    rec('tps720 4x4 tile target_ctas=%d' % tc, ms, px, 24)
+                lib.dvsg_set_tile_tuning(6144, 148 * 5 * 12)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True))
+                rec('tps720 4x4 tile +xy', ms, px, 32)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, want_mask=True))
+                rec('tps720 4x4 tile +mask', ms, px, 28)
+                lib.dvsg_set_strip_tuning(148 * 12, 0)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, flags=4))
+                rec('tps720 4x4 strip pipe=0 (old)', ms, px, 24)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, flags=1))
+                rec('tps720 4x4 direct (old)', ms, px, 24)
+        U5, c5, T5 = tps_case(B, H, W, 5)
+        ms = timeit(lambda: ops.tps_warp_fwd(U5, c5, T5, (H, W), want_grid=False))
+        rec('tps720 5x5 tile', ms, px, 24)
+        del U, U5
+        U8, c8, T8 = tps_case(64, 1080, 1920, 4)
+        ms = timeit(lambda: ops.tps_warp_fwd(U8, c8, T8, (1080, 1920), want_grid=False))
+        rec('tps1080 4x4 B=64 tile', ms, 64 * 1080 * 1920, 24)
+        del U8
+        Uc, cc, Tc = tps_case(4, 2160, 3840, 16)
+        ms = timeit(lambda: ops.tps_warp_fwd(Uc, cc, Tc, (2160, 3840), want_grid=False), n=5, warm=1)
+        rec('tps4k 16x16 B=4 tile', ms, 4 * 2160 * 3840, 24)
+        del Uc
+        Us, cs, Ts = tps_case(32, 288, 512, 4)
+        ms = timeit(lambda: ops.tps_warp_fwd(Us, cs, Ts, (288, 512), want_grid=True))
+        rec('tps 288x512 B=32 +xy (L2-resident) tile', ms, 32 * 288 * 512, 32)
+        U1, c1, T1 = tps_case(1, 288, 512, 4)
+        ms = timeit(lambda: ops.tps_warp_fwd(U1, c1, T1, (288, 512), want_grid=False))
+        rec('tps 288x512 B=1 tile (latency)', ms, 288 * 512, 24)
+    if only in ('all', 'flow'):
+        im = torch.rand((16, 1080, 1920, 3), device=dev)
+        out = torch.empty_like(im)
+        pxf = 16 * 1080 * 1920
+        for fname, flow in (('smooth', smooth_flow(16, 1080, 1920)), ('random+-8', (torch.rand((16, 1080, 1920, 2), device=dev) - 0.5) * 16),
+                            ('zero', torch.zeros((16, 1080, 1920, 2), device=dev))):
+            for stage in (5120, 6144, 8192):
+                lib.dvsg_set_tile_tuning(stage, -1)
+                ms = timeit(lambda: flow_call(im, flow, out, 0))
+                rec('flow1080 %s tile stage=%d' % (fname, stage), ms, pxf, 32)
+            lib.dvsg_set_tile_tuning(6144, -1)
+            lib.dvsg_set_strip_tuning(148 * 12, 0)
+            for name, flags in (('strip pipe=0 (old)', 4), ('direct (old)', 1)):
+                ms = timeit(lambda: flow_call(im, flow, out, flags))
+                rec('flow1080 %s %s' % (fname, name), ms, pxf, 32)
+        x = torch.rand(pxf, device=dev) * 2 - 1
+        y = torch.rand(pxf, device=dev) * 2 - 1
+        ms = timeit(lambda: ops.bilinear_interp(im, x, y, (1080, 1920)))
+        rec('bilinear1080 random xy tile', ms, pxf, 32)
+        ms = timeit(lambda: out.copy_(im))
+        rec('torch copy 398MB', ms, pxf, 24)
+
+
+main()
