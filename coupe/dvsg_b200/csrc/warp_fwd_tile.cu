@@ -38,6 +38,7 @@ constexpr int TNW = 4;                      // warps per CTA
 constexpr int TNT = TNW * 32;
 constexpr int TKC = 256;                    // control points resident in shared memory
 constexpr int TOUT_BYTES = TR * TC * 12;    // output tile, 3072 B
+constexpr int TSTORES = TOUT_BYTES / 16 / 32; // float4 stores per lane and tile
 constexpr float TLN2 = 0.6931471805599453f;
 constexpr float MAGIC23 = 8388608.0f;       // 2^23: (x + 2^23) - 2^23 = rint(x) for 0 <= x < 2^22
 
@@ -74,6 +75,10 @@ struct __align__(16) TpsRec {   // one control point, 64 B, read with broadcast 
 // ---- small PTX helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float t_lds(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void t_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+// compile-time byte offsets go into the instruction's immediate field instead of an IADD3 per access
+template <int OFF> __device__ __forceinline__ float t_ldsi(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ void t_stsi(uint32_t a, float v) { asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 t_lds128(uint32_t a) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ float min3n(float a, float b, float c) { float r; asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float max3n(float a, float b, float c) { float r; asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float min2n(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
@@ -160,6 +165,44 @@ __device__ __forceinline__ void general_pixel(float xp, float yp, int W, int H, 
     }
 }
 
+// ---- interior gather of one pixel pair (rows 2J, 2J+1 of the thread's column) -----------------------
+// No corner of the tile touches the frame border: corners are a, a+12, a+pitch, a+pitch+12.  floor() and
+// the byte offset y0*pitch + x0*12 are formed on the FMA/ALU pipes with the 2^23 constant (exact: all
+// quantities are integers below 2^22), so the XU pipe only sees the logarithms.
+template <int MODE, int J>
+__device__ __forceinline__ void interior_pair(const float2 xp, const float2 yp, const int pitch, const unsigned char* __restrict__ sb,
+                                              float* __restrict__ ot, float2& msum) {
+    // sb: staging-buffer address of frame pixel (0,0) (padded-frame modes: of padded pixel (0,0)); ot: this lane's
+    // column of the output tile.  Plain loads / stores (not volatile asm) so that the compiler may overlap the
+    // pairs; __restrict__ tells it the staging buffer and the output tile never alias.
+    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23);
+    const float2 rx = __fadd2_rn(__fadd2_rn(xp, m23), f2dup(-MAGIC23));     // rint
+    const float2 ry = __fadd2_rn(__fadd2_rn(yp, m23), f2dup(-MAGIC23));
+    const float2 x0f = f2(rx.x > xp.x ? rx.x - 1.0f : rx.x, rx.y > xp.y ? rx.y - 1.0f : rx.y);   // floor
+    const float2 y0f = f2(ry.x > yp.x ? ry.x - 1.0f : ry.x, ry.y > yp.y ? ry.y - 1.0f : ry.y);
+    const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
+    const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
+    // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
+    const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
+    const float2 offf = __ffma2_rn(y0f, f2dup((float)pitch), __ffma2_rn(x0f, f2dup(12.0f), m23));
+    const float* __restrict__ pa = reinterpret_cast<const float*>(sb + (__float_as_int(offf.x) & 0x7fffff));
+    const float* __restrict__ pb = reinterpret_cast<const float*>(sb + (__float_as_int(offf.y) & 0x7fffff));
+    const float* __restrict__ qa = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pa) + pitch);
+    const float* __restrict__ qb = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pb) + pitch);
+    if (MODE == TMODE_TPS) msum = add2s(add2s(add2s(w00, w10), w01), w11);   // A4 add_n order (mask = warp of ones)
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float2 i00 = f2(pa[ch], pb[ch]), i01 = f2(pa[3 + ch], pb[3 + ch]);
+        const float2 i10 = f2(qa[ch], qb[ch]), i11 = f2(qa[3 + ch], qb[3 + ch]);
+        const float2 t00 = __fmul2_rn(w00, i00), t01 = __fmul2_rn(w01, i01), t10 = __fmul2_rn(w10, i10), t11 = __fmul2_rn(w11, i11);
+        float2 o;
+        if (MODE == TMODE_TPS) o = add2s(add2s(add2s(t00, t10), t01), t11);   // ThinPlateSpline.py:89
+        else o = add2s(add2s(add2s(t00, t01), t10), t11);                       // spatial_transformer.py:562
+        ot[(2 * J) * TC * 3 + ch] = o.x;
+        ot[(2 * J + 1) * TC * 3 + ch] = o.y;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -169,11 +212,8 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, oh = p.oh, ow = p.ow;
-    int bid = blockIdx.x;
-    const int seg = bid % p.segs; bid /= p.segs;
-    const int ty = bid % p.n_ty;
-    const int b = bid / p.n_ty;
-    const int row0 = ty * TR;
+    const int seg = blockIdx.x, b = blockIdx.z;      // grid = (CTAs per strip, strips per frame, frames)
+    const int row0 = blockIdx.y * TR;
     const int t_begin = seg * p.seg_len, t_end = min(t_begin + p.seg_len, p.n_tx);
 
     unsigned char* w_out = smem + (size_t)warp * (TOUT_BYTES + p.stage_bytes);
@@ -213,8 +253,15 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
 
     const float* srcb = p.src + (size_t)b * H * W * 3;
     const float2 one2 = f2dup(1.0f);
+    // store phase: float4 f = i*32 + lane of the [8][384 B] output tile is row f/24, byte column (f%24)*16
+    int st_goff[TSTORES], st_col[TSTORES];
+#pragma unroll
+    for (int i = 0; i < TSTORES; ++i) {
+        const int f = i * 32 + lane, r = f / 24;
+        st_col[i] = (f - r * 24) * 16;
+        st_goff[i] = row0 + r < oh ? r * ow * 12 + st_col[i] : -1;
+    }
     unsigned phase = 0;
-    bool out_pending = false;
 
     for (int t = t_begin + warp; t < t_end; t += TNW) {
         const int col0 = t * TC;
@@ -354,53 +401,27 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             __syncwarp();
             if (lane < nrows) bulk_g2s(stage_s + (unsigned)(lane * pitch), srcb + ((size_t)(fy_lo + lane) * W + fx0) * 3, (unsigned)pitch, mbar);
         }
-        if (out_pending) {                 // the previous tile's bulk stores must have read the output tile
-            if (lane < TR) bulk_wait_read0();
-            __syncwarp();
-            out_pending = false;
-        }
         if (staged) { mbar_wait(mbar, phase); phase ^= 1u; }
 
         // ================= G: gather + blend =================
         const uint32_t sbase = stage_s - (uint32_t)(fy_lo * pitch + fx0 * 12);   // shared address of frame pixel (0,0)
-        const uint32_t obase = out_s + (uint32_t)lane * 12u;
+        const uint32_t obase = out_s + (uint32_t)lane * 12u;   // general / direct paths
         const bool want_mask = MODE == TMODE_TPS && p.mask_out != nullptr;
         if (interior) {
             // padded-frame modes address real pixel idx-1: fold the -1 into the base
-            const uint32_t ib = MODE == TMODE_TPS ? sbase : sbase - (uint32_t)(pitch + 12);
-            const float2 pitchf = f2dup((float)pitch), twelve = f2dup(12.0f), m23 = f2dup(MAGIC23);
-            const int ioff = (int)ib - 0x4B000000;
+            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 12) - (MODE == TMODE_TPS ? 0 : pitch + 12);
+            float* ot = reinterpret_cast<float*>(w_out) + lane * 3;
+            float2 ms[TR / 2];
+            interior_pair<MODE, 0>(XP[0], YP[0], pitch, sb, ot, ms[0]);
+            interior_pair<MODE, 1>(XP[1], YP[1], pitch, sb, ot, ms[1]);
+            interior_pair<MODE, 2>(XP[2], YP[2], pitch, sb, ot, ms[2]);
+            interior_pair<MODE, 3>(XP[3], YP[3], pitch, sb, ot, ms[3]);
+            if (want_mask && col_ok) {
 #pragma unroll
-            for (int j = 0; j < TR / 2; ++j) {
-                const float2 xp = XP[j], yp = YP[j];
-                // floor on the FMA/ALU pipes: rint via the 2^23 constant, minus one where it rounded up
-                const float2 rx = __fadd2_rn(__fadd2_rn(xp, m23), f2dup(-MAGIC23));
-                const float2 ry = __fadd2_rn(__fadd2_rn(yp, m23), f2dup(-MAGIC23));
-                const float2 x0f = f2(rx.x > xp.x ? rx.x - 1.0f : rx.x, rx.y > xp.y ? rx.y - 1.0f : rx.y);
-                const float2 y0f = f2(ry.x > yp.x ? ry.x - 1.0f : ry.x, ry.y > yp.y ? ry.y - 1.0f : ry.y);
-                const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
-                const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
-                const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
-                // byte offset y0*pitch + x0*12 as an exact fp32 integer riding on 2^23
-                const float2 offf = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
-                const uint32_t aa = (uint32_t)(__float_as_int(offf.x) + ioff), ab = (uint32_t)(__float_as_int(offf.y) + ioff);
-                const uint32_t ca = aa + (uint32_t)pitch, cb_ = ab + (uint32_t)pitch;
-                if (want_mask) {
-                    const float2 m = add2s(add2s(add2s(w00, w10), w01), w11);
+                for (int j = 0; j < TR / 2; ++j) {
                     const int row = row0 + 2 * j;
-                    if (col_ok && row < oh) p.mask_out[((size_t)b * oh + row) * ow + col] = m.x;
-                    if (col_ok && row + 1 < oh) p.mask_out[((size_t)b * oh + row + 1) * ow + col] = m.y;
-                }
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float2 i00 = f2(t_lds(aa + 4 * ch), t_lds(ab + 4 * ch)), i01 = f2(t_lds(aa + 12 + 4 * ch), t_lds(ab + 12 + 4 * ch));
-                    const float2 i10 = f2(t_lds(ca + 4 * ch), t_lds(cb_ + 4 * ch)), i11 = f2(t_lds(ca + 12 + 4 * ch), t_lds(cb_ + 12 + 4 * ch));
-                    const float2 t00 = __fmul2_rn(w00, i00), t01 = __fmul2_rn(w01, i01), t10 = __fmul2_rn(w10, i10), t11 = __fmul2_rn(w11, i11);
-                    float2 o;
-                    if (MODE == TMODE_TPS) o = add2s(add2s(add2s(t00, t10), t01), t11);   // ThinPlateSpline.py:89
-                    else o = add2s(add2s(add2s(t00, t01), t10), t11);                       // spatial_transformer.py:562
-                    t_sts(obase + (uint32_t)((2 * j) * TC * 12 + 4 * ch), o.x);
-                    t_sts(obase + (uint32_t)((2 * j + 1) * TC * 12 + 4 * ch), o.y);
+                    if (row < oh) p.mask_out[((size_t)b * oh + row) * ow + col] = ms[j].x;
+                    if (row + 1 < oh) p.mask_out[((size_t)b * oh + row + 1) * ow + col] = ms[j].y;
                 }
             }
         } else {
@@ -416,23 +437,26 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             }
         }
 
-        // ================= S: output tile -> global with bulk async stores =================
-        fence_proxy_async_smem();
+        // ================= S: output tile -> global, 128-bit coalesced stores =================
         __syncwarp();
-        const int vcols = min(TC, ow - col0);
-        if (lane < TR && row0 + lane < oh) {
-            bulk_s2g(p.out + (((size_t)b * oh + row0 + lane) * ow + col0) * 3, out_s + (uint32_t)(lane * TC * 12), (unsigned)vcols * 12u);
-            bulk_commit();
+        {
+            const int vbytes = min(TC, ow - col0) * 12;
+            unsigned char* tile_g = reinterpret_cast<unsigned char*>(p.out + (((size_t)b * oh + row0) * ow + col0) * 3);
+            const float4* ot4 = reinterpret_cast<const float4*>(w_out) + lane;
+#pragma unroll
+            for (int i = 0; i < TSTORES; ++i) {
+                const float4 v = ot4[i * 32];
+                if (st_goff[i] >= 0 && st_col[i] < vbytes) *reinterpret_cast<float4*>(tile_g + (unsigned)st_goff[i]) = v;
+            }
         }
-        out_pending = true;
+        __syncwarp();     // the output tile is rewritten by the next tile's gather
     }
-    if (out_pending && lane < TR) bulk_wait_read0();   // shared memory must outlive the bulk stores' reads
 }
 
 // ---- host side ---------------------------------------------------------------------------------
 static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 static int g_tile_stage = 6144;            // per-warp staging bytes
-static int g_tile_target_ctas = 148 * 5 * 12;
+static int g_tile_target_ctas = 148 * 5 * 4;
 
 bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0) {
     return C == 3 && W % 4 == 0 && ow % 4 == 0 && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
@@ -451,12 +475,11 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     if (strips < g_tile_target_ctas) segs = (int)min((long long)max(p.n_tx / TNW, 1), (g_tile_target_ctas + strips - 1) / strips);
     p.seg_len = (p.n_tx + segs - 1) / segs;
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
-    const long long ctas = strips * p.segs;
-    DVSG_REQUIRE(ctas < (1LL << 31), "tile kernel: %lld CTAs exceed the grid limit: split the batch", ctas);
+    DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
     const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)p.pn * sizeof(TpsRec) : 0);
     auto k = warp_fwd_tile_kernel<MODE>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<(unsigned)ctas, TNT, smem, st>>>(p);
+    k<<<dim3((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B), TNT, smem, st>>>(p);
     count_launch();
     return check_launch("warp_fwd_tile_kernel");
 }
