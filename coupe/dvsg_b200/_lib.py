@@ -40,7 +40,7 @@ TUNING_PROTOTYPES = {
     'dvsg_set_tuning': (c_int, [c_int, c_int]),
     'dvsg_set_bwd_tuning': (c_int, [c_int]),
     'dvsg_set_strip_tuning': (c_int, [c_int, c_int]),
-    'dvsg_set_tile_tuning': (c_int, [c_int, c_int]),
+    'dvsg_set_tile_tuning': (c_int, [c_int, c_int, c_int]),
 }
 
 _lib = None

@@ -405,7 +405,7 @@ int tile_given(const float* im, const float* x, const float* y, float* out, int 
 int tile_flow(const float* im, const float* flow, float* out, int B, int H, int W, cudaStream_t st);
 int tile_homog(const float* im, const float* theta, int projective, float* out, float* x_out, float* y_out, int B, int H, int W,
                int oh, int ow, cudaStream_t st);
-void tile_set_tuning(int stage_bytes, int target_ctas);
+void tile_set_tuning(int stage_bytes, int target_ctas, int minb);
 
 constexpr int FLAG_LEGACY_STAGED = 2;   // experiments only: the non-pipelined one-tile-per-CTA staged kernel
 constexpr int FLAG_STRIP = 4;           // experiments only: the CTA-synchronous strip kernel (warp_fwd_strip.cu)
@@ -455,8 +455,8 @@ extern "C" int dvsg_set_tuning(int src_smem_bytes, int pack) {
     return DVSG_OK;
 }
 
-extern "C" int dvsg_set_tile_tuning(int stage_bytes, int target_ctas) {
-    tile_set_tuning(stage_bytes, target_ctas);
+extern "C" int dvsg_set_tile_tuning(int stage_bytes, int target_ctas, int min_ctas_per_sm) {
+    tile_set_tuning(stage_bytes, target_ctas, min_ctas_per_sm);
     return DVSG_OK;
 }
 

@@ -6,23 +6,26 @@
 // the arithmetic phase while others wait for their source rows:
 //
 //   A  coordinates   TPS basis in packed fp32x2 (FADD2 / FMUL2 / FFMA2), one MUFU.LG2 per
-//                    (pixel, control point), table records of 64 B per control point read
-//                    as shared-memory broadcasts; or flow / given x,y / homography
+//                    (pixel, control point), 64-B table records per control point read as
+//                    shared-memory broadcasts; or flow / given x,y / homography
 //   F  footprint     NaN-propagating FMNMX3 bounding box of the tile's sampling coordinates,
-//                    4 warp REDUX, no shared atomics
-//   L  staging       the footprint's rows -> the warp's private staging buffer with 1-D bulk
-//                    async copies (cp.async.bulk / UBLKCP), completion on the warp's mbarrier
+//                    4 warp REDUX, no shared atomics, no CTA barrier
+//   L  staging       the footprint's rows -> the warp's private staging buffer with 16-byte
+//                    cp.async (LDGSTS), one instruction per row for the whole warp
 //   G  gather+blend  four corners from shared memory; weights and add_n in the reference's
 //                    op order with separately rounded products and sums (bit-exact sampler)
-//   S  store         output tile staged in shared memory, written with bulk async stores
+//   S  store         output tile staged in shared memory, then 128-bit coalesced stores
 //
-// Three gather variants, chosen per tile (warp-uniform):
+// Gather variants, chosen per tile (warp-uniform):
 //   interior  every corner of every pixel lies strictly inside the frame: no clamps, corners
-//             are a00, a00+12, a00+pitch, a00+pitch+12; floor and the address arithmetic run
-//             on the FMA/ALU pipes (2^23 magic constants) so the XU pipe only sees the logs
-//   general   staged, full clamp / zero-pad semantics (frame-border tiles)
-//   direct    footprint larger than the staging buffer (or non-finite coordinates): corners
-//             gathered straight from global memory, same arithmetic
+//             are a, a+12, a+pitch, a+pitch+12; floor (FADD2.RM with the 2^23 constant) and
+//             the address arithmetic run packed on the FMA/ALU pipes, so the XU pipe only
+//             sees the logarithms
+//   clamped   TPS tiles touching the frame border: same scheme plus the integer clamps of
+//             ThinPlateSpline.py:57-60 done on exact fp32 integers
+//   general   per-pixel scalar code with the full reference semantics (zero-padded samplers at
+//             the frame border, non-finite coordinates), staged or, when the footprint does
+//             not fit the staging buffer, straight from global memory
 // Nothing but the frames themselves touches HBM: the [B, pn+3, h*w] basis and the sampling
 // grid of the reference never exist (x, y are written only when the caller asks).
 #include "dvsg_common.cuh"
@@ -32,15 +35,16 @@ namespace dvsg {
 
 enum { TMODE_TPS = 0, TMODE_GIVEN = 1, TMODE_FLOW = 2, TMODE_HOMOG = 3 };
 
-constexpr int TR = 8;                       // rows per tile = pixels per thread
-constexpr int TC = 32;                      // columns per tile = lanes
-constexpr int TNW = 4;                      // warps per CTA
+constexpr int TR = 8;                         // rows per tile = pixels per thread
+constexpr int TC = 32;                        // columns per tile = lanes
+constexpr int TNW = 4;                        // warps per CTA
 constexpr int TNT = TNW * 32;
-constexpr int TKC = 256;                    // control points resident in shared memory
-constexpr int TOUT_BYTES = TR * TC * 12;    // output tile, 3072 B
+constexpr int TKC = 256;                      // control points resident in shared memory
+constexpr int TOUT_BYTES = TR * TC * 12;      // output tile, 3072 B
 constexpr int TSTORES = TOUT_BYTES / 16 / 32; // float4 stores per lane and tile
 constexpr float TLN2 = 0.6931471805599453f;
-constexpr float MAGIC23 = 8388608.0f;       // 2^23: (x + 2^23) - 2^23 = rint(x) for 0 <= x < 2^22
+constexpr float MAGIC23 = 8388608.0f;         // 2^23
+constexpr float MAGIC15 = 12582912.0f;        // 1.5 * 2^23
 
 struct TileParams {
     const float* src;
@@ -64,7 +68,7 @@ struct TileParams {
     int segs, seg_len;    // CTAs per strip, tiles per CTA
 };
 
-struct __align__(16) TpsRec {   // one control point, 64 B, read with broadcast LDS.64 / LDS.128
+struct __align__(16) TpsRec {   // one control point, 64 B, read with broadcast LDS.32 / LDS.128
     float2 npx;   // (-px, -px)
     float2 pad;
     float4 cf;    // (cx ln2, cx ln2, cy ln2, cy ln2)
@@ -72,47 +76,50 @@ struct __align__(16) TpsRec {   // one control point, 64 B, read with broadcast 
     float4 dyb;   // r = 4..7
 };
 
-// ---- small PTX helpers ---------------------------------------------------------------------
+// ---- small helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float t_lds(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void t_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-// compile-time byte offsets go into the instruction's immediate field instead of an IADD3 per access
-template <int OFF> __device__ __forceinline__ float t_ldsi(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF)); return v; }
-template <int OFF> __device__ __forceinline__ void t_stsi(uint32_t a, float v) { asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory"); }
-__device__ __forceinline__ float4 t_lds128(uint32_t a) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ float min3n(float a, float b, float c) { float r; asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float max3n(float a, float b, float c) { float r; asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float min2n(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float max2n(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float min8n(const float2 (&v)[4]) { return min2n(min3n(v[0].x, v[0].y, v[1].x), min3n(v[1].y, v[2].x, min3n(v[2].y, v[3].x, v[3].y))); }
-__device__ __forceinline__ float max8n(const float2 (&v)[4]) { return max2n(max3n(v[0].x, v[0].y, v[1].x), max3n(v[1].y, v[2].x, max3n(v[2].y, v[3].x, v[3].y))); }
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2dup(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float min8n(const float2 (&v)[4]) { return min2n(min3n(v[0].x, v[0].y, v[1].x), min3n(v[1].y, v[2].x, min3n(v[2].y, v[3].x, v[3].y))); }
+__device__ __forceinline__ float max8n(const float2 (&v)[4]) { return max2n(max3n(v[0].x, v[0].y, v[1].x), max3n(v[1].y, v[2].x, max3n(v[2].y, v[3].x, v[3].y))); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }   // per-lane IEEE a - b
 // ptxas (CUDA 12.9) contracts mul.rn.f32x2 feeding add/fma.rn.f32x2 into one FFMA2 although both carry
 // .rn, which would fuse roundings the reference keeps apart: sums of products use scalar rounded adds.
 __device__ __forceinline__ float2 add2s(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-
-// floor for |x| < 2^22 on the FMA/ALU pipes (F2I / FRND would occupy the XU pipe the logs need)
-__device__ __forceinline__ int floor_small(float x) {
-    const float v = __fadd_rn(x, 12582912.0f);             // 1.5 * 2^23: integer part lands in the mantissa
-    int n = __float_as_int(v) - 0x4B400000;
-    const float nf = __fadd_rn(v, -12582912.0f);
-    return nf > x ? n - 1 : n;
+// per-lane add rounded toward -infinity (FADD2.RM): x +rm 2^23 drops the fraction downwards = floor
+__device__ __forceinline__ float2 add2_rm(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rm.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
 }
+__device__ __forceinline__ float2 floor2_pos(float2 x) { return __fadd2_rn(add2_rm(x, f2dup(MAGIC23)), f2dup(-MAGIC23)); }   // 0 <= x < 2^22
+__device__ __forceinline__ float2 floor2_any(float2 x) { return __fadd2_rn(add2_rm(x, f2dup(MAGIC15)), f2dup(-MAGIC15)); }   // |x| < 2^22
+__device__ __forceinline__ int floor_small(float x) { return __float_as_int(__fadd_rd(x, MAGIC15)) - 0x4B400000; }             // |x| < 2^22
 __device__ __forceinline__ float t_u2f(unsigned v) { return __uint_as_float(0x4B000000u | v) - MAGIC23; }   // v < 2^23, exact
 __device__ __forceinline__ int t_floor_i32(float f) {
     // floor + the reference's CPU cast semantics (out-of-range / NaN -> INT_MIN)
     const int v = __float2int_rd(f);
     return fabsf(f) < 2147483648.0f ? v : (int)0x80000000;
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// ---- per-pixel general gather (border tiles and the direct path): full reference semantics --------
+// ---- per-pixel general gather: full reference semantics --------------------------------------------
 // xp, yp: TPS -> pixel-space coordinate of the A4 sampler; other modes -> clipped+1 coordinate in the
 // zero-padded frame.  STAGED: corners come from the warp's staging buffer (sbase = shared address of
 // frame pixel (0,0) inside it), else from global memory.
 template <int MODE, bool STAGED>
-__device__ __forceinline__ void general_pixel(float xp, float yp, int W, int H, uint32_t sbase, int pitch, const float* __restrict__ srcb,
-                                              float (&o)[3], float& msum) {
+__device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, uint32_t sbase, int pitch, const float* __restrict__ srcb,
+                                           uint32_t oaddr, float* mask_ptr) {
     int x0, x1, y0, y1;
     float ax0, ax1, ay0, ay1;
     bool v00 = true, v01 = true, v10 = true, v11 = true;   // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
@@ -136,7 +143,7 @@ __device__ __forceinline__ void general_pixel(float xp, float yp, int W, int H, 
         y0 = min(max(qy0, 1) - 1, H - 1); y1 = max(min(qy1, H) - 1, 0);
     }
     const float w00 = DVSG_MUL(ax1, ay1), w01 = DVSG_MUL(ax0, ay1), w10 = DVSG_MUL(ax1, ay0), w11 = DVSG_MUL(ax0, ay0);
-    if (MODE == TMODE_TPS) msum = DVSG_ADD(DVSG_ADD(DVSG_ADD(w00, w10), w01), w11);   // A4 add_n order
+    if (MODE == TMODE_TPS && mask_ptr) *mask_ptr = DVSG_ADD(DVSG_ADD(DVSG_ADD(w00, w10), w01), w11);   // A4 add_n order
     float i00[3], i01[3], i10[3], i11[3];
     if (STAGED) {
         const uint32_t r0 = sbase + (uint32_t)(y0 * pitch), r1 = sbase + (uint32_t)(y1 * pitch);
@@ -160,40 +167,66 @@ __device__ __forceinline__ void general_pixel(float xp, float yp, int W, int H, 
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float t00 = DVSG_MUL(w00, i00[ch]), t01 = DVSG_MUL(w01, i01[ch]), t10 = DVSG_MUL(w10, i10[ch]), t11 = DVSG_MUL(w11, i11[ch]);
-        if (MODE == TMODE_TPS) o[ch] = DVSG_ADD(DVSG_ADD(DVSG_ADD(t00, t10), t01), t11);   // ThinPlateSpline.py:89
-        else o[ch] = DVSG_ADD(DVSG_ADD(DVSG_ADD(t00, t01), t10), t11);                       // spatial_transformer.py:562
+        float o;
+        if (MODE == TMODE_TPS) o = DVSG_ADD(DVSG_ADD(DVSG_ADD(t00, t10), t01), t11);   // ThinPlateSpline.py:89
+        else o = DVSG_ADD(DVSG_ADD(DVSG_ADD(t00, t01), t10), t11);                       // spatial_transformer.py:562
+        t_sts(oaddr + 4 * ch, o);
     }
 }
 
-// ---- interior gather of one pixel pair (rows 2J, 2J+1 of the thread's column) -----------------------
-// No corner of the tile touches the frame border: corners are a, a+12, a+pitch, a+pitch+12.  floor() and
-// the byte offset y0*pitch + x0*12 are formed on the FMA/ALU pipes with the 2^23 constant (exact: all
-// quantities are integers below 2^22), so the XU pipe only sees the logarithms.
-template <int MODE, int J>
-__device__ __forceinline__ void interior_pair(const float2 xp, const float2 yp, const int pitch, const unsigned char* __restrict__ sb,
-                                              float* __restrict__ ot, float2& msum) {
-    // sb: staging-buffer address of frame pixel (0,0) (padded-frame modes: of padded pixel (0,0)); ot: this lane's
-    // column of the output tile.  Plain loads / stores (not volatile asm) so that the compiler may overlap the
-    // pairs; __restrict__ tells it the staging buffer and the output tile never alias.
-    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23);
-    const float2 rx = __fadd2_rn(__fadd2_rn(xp, m23), f2dup(-MAGIC23));     // rint
-    const float2 ry = __fadd2_rn(__fadd2_rn(yp, m23), f2dup(-MAGIC23));
-    const float2 x0f = f2(rx.x > xp.x ? rx.x - 1.0f : rx.x, rx.y > xp.y ? rx.y - 1.0f : rx.y);   // floor
-    const float2 y0f = f2(ry.x > yp.x ? ry.x - 1.0f : ry.x, ry.y > yp.y ? ry.y - 1.0f : ry.y);
-    const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
-    const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
+// ---- packed gather of one pixel pair (rows 2J, 2J+1 of the thread's column) ------------------------
+// sb: staging-buffer address of frame pixel (0,0) (padded-frame modes: of padded pixel (0,0)); ot: this
+// lane's column of the output tile.  All index quantities are exact fp32 integers below 2^22; floor() is
+// FADD2.RM against 2^23 and the byte offset y*pitch + x*12 rides on the same constant, so the XU pipe
+// (F2I / I2F) is not used at all.  Plain loads / stores (not volatile asm) and __restrict__ so that the
+// compiler may overlap the pairs.
+// CLAMP = false: no corner of the tile touches the frame border (corners a, a+12, a+pitch, a+pitch+12).
+// CLAMP = true : TPS sampler at the frame border, corners clamped first and weights taken FROM the clamped
+//                corners (ThinPlateSpline.py:57-60, 81-88).
+template <int MODE, bool CLAMP, int J>
+__device__ __forceinline__ void gather_pair(const float2 xp, const float2 yp, const int pitch, const unsigned char* __restrict__ sb,
+                                            float* __restrict__ ot, float2& msum, const float wm1, const float hm1) {
+    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
+    float2 x0f, y0f, x1f, y1f;
+    if (!CLAMP) {
+        x0f = floor2_pos(xp); y0f = floor2_pos(yp);
+        x1f = __fadd2_rn(x0f, one2); y1f = __fadd2_rn(y0f, one2);
+    } else {
+        const float2 fx = floor2_any(xp), fy = floor2_any(yp);
+        const float2 gx = __fadd2_rn(fx, one2), gy = __fadd2_rn(fy, one2);
+        x0f = f2(fminf(fmaxf(fx.x, 0.0f), wm1), fminf(fmaxf(fx.y, 0.0f), wm1));
+        x1f = f2(fminf(fmaxf(gx.x, 0.0f), wm1), fminf(fmaxf(gx.y, 0.0f), wm1));
+        y0f = f2(fminf(fmaxf(fy.x, 0.0f), hm1), fminf(fmaxf(fy.y, 0.0f), hm1));
+        y1f = f2(fminf(fmaxf(gy.x, 0.0f), hm1), fminf(fmaxf(gy.y, 0.0f), hm1));
+    }
+    const float2 ax1 = sub2(x1f, xp), ax0 = sub2(xp, x0f), ay1 = sub2(y1f, yp), ay0 = sub2(yp, y0f);
     // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
     const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
-    const float2 offf = __ffma2_rn(y0f, f2dup((float)pitch), __ffma2_rn(x0f, f2dup(12.0f), m23));
-    const float* __restrict__ pa = reinterpret_cast<const float*>(sb + (__float_as_int(offf.x) & 0x7fffff));
-    const float* __restrict__ pb = reinterpret_cast<const float*>(sb + (__float_as_int(offf.y) & 0x7fffff));
-    const float* __restrict__ qa = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pa) + pitch);
-    const float* __restrict__ qb = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pb) + pitch);
     if (MODE == TMODE_TPS) msum = add2s(add2s(add2s(w00, w10), w01), w11);   // A4 add_n order (mask = warp of ones)
+    const float2 tx0 = __ffma2_rn(x0f, twelve, m23);
+    const float2 o00 = __ffma2_rn(y0f, pitchf, tx0);
+    const float* __restrict__ p00a = reinterpret_cast<const float*>(sb + (__float_as_int(o00.x) & 0x7fffff));
+    const float* __restrict__ p00b = reinterpret_cast<const float*>(sb + (__float_as_int(o00.y) & 0x7fffff));
+    const float *__restrict__ p01a, *__restrict__ p01b, *__restrict__ p10a, *__restrict__ p10b, *__restrict__ p11a, *__restrict__ p11b;
+    if (!CLAMP) {
+        p01a = p00a + 3; p01b = p00b + 3;
+        p10a = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p00a) + pitch);
+        p10b = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p00b) + pitch);
+        p11a = p10a + 3; p11b = p10b + 3;
+    } else {
+        const float2 tx1 = __ffma2_rn(x1f, twelve, m23);
+        const float2 o01 = __ffma2_rn(y0f, pitchf, tx1), o10 = __ffma2_rn(y1f, pitchf, tx0), o11 = __ffma2_rn(y1f, pitchf, tx1);
+        p01a = reinterpret_cast<const float*>(sb + (__float_as_int(o01.x) & 0x7fffff));
+        p01b = reinterpret_cast<const float*>(sb + (__float_as_int(o01.y) & 0x7fffff));
+        p10a = reinterpret_cast<const float*>(sb + (__float_as_int(o10.x) & 0x7fffff));
+        p10b = reinterpret_cast<const float*>(sb + (__float_as_int(o10.y) & 0x7fffff));
+        p11a = reinterpret_cast<const float*>(sb + (__float_as_int(o11.x) & 0x7fffff));
+        p11b = reinterpret_cast<const float*>(sb + (__float_as_int(o11.y) & 0x7fffff));
+    }
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const float2 i00 = f2(pa[ch], pb[ch]), i01 = f2(pa[3 + ch], pb[3 + ch]);
-        const float2 i10 = f2(qa[ch], qb[ch]), i11 = f2(qa[3 + ch], qb[3 + ch]);
+        const float2 i00 = f2(p00a[ch], p00b[ch]), i01 = f2(p01a[ch], p01b[ch]);
+        const float2 i10 = f2(p10a[ch], p10b[ch]), i11 = f2(p11a[ch], p11b[ch]);
         const float2 t00 = __fmul2_rn(w00, i00), t01 = __fmul2_rn(w01, i01), t10 = __fmul2_rn(w10, i10), t11 = __fmul2_rn(w11, i11);
         float2 o;
         if (MODE == TMODE_TPS) o = add2s(add2s(add2s(t00, t10), t01), t11);   // ThinPlateSpline.py:89
@@ -203,10 +236,9 @@ __device__ __forceinline__ void interior_pair(const float2 xp, const float2 yp, 
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams p) {
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TileParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long s_mbar[TNW];
     __shared__ float s_lin[12];
     __shared__ __align__(16) float s_yt[TR];
 
@@ -219,11 +251,10 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
     unsigned char* w_out = smem + (size_t)warp * (TOUT_BYTES + p.stage_bytes);
     unsigned char* w_stage = w_out + TOUT_BYTES;
     const unsigned char* recs = smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes);
-    const uint32_t mbar = smem_u32(&s_mbar[warp]);
     const uint32_t out_s = smem_u32(w_out), stage_s = smem_u32(w_stage);
+    const int pn4 = (p.pn + 3) & ~3;                 // table padded with zero-weight records to a multiple of 4
 
-    // ---- prologue: mbarriers, per-strip tables (the only CTA barrier of the kernel) ---------------
-    if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    // ---- prologue: per-strip tables (the only CTA barrier of the kernel) --------------------------
     if (tid < TR) s_yt[tid] = lin_coord(min(row0 + tid, oh - 1), p.step_y);
     if (MODE == TMODE_TPS) {
         const int N = p.pn + 3;
@@ -231,14 +262,15 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
         const float* cb = p.coord + (size_t)b * p.coord_stride;
         if (tid < 6) s_lin[tid] = __ldg(Tb + (tid < 3 ? tid : N + tid - 3));
         TpsRec* wr = reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes));
-        for (int k = tid; k < p.pn; k += TNT) {
-            const float px = __ldg(cb + 2 * k), py = __ldg(cb + 2 * k + 1);
-            const float cx = __ldg(Tb + 3 + k) * TLN2, cy = __ldg(Tb + N + 3 + k) * TLN2;
+        for (int k = tid; k < pn4; k += TNT) {
+            const bool real = k < p.pn;
+            const float px = real ? __ldg(cb + 2 * k) : 0.0f, py = real ? __ldg(cb + 2 * k + 1) : 0.0f;
+            const float cx = real ? __ldg(Tb + 3 + k) * TLN2 : 0.0f, cy = real ? __ldg(Tb + N + 3 + k) * TLN2 : 0.0f;
             float d[TR];
 #pragma unroll
             for (int r = 0; r < TR; ++r) {
                 const float dy = DVSG_SUB(lin_coord(min(row0 + r, oh - 1), p.step_y), py);
-                d[r] = DVSG_MUL(dy, dy);
+                d[r] = real ? DVSG_MUL(dy, dy) : 1.0f;     // padding: d2 >= 1, weight 0 -> adds exactly 0
             }
             TpsRec rec;
             rec.npx = f2(-px, -px); rec.pad = f2(0.f, 0.f); rec.cf = make_float4(cx, cx, cy, cy);
@@ -253,15 +285,14 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
 
     const float* srcb = p.src + (size_t)b * H * W * 3;
     const float2 one2 = f2dup(1.0f);
+    const bool full_rows = row0 + TR <= oh;
     // store phase: float4 f = i*32 + lane of the [8][384 B] output tile is row f/24, byte column (f%24)*16
-    int st_goff[TSTORES], st_col[TSTORES];
+    int st_goff[TSTORES];
 #pragma unroll
     for (int i = 0; i < TSTORES; ++i) {
         const int f = i * 32 + lane, r = f / 24;
-        st_col[i] = (f - r * 24) * 16;
-        st_goff[i] = row0 + r < oh ? r * ow * 12 + st_col[i] : -1;
+        st_goff[i] = r * ow * 12 + (f - r * 24) * 16;
     }
-    unsigned phase = 0;
 
     for (int t = t_begin + warp; t < t_end; t += TNW) {
         const int col0 = t * TC;
@@ -283,25 +314,27 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             }
             const float2 eps = f2dup(1e-6f);
             const unsigned char* rp = recs;
-#pragma unroll 4
-            for (int k = 0; k < p.pn; ++k, rp += sizeof(TpsRec)) {
-                const float2 npx = *reinterpret_cast<const float2*>(rp);
-                const float4 cf = *reinterpret_cast<const float4*>(rp + 16);
-                const float4 da = *reinterpret_cast<const float4*>(rp + 32);
-                const float4 db = *reinterpret_cast<const float4*>(rp + 48);
-                // scalar, separately rounded (x_t - px)^2 as in the reference (a packed mul feeding the packed
-                // add below would be contracted into FFMA2 by ptxas); FADD2 takes it as a broadcast operand
-                const float dx = DVSG_ADD(xt, npx.x);
-                const float2 dxx = f2dup(DVSG_MUL(dx, dx));
-                const float2 cfx = f2(cf.x, cf.y), cfy = f2(cf.z, cf.w);
-                const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
+            for (int k = 0; k < pn4; k += 4) {
 #pragma unroll
-                for (int j = 0; j < TR / 2; ++j) {
-                    const float2 d2 = __fadd2_rn(dxx, dy[j]);
-                    const float2 tt = __fadd2_rn(d2, eps);
-                    const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
-                    XP[j] = __ffma2_rn(cfx, r, XP[j]);
-                    YP[j] = __ffma2_rn(cfy, r, YP[j]);
+                for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
+                    const float npx = *reinterpret_cast<const float*>(rp);
+                    const float4 cf = *reinterpret_cast<const float4*>(rp + 16);
+                    const float4 da = *reinterpret_cast<const float4*>(rp + 32);
+                    const float4 db = *reinterpret_cast<const float4*>(rp + 48);
+                    // scalar, separately rounded (x_t - px)^2 as in the reference (a packed mul feeding the packed
+                    // add below would be contracted into FFMA2 by ptxas); FADD2 takes it as a broadcast operand
+                    const float dx = DVSG_ADD(xt, npx);
+                    const float2 dxx = f2dup(DVSG_MUL(dx, dx));
+                    const float2 cfx = f2(cf.x, cf.y), cfy = f2(cf.z, cf.w);
+                    const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
+#pragma unroll
+                    for (int j = 0; j < TR / 2; ++j) {
+                        const float2 d2 = __fadd2_rn(dxx, dy[j]);
+                        const float2 tt = __fadd2_rn(d2, eps);
+                        const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
+                        XP[j] = __ffma2_rn(cfx, r, XP[j]);
+                        YP[j] = __ffma2_rn(cfy, r, YP[j]);
+                    }
                 }
             }
             if (p.x_out && col_ok) {
@@ -367,12 +400,13 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
 
         // ================= F: footprint of the tile (warp-uniform after the REDUX) =================
         const float xmn = min8n(XP), xmx = max8n(XP), ymn = min8n(YP), ymx = max8n(YP);
-        // finite and small enough for floor_small(); NaN fails every comparison
-        const bool sane = xmn > -4.0e6f && xmx < 4.0e6f && ymn > -4.0e6f && ymx < 4.0e6f;
+        // finite and small enough for the 2^23 arithmetic; NaN fails the comparison
+        const bool sane = (fabsf(xmn) + fabsf(xmx)) + (fabsf(ymn) + fabsf(ymx)) < 4.0e6f;
         int x_lo = sane ? floor_small(xmn) : -(1 << 30), x_hi = sane ? floor_small(xmx) + 1 : (1 << 30);
         int y_lo = sane ? floor_small(ymn) : -(1 << 30), y_hi = sane ? floor_small(ymx) + 1 : (1 << 30);
         x_lo = __reduce_min_sync(0xffffffffu, x_lo); x_hi = __reduce_max_sync(0xffffffffu, x_hi);
         y_lo = __reduce_min_sync(0xffffffffu, y_lo); y_hi = __reduce_max_sync(0xffffffffu, y_hi);
+        const bool all_sane = x_lo > -(1 << 30);
         bool interior;
         int fx_lo, fx_hi, fy_lo, fy_hi;    // real source pixels the tile can touch (inclusive)
         if (MODE == TMODE_TPS) {
@@ -390,32 +424,44 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
         const int wpx = min(((fx_hi - fx0 + 1) + 3) & ~3, W - fx0);
         const int nrows = fy_hi - fy_lo + 1;
         const int pitch = wpx * 12;
-        const bool staged = nonempty && nrows <= 32 && (long long)pitch * nrows <= (long long)p.stage_bytes;
-        // the interior path forms byte offsets as exact fp32 integers below 2^22
-        interior = interior && staged && (long long)(fy_hi + 1) * pitch + (long long)(fx_hi + 2) * 12 < (1LL << 22);
+        const bool staged = nonempty && pitch <= 1024 && (long long)pitch * nrows <= (long long)p.stage_bytes;
+        // the packed paths form byte offsets as exact fp32 integers below 2^22
+        const bool packed_ok = staged && all_sane && (long long)(fy_hi + 1) * pitch + (long long)(fx_hi + 2) * 12 < (1LL << 22);
 
-        // ================= L: stage the footprint =================
+        // ================= L: stage the footprint (one 16-byte cp.async per lane and row) =================
         if (staged) {
-            fence_proxy_async_smem();      // earlier generic reads of the staging buffer vs. the async writes
-            if (lane == 0) mbar_arrive_expect_tx(mbar, (unsigned)(pitch * nrows));
+            const unsigned char* g = reinterpret_cast<const unsigned char*>(srcb) + ((size_t)fy_lo * W + fx0) * 12 + lane * 16;
+            uint32_t d = stage_s + lane * 16;
+            const bool c0 = lane * 16 < pitch, c1 = 512 + lane * 16 < pitch;   // rows are at most 2 x 512 B
+#pragma unroll 2
+            for (int r = 0; r < nrows; ++r, d += pitch, g += (size_t)W * 12) {
+                if (c0) cp_async16(d, g);
+                if (c1) cp_async16(d + 512, g + 512);
+            }
+            cp_async_commit();
+            cp_async_wait_all();
             __syncwarp();
-            if (lane < nrows) bulk_g2s(stage_s + (unsigned)(lane * pitch), srcb + ((size_t)(fy_lo + lane) * W + fx0) * 3, (unsigned)pitch, mbar);
         }
-        if (staged) { mbar_wait(mbar, phase); phase ^= 1u; }
 
         // ================= G: gather + blend =================
-        const uint32_t sbase = stage_s - (uint32_t)(fy_lo * pitch + fx0 * 12);   // shared address of frame pixel (0,0)
-        const uint32_t obase = out_s + (uint32_t)lane * 12u;   // general / direct paths
         const bool want_mask = MODE == TMODE_TPS && p.mask_out != nullptr;
-        if (interior) {
+        if (packed_ok && (interior || MODE == TMODE_TPS)) {
             // padded-frame modes address real pixel idx-1: fold the -1 into the base
             const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 12) - (MODE == TMODE_TPS ? 0 : pitch + 12);
             float* ot = reinterpret_cast<float*>(w_out) + lane * 3;
+            const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
             float2 ms[TR / 2];
-            interior_pair<MODE, 0>(XP[0], YP[0], pitch, sb, ot, ms[0]);
-            interior_pair<MODE, 1>(XP[1], YP[1], pitch, sb, ot, ms[1]);
-            interior_pair<MODE, 2>(XP[2], YP[2], pitch, sb, ot, ms[2]);
-            interior_pair<MODE, 3>(XP[3], YP[3], pitch, sb, ot, ms[3]);
+            if (interior) {
+                gather_pair<MODE, false, 0>(XP[0], YP[0], pitch, sb, ot, ms[0], wm1, hm1);
+                gather_pair<MODE, false, 1>(XP[1], YP[1], pitch, sb, ot, ms[1], wm1, hm1);
+                gather_pair<MODE, false, 2>(XP[2], YP[2], pitch, sb, ot, ms[2], wm1, hm1);
+                gather_pair<MODE, false, 3>(XP[3], YP[3], pitch, sb, ot, ms[3], wm1, hm1);
+            } else if (MODE == TMODE_TPS) {
+                gather_pair<MODE, true, 0>(XP[0], YP[0], pitch, sb, ot, ms[0], wm1, hm1);
+                gather_pair<MODE, true, 1>(XP[1], YP[1], pitch, sb, ot, ms[1], wm1, hm1);
+                gather_pair<MODE, true, 2>(XP[2], YP[2], pitch, sb, ot, ms[2], wm1, hm1);
+                gather_pair<MODE, true, 3>(XP[3], YP[3], pitch, sb, ot, ms[3], wm1, hm1);
+            }
             if (want_mask && col_ok) {
 #pragma unroll
                 for (int j = 0; j < TR / 2; ++j) {
@@ -425,31 +471,35 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
                 }
             }
         } else {
+            const uint32_t sbase = stage_s - (uint32_t)(fy_lo * pitch + fx0 * 12);   // shared address of frame pixel (0,0)
+            const uint32_t obase = out_s + (uint32_t)lane * 12u;
 #pragma unroll
-            for (int q = 0; q < TR; ++q) {
+            for (int q = 0; q < TR; ++q) {     // unrolled: XP / YP must stay in registers (no dynamic indexing)
                 const float xp = (q & 1) ? XP[q >> 1].y : XP[q >> 1].x, yp = (q & 1) ? YP[q >> 1].y : YP[q >> 1].x;
-                float o[3], msum = 0.0f;
-                if (staged) general_pixel<MODE, true>(xp, yp, W, H, sbase, pitch, srcb, o, msum);
-                else general_pixel<MODE, false>(xp, yp, W, H, 0u, 0, srcb, o, msum);
-                if (want_mask && col_ok && row0 + q < oh) p.mask_out[((size_t)b * oh + row0 + q) * ow + col] = msum;
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) t_sts(obase + (uint32_t)(q * TC * 12 + 4 * ch), o[ch]);
+                float* mp = want_mask && col_ok && row0 + q < oh ? p.mask_out + ((size_t)b * oh + row0 + q) * ow + col : nullptr;
+                if (staged) general_pixel<MODE, true>(xp, yp, W, H, sbase, pitch, srcb, obase + (uint32_t)(q * TC * 12), mp);
+                else general_pixel<MODE, false>(xp, yp, W, H, 0u, 0, srcb, obase + (uint32_t)(q * TC * 12), mp);
             }
         }
 
         // ================= S: output tile -> global, 128-bit coalesced stores =================
         __syncwarp();
         {
-            const int vbytes = min(TC, ow - col0) * 12;
             unsigned char* tile_g = reinterpret_cast<unsigned char*>(p.out + (((size_t)b * oh + row0) * ow + col0) * 3);
             const float4* ot4 = reinterpret_cast<const float4*>(w_out) + lane;
+            if (full_rows && col0 + TC <= ow) {
 #pragma unroll
-            for (int i = 0; i < TSTORES; ++i) {
-                const float4 v = ot4[i * 32];
-                if (st_goff[i] >= 0 && st_col[i] < vbytes) *reinterpret_cast<float4*>(tile_g + (unsigned)st_goff[i]) = v;
+                for (int i = 0; i < TSTORES; ++i) *reinterpret_cast<float4*>(tile_g + (unsigned)st_goff[i]) = ot4[i * 32];
+            } else {
+                const int vbytes = min(TC, ow - col0) * 12;
+#pragma unroll
+                for (int i = 0; i < TSTORES; ++i) {
+                    const int f = i * 32 + lane, r = f / 24, c = (f - r * 24) * 16;
+                    if (row0 + r < oh && c < vbytes) *reinterpret_cast<float4*>(tile_g + (unsigned)st_goff[i]) = ot4[i * 32];
+                }
             }
         }
-        __syncwarp();     // the output tile is rewritten by the next tile's gather
+        __syncwarp();     // the output tile and the staging buffer are rewritten by the next tile
     }
 }
 
@@ -457,10 +507,11 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
 static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 static int g_tile_stage = 6144;            // per-warp staging bytes
 static int g_tile_target_ctas = 148 * 5 * 4;
+static int g_tile_minb = 5;                // resident CTAs per SM the kernel is compiled for (5 or 6)
 
 bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0) {
     return C == 3 && W % 4 == 0 && ow % 4 == 0 && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
-           (long long)H * W < (1LL << 28) && pn_or_0 <= TKC;
+           (long long)H * W < (1LL << 28) && (long long)oh * ow < (1LL << 28) && pn_or_0 <= TKC;
 }
 
 template <int MODE>
@@ -476,10 +527,17 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     p.seg_len = (p.n_tx + segs - 1) / segs;
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
-    const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)p.pn * sizeof(TpsRec) : 0);
-    auto k = warp_fwd_tile_kernel<MODE>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<dim3((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B), TNT, smem, st>>>(p);
+    const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)((p.pn + 3) & ~3) * sizeof(TpsRec) : 0);
+    const dim3 grid((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B);
+    if (g_tile_minb >= 6) {
+        auto k = warp_fwd_tile_kernel<MODE, 6>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, TNT, smem, st>>>(p);
+    } else {
+        auto k = warp_fwd_tile_kernel<MODE, 5>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, TNT, smem, st>>>(p);
+    }
     count_launch();
     return check_launch("warp_fwd_tile_kernel");
 }
@@ -517,9 +575,10 @@ int tile_homog(const float* im, const float* theta, int projective, float* out, 
     return launch_tile<TMODE_HOMOG>(p, st);
 }
 
-void tile_set_tuning(int stage_bytes, int target_ctas) {
+void tile_set_tuning(int stage_bytes, int target_ctas, int minb) {
     if (stage_bytes >= 0) g_tile_stage = (stage_bytes + 127) & ~127;
     if (target_ctas > 0) g_tile_target_ctas = target_ctas;
+    if (minb > 0) g_tile_minb = minb;
 }
 
 }  // namespace dvsg
