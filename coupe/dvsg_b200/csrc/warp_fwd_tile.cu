@@ -287,12 +287,13 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
     const float2 one2 = f2dup(1.0f);
     const bool full_rows = row0 + TR <= oh;
     // store phase: float4 f = i*32 + lane of the [8][384 B] output tile is row f/24, byte column (f%24)*16
-    int st_goff[TSTORES];
+    unsigned st_goff[TSTORES];
 #pragma unroll
     for (int i = 0; i < TSTORES; ++i) {
         const int f = i * 32 + lane, r = f / 24;
-        st_goff[i] = r * ow * 12 + (f - r * 24) * 16;
+        st_goff[i] = (unsigned)(r * ow * 12 + (f - r * 24) * 16);
     }
+    unsigned char* strip_g = reinterpret_cast<unsigned char*>(p.out + ((size_t)b * oh + row0) * ow * 3);
 
     for (int t = t_begin + warp; t < t_end; t += TNW) {
         const int col0 = t * TC;
@@ -423,20 +424,28 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
         const int fx0 = fx_lo & ~3;                                          // 4 px = 48 B keeps rows 16-B aligned
         const int wpx = min(((fx_hi - fx0 + 1) + 3) & ~3, W - fx0);
         const int nrows = fy_hi - fy_lo + 1;
-        const int pitch = wpx * 12;
-        const bool staged = nonempty && pitch <= 1024 && (long long)pitch * nrows <= (long long)p.stage_bytes;
+        const int row_bytes = wpx * 12;
+        // shared-memory row pitch = a multiple of 128 B: the bank of a corner then depends on its column only
+        // (3*x mod 32, all different for 32 consecutive columns), whatever row each lane reads
+        const int pitch = (row_bytes + 127) & ~127;
+        const bool staged = nonempty && row_bytes <= 1024 && (long long)pitch * nrows <= (long long)p.stage_bytes;
         // the packed paths form byte offsets as exact fp32 integers below 2^22
         const bool packed_ok = staged && all_sane && (long long)(fy_hi + 1) * pitch + (long long)(fx_hi + 2) * 12 < (1LL << 22);
 
         // ================= L: stage the footprint (one 16-byte cp.async per lane and row) =================
         if (staged) {
             const unsigned char* g = reinterpret_cast<const unsigned char*>(srcb) + ((size_t)fy_lo * W + fx0) * 12 + lane * 16;
-            uint32_t d = stage_s + lane * 16;
-            const bool c0 = lane * 16 < pitch, c1 = 512 + lane * 16 < pitch;   // rows are at most 2 x 512 B
-#pragma unroll 2
-            for (int r = 0; r < nrows; ++r, d += pitch, g += (size_t)W * 12) {
-                if (c0) cp_async16(d, g);
-                if (c1) cp_async16(d + 512, g + 512);
+            const unsigned gstride = (unsigned)W * 12u;
+            if (lane * 16 < row_bytes) {
+                uint32_t d = stage_s + lane * 16;
+                const unsigned char* gr = g;
+#pragma unroll 4
+                for (int r = 0; r < nrows; ++r, d += pitch, gr += gstride) cp_async16(d, gr);
+            }
+            if (row_bytes > 512 && 512 + lane * 16 < row_bytes) {      // rare: rows of more than 42 pixels
+                uint32_t d = stage_s + 512 + lane * 16;
+                const unsigned char* gr = g + 512;
+                for (int r = 0; r < nrows; ++r, d += pitch, gr += gstride) cp_async16(d, gr);
             }
             cp_async_commit();
             cp_async_wait_all();
@@ -485,17 +494,17 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
         // ================= S: output tile -> global, 128-bit coalesced stores =================
         __syncwarp();
         {
-            unsigned char* tile_g = reinterpret_cast<unsigned char*>(p.out + (((size_t)b * oh + row0) * ow + col0) * 3);
+            unsigned char* tile_g = strip_g + (unsigned)col0 * 12u;
             const float4* ot4 = reinterpret_cast<const float4*>(w_out) + lane;
             if (full_rows && col0 + TC <= ow) {
 #pragma unroll
-                for (int i = 0; i < TSTORES; ++i) *reinterpret_cast<float4*>(tile_g + (unsigned)st_goff[i]) = ot4[i * 32];
+                for (int i = 0; i < TSTORES; ++i) *reinterpret_cast<float4*>(tile_g + st_goff[i]) = ot4[i * 32];
             } else {
                 const int vbytes = min(TC, ow - col0) * 12;
 #pragma unroll
                 for (int i = 0; i < TSTORES; ++i) {
                     const int f = i * 32 + lane, r = f / 24, c = (f - r * 24) * 16;
-                    if (row0 + r < oh && c < vbytes) *reinterpret_cast<float4*>(tile_g + (unsigned)st_goff[i]) = ot4[i * 32];
+                    if (row0 + r < oh && c < vbytes) *reinterpret_cast<float4*>(tile_g + st_goff[i]) = ot4[i * 32];
                 }
             }
         }
@@ -505,7 +514,7 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
 
 // ---- host side ---------------------------------------------------------------------------------
 static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
-static int g_tile_stage = 6144;            // per-warp staging bytes
+static int g_tile_stage = 6656;            // per-warp staging bytes (13 rows of 512 B)
 static int g_tile_target_ctas = 148 * 5 * 4;
 static int g_tile_minb = 5;                // resident CTAs per SM the kernel is compiled for (5 or 6)
 

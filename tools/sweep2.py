@@ -27,17 +27,17 @@ def main():
     if only in ('all', 'tps'):
         for amp in (0.2, 0.04, 0.0):
             U, coord, T = tps_case(B, H, W, 4, amp)
-            for stage, minb in ((6144, 5), (5632, 6), (5120, 6), (8192, 5)):
+            for stage, minb in ((6656, 5), (6144, 5), (5632, 6), (5120, 6), (7680, 4)):
                 lib.dvsg_set_tile_tuning(stage, -1, minb)
                 ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
                 rec('tps720 4x4 amp=%.2f tile stage=%d ctas/sm=%d' % (amp, stage, minb), ms, px, 24)
-            lib.dvsg_set_tile_tuning(6144, -1, 5)
+            lib.dvsg_set_tile_tuning(6656, -1, 5)
             if amp == 0.2:
                 for tc in (148 * 5 * 4, 148 * 5 * 24):
-                    lib.dvsg_set_tile_tuning(6144, tc, -1)
+                    lib.dvsg_set_tile_tuning(6656, tc, -1)
                     ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
                     rec('tps720 4x4 tile target_ctas=%d' % tc, ms, px, 24)
-                lib.dvsg_set_tile_tuning(6144, 148 * 5 * 12, -1)
+                lib.dvsg_set_tile_tuning(6656, 148 * 5 * 4, -1)
                 ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True))
                 rec('tps720 4x4 tile +xy', ms, px, 32)
                 ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, want_mask=True))
@@ -71,11 +71,11 @@ def main():
         pxf = 16 * 1080 * 1920
         for fname, flow in (('smooth', smooth_flow(16, 1080, 1920)), ('random+-8', (torch.rand((16, 1080, 1920, 2), device=dev) - 0.5) * 16),
                             ('zero', torch.zeros((16, 1080, 1920, 2), device=dev))):
-            for stage, minb in ((6144, 5), (5632, 6), (5120, 6), (8192, 5)):
+            for stage, minb in ((6656, 5), (6144, 5), (5632, 6), (5120, 6), (7680, 4)):
                 lib.dvsg_set_tile_tuning(stage, -1, minb)
                 ms = timeit(lambda: flow_call(im, flow, out, 0))
                 rec('flow1080 %s tile stage=%d ctas/sm=%d' % (fname, stage, minb), ms, pxf, 32)
-            lib.dvsg_set_tile_tuning(6144, -1, 5)
+            lib.dvsg_set_tile_tuning(6656, -1, 5)
             lib.dvsg_set_strip_tuning(148 * 12, 0)
             for name, flags in (('strip pipe=0 (old)', 4), ('direct (old)', 1)):
                 ms = timeit(lambda: flow_call(im, flow, out, flags))
