@@ -10,11 +10,14 @@
 //                    shared-memory broadcasts; or flow / given x,y / homography
 //   F  footprint     NaN-propagating FMNMX3 bounding box of the tile's sampling coordinates,
 //                    4 warp REDUX, no shared atomics, no CTA barrier
-//   L  staging       the footprint's rows -> the warp's private staging buffer with 16-byte
-//                    cp.async (LDGSTS), one instruction per row for the whole warp
+//   L  staging       the footprint -> the warp's private staging buffer with ONE 3-D TMA tensor
+//                    copy (cp.async.bulk.tensor, SASS UTMALDG) of a 128- or 160-float wide box,
+//                    completion on the warp's mbarrier; out-of-frame parts arrive as zeros,
+//                    which IS the zero padding of bilinear_interp / tf_warp
 //   G  gather+blend  four corners from shared memory; weights and add_n in the reference's
 //                    op order with separately rounded products and sums (bit-exact sampler)
-//   S  store         output tile staged in shared memory, then 128-bit coalesced stores
+//   S  store         output tile staged in shared memory, then one TMA tensor store (clipped at
+//                    the frame edge by the hardware)
 //
 // Gather variants, chosen per tile (warp-uniform):
 //   interior  every corner of every pixel lies strictly inside the frame: no clamps, corners
@@ -23,11 +26,12 @@
 //             sees the logarithms
 //   clamped   TPS tiles touching the frame border: same scheme plus the integer clamps of
 //             ThinPlateSpline.py:57-60 done on exact fp32 integers
-//   general   per-pixel scalar code with the full reference semantics (zero-padded samplers at
-//             the frame border, non-finite coordinates), staged or, when the footprint does
-//             not fit the staging buffer, straight from global memory
+//   general   per-pixel scalar code with the full reference semantics, corners straight from
+//             global memory: footprints larger than the biggest box, non-finite coordinates
 // Nothing but the frames themselves touches HBM: the [B, pn+3, h*w] basis and the sampling
 // grid of the reference never exist (x, y are written only when the caller asks).
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "dvsg_common.cuh"
 #include "sampler_math.cuh"
 
@@ -41,7 +45,6 @@ constexpr int TNW = 4;                        // warps per CTA
 constexpr int TNT = TNW * 32;
 constexpr int TKC = 256;                      // control points resident in shared memory
 constexpr int TOUT_BYTES = TR * TC * 12;      // output tile, 3072 B
-constexpr int TSTORES = TOUT_BYTES / 16 / 32; // float4 stores per lane and tile
 constexpr float TLN2 = 0.6931471805599453f;
 constexpr float MAGIC23 = 8388608.0f;         // 2^23
 constexpr float MAGIC15 = 12582912.0f;        // 1.5 * 2^23
@@ -64,8 +67,24 @@ struct TileParams {
     const float* theta;
     int projective;
     int stage_bytes;      // per-warp staging buffer
+    int dbg;
+    int bw[3], bh[3];     // staging boxes (floats x rows) of the three source tensor maps, clamped to the frame
     int n_tx, n_ty;       // tiles per strip / strips per frame
     int segs, seg_len;    // CTAs per strip, tiles per CTA
+};
+
+// staging boxes (floats wide x rows): pitch = 512 or 640 B keeps the row pitch a multiple of 128 B, so the
+// bank of a corner depends on its column only (3*x mod 32), whatever row each lane reads
+constexpr int NBOX = 3;
+constexpr int BOX_W0 = 128, BOX_W2 = 160;     // box 0: 128 x 10, box 1: 128 x 13, box 2: 160 x 10
+constexpr int BOX_H0 = 10, BOX_H1 = 13, BOX_H2 = 10;
+constexpr int TSTAGE_BYTES = 6656;            // largest box
+__host__ __device__ constexpr int box_w(int i) { return i == 2 ? BOX_W2 : BOX_W0; }
+__host__ __device__ constexpr int box_h(int i) { return i == 0 ? BOX_H0 : (i == 1 ? BOX_H1 : BOX_H2); }
+
+struct alignas(64) TileMaps {
+    CUtensorMap src[NBOX];   // source [B][H][3W] floats, one map per box shape
+    CUtensorMap out;         // output [B][oh][3ow] floats, box = one 96 x 8 tile
 };
 
 struct __align__(16) TpsRec {   // one control point, 64 B, read with broadcast LDS.32 / LDS.128
@@ -107,19 +126,20 @@ __device__ __forceinline__ int t_floor_i32(float f) {
     const int v = __float2int_rd(f);
     return fabsf(f) < 2147483648.0f ? v : (int)0x80000000;
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int x, int y, int z, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst_smem), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(mbar) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const void* tmap, int x, int y, int z, uint32_t src_smem) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tmap), "r"(x), "r"(y), "r"(z), "r"(src_smem) : "memory");
+}
 
 // ---- per-pixel general gather: full reference semantics --------------------------------------------
 // xp, yp: TPS -> pixel-space coordinate of the A4 sampler; other modes -> clipped+1 coordinate in the
-// zero-padded frame.  STAGED: corners come from the warp's staging buffer (sbase = shared address of
-// frame pixel (0,0) inside it), else from global memory.
-template <int MODE, bool STAGED>
-__device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, uint32_t sbase, int pitch, const float* __restrict__ srcb,
-                                           uint32_t oaddr, float* mask_ptr) {
+// zero-padded frame.  Corners come straight from global memory.
+template <int MODE>
+__device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, const float* __restrict__ srcb, uint32_t oaddr, float* mask_ptr) {
     int x0, x1, y0, y1;
     float ax0, ax1, ay0, ay1;
     bool v00 = true, v01 = true, v10 = true, v11 = true;   // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
@@ -145,15 +165,7 @@ __device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, uin
     const float w00 = DVSG_MUL(ax1, ay1), w01 = DVSG_MUL(ax0, ay1), w10 = DVSG_MUL(ax1, ay0), w11 = DVSG_MUL(ax0, ay0);
     if (MODE == TMODE_TPS && mask_ptr) *mask_ptr = DVSG_ADD(DVSG_ADD(DVSG_ADD(w00, w10), w01), w11);   // A4 add_n order
     float i00[3], i01[3], i10[3], i11[3];
-    if (STAGED) {
-        const uint32_t r0 = sbase + (uint32_t)(y0 * pitch), r1 = sbase + (uint32_t)(y1 * pitch);
-        const uint32_t a00 = r0 + (uint32_t)x0 * 12u, a01 = r0 + (uint32_t)x1 * 12u, a10 = r1 + (uint32_t)x0 * 12u, a11 = r1 + (uint32_t)x1 * 12u;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            i00[ch] = v00 ? t_lds(a00 + 4 * ch) : 0.0f; i01[ch] = v01 ? t_lds(a01 + 4 * ch) : 0.0f;
-            i10[ch] = v10 ? t_lds(a10 + 4 * ch) : 0.0f; i11[ch] = v11 ? t_lds(a11 + 4 * ch) : 0.0f;
-        }
-    } else {
+    {
         const float* a00 = srcb + ((size_t)y0 * W + x0) * 3;
         const float* a01 = srcb + ((size_t)y0 * W + x1) * 3;
         const float* a10 = srcb + ((size_t)y1 * W + x0) * 3;
@@ -237,8 +249,9 @@ __device__ __forceinline__ void gather_pair(const float2 xp, const float2 yp, co
 }
 
 template <int MODE, int MINB>
-__global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TileParams p) {
+__global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TileParams p, const __grid_constant__ TileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long s_mbar[TNW];
     __shared__ float s_lin[12];
     __shared__ __align__(16) float s_yt[TR];
 
@@ -251,10 +264,11 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
     unsigned char* w_out = smem + (size_t)warp * (TOUT_BYTES + p.stage_bytes);
     unsigned char* w_stage = w_out + TOUT_BYTES;
     const unsigned char* recs = smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes);
-    const uint32_t out_s = smem_u32(w_out), stage_s = smem_u32(w_stage);
+    const uint32_t out_s = smem_u32(w_out), stage_s = smem_u32(w_stage), mbar = smem_u32(&s_mbar[warp]);
     const int pn4 = (p.pn + 3) & ~3;                 // table padded with zero-weight records to a multiple of 4
 
-    // ---- prologue: per-strip tables (the only CTA barrier of the kernel) --------------------------
+    // ---- prologue: mbarriers, per-strip tables (the only CTA barrier of the kernel) -----------------
+    if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     if (tid < TR) s_yt[tid] = lin_coord(min(row0 + tid, oh - 1), p.step_y);
     if (MODE == TMODE_TPS) {
         const int N = p.pn + 3;
@@ -285,15 +299,8 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
 
     const float* srcb = p.src + (size_t)b * H * W * 3;
     const float2 one2 = f2dup(1.0f);
-    const bool full_rows = row0 + TR <= oh;
-    // store phase: float4 f = i*32 + lane of the [8][384 B] output tile is row f/24, byte column (f%24)*16
-    unsigned st_goff[TSTORES];
-#pragma unroll
-    for (int i = 0; i < TSTORES; ++i) {
-        const int f = i * 32 + lane, r = f / 24;
-        st_goff[i] = (unsigned)(r * ow * 12 + (f - r * 24) * 16);
-    }
-    unsigned char* strip_g = reinterpret_cast<unsigned char*>(p.out + ((size_t)b * oh + row0) * ow * 3);
+    unsigned phase = 0;
+    bool out_pending = false;
 
     for (int t = t_begin + warp; t < t_end; t += TNW) {
         const int col0 = t * TC;
@@ -409,54 +416,49 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
         y_lo = __reduce_min_sync(0xffffffffu, y_lo); y_hi = __reduce_max_sync(0xffffffffu, y_hi);
         const bool all_sane = x_lo > -(1 << 30);
         bool interior;
-        int fx_lo, fx_hi, fy_lo, fy_hi;    // real source pixels the tile can touch (inclusive)
+        int fx_lo, fx_hi, fy_lo, fy_hi;    // source pixels to stage (inclusive; may reach outside the frame for the padded modes)
         if (MODE == TMODE_TPS) {
             interior = x_lo >= 0 && x_hi <= W - 1 && y_lo >= 0 && y_hi <= H - 1;
             fx_lo = min(max(x_lo, 0), W - 1); fx_hi = min(max(x_hi, 0), W - 1);
             fy_lo = min(max(y_lo, 0), H - 1); fy_hi = min(max(y_hi, 0), H - 1);
         } else {
-            // padded-frame corners x0 in [x_lo, x_hi-1], x1 <= x_hi; valid iff 1 <= idx <= W; real pixel = idx - 1
-            interior = x_lo >= 1 && x_hi <= W && y_lo >= 1 && y_hi <= H;
-            fx_lo = max(x_lo, 1) - 1; fx_hi = min(x_hi, W) - 1;
-            fy_lo = max(y_lo, 1) - 1; fy_hi = min(y_hi, H) - 1;
+            // padded-frame corners lie in [x_lo, x_hi]; real pixel = idx - 1.  Whatever falls outside the frame is
+            // zero-filled by the TMA copy -- exactly the zero padding of the reference -- so every tile is "interior"
+            interior = true;
+            fx_lo = x_lo - 1; fx_hi = x_hi - 1; fy_lo = y_lo - 1; fy_hi = y_hi - 1;
         }
-        const bool nonempty = fx_lo <= fx_hi && fy_lo <= fy_hi;
-        const int fx0 = fx_lo & ~3;                                          // 4 px = 48 B keeps rows 16-B aligned
-        const int wpx = min(((fx_hi - fx0 + 1) + 3) & ~3, W - fx0);
-        const int nrows = fy_hi - fy_lo + 1;
-        const int row_bytes = wpx * 12;
-        // shared-memory row pitch = a multiple of 128 B: the bank of a corner then depends on its column only
-        // (3*x mod 32, all different for 32 consecutive columns), whatever row each lane reads
-        const int pitch = (row_bytes + 127) & ~127;
-        const bool staged = nonempty && row_bytes <= 1024 && (long long)pitch * nrows <= (long long)p.stage_bytes;
-        // the packed paths form byte offsets as exact fp32 integers below 2^22
-        const bool packed_ok = staged && all_sane && (long long)(fy_hi + 1) * pitch + (long long)(fx_hi + 2) * 12 < (1LL << 22);
+        // the box starts at a 16-byte aligned float (TMA faults on unaligned box origins)
+        const int fx0 = (fx_lo * 3) & ~3;
+        const int fw = (fx_hi + 1) * 3 - fx0, nrows = fy_hi - fy_lo + 1;
+        int box = -1;
+        if (fw <= p.bw[0]) box = nrows <= p.bh[0] ? 0 : (nrows <= p.bh[1] ? 1 : -1);
+        else if (fw <= p.bw[2] && nrows <= p.bh[2]) box = 2;
+        if ((p.dbg & 1) && box == 1) box = -1;
+        if ((p.dbg & 2) && box == 2) box = -1;
+        const int pitch = (box == 2 ? p.bw[2] : p.bw[0]) * 4;
+        const int box_rows = box == 0 ? p.bh[0] : (box == 1 ? p.bh[1] : p.bh[2]);
+        // the packed gather forms byte offsets as exact fp32 integers below 2^22
+        const bool staged = box >= 0 && all_sane && (long long)(fy_hi + 3) * pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
 
-        // ================= L: stage the footprint (one 16-byte cp.async per lane and row) =================
+        // ================= L: stage the footprint with one TMA tensor copy =================
         if (staged) {
-            const unsigned char* g = reinterpret_cast<const unsigned char*>(srcb) + ((size_t)fy_lo * W + fx0) * 12 + lane * 16;
-            const unsigned gstride = (unsigned)W * 12u;
-            if (lane * 16 < row_bytes) {
-                uint32_t d = stage_s + lane * 16;
-                const unsigned char* gr = g;
-#pragma unroll 4
-                for (int r = 0; r < nrows; ++r, d += pitch, gr += gstride) cp_async16(d, gr);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(mbar, (unsigned)(pitch * box_rows));
+                tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
             }
-            if (row_bytes > 512 && 512 + lane * 16 < row_bytes) {      // rare: rows of more than 42 pixels
-                uint32_t d = stage_s + 512 + lane * 16;
-                const unsigned char* gr = g + 512;
-                for (int r = 0; r < nrows; ++r, d += pitch, gr += gstride) cp_async16(d, gr);
-            }
-            cp_async_commit();
-            cp_async_wait_all();
-            __syncwarp();
         }
+        if (out_pending) {                 // the previous tile's tensor store must have read the output tile
+            if (lane == 0) bulk_wait_read0();
+            out_pending = false;
+        }
+        __syncwarp();
+        if (staged) { mbar_wait(mbar, phase); phase ^= 1u; }
 
         // ================= G: gather + blend =================
         const bool want_mask = MODE == TMODE_TPS && p.mask_out != nullptr;
-        if (packed_ok && (interior || MODE == TMODE_TPS)) {
-            // padded-frame modes address real pixel idx-1: fold the -1 into the base
-            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 12) - (MODE == TMODE_TPS ? 0 : pitch + 12);
+        if (staged) {
+            // sb = staging address of frame pixel (0,0); padded-frame modes index pixel idx-1: fold the -1 into it
+            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
             float* ot = reinterpret_cast<float*>(w_out) + lane * 3;
             const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
             float2 ms[TR / 2];
@@ -480,53 +482,72 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
                 }
             }
         } else {
-            const uint32_t sbase = stage_s - (uint32_t)(fy_lo * pitch + fx0 * 12);   // shared address of frame pixel (0,0)
             const uint32_t obase = out_s + (uint32_t)lane * 12u;
 #pragma unroll
             for (int q = 0; q < TR; ++q) {     // unrolled: XP / YP must stay in registers (no dynamic indexing)
                 const float xp = (q & 1) ? XP[q >> 1].y : XP[q >> 1].x, yp = (q & 1) ? YP[q >> 1].y : YP[q >> 1].x;
                 float* mp = want_mask && col_ok && row0 + q < oh ? p.mask_out + ((size_t)b * oh + row0 + q) * ow + col : nullptr;
-                if (staged) general_pixel<MODE, true>(xp, yp, W, H, sbase, pitch, srcb, obase + (uint32_t)(q * TC * 12), mp);
-                else general_pixel<MODE, false>(xp, yp, W, H, 0u, 0, srcb, obase + (uint32_t)(q * TC * 12), mp);
+                if (!(p.dbg & 4)) general_pixel<MODE>(xp, yp, W, H, srcb, obase + (uint32_t)(q * TC * 12), mp);
             }
         }
 
-        // ================= S: output tile -> global, 128-bit coalesced stores =================
+        // ================= S: output tile -> global with one TMA tensor store (clipped at the frame edge) ===
+        fence_proxy_async_smem();          // this lane's generic-proxy writes -> visible to the async proxy
         __syncwarp();
-        {
-            unsigned char* tile_g = strip_g + (unsigned)col0 * 12u;
-            const float4* ot4 = reinterpret_cast<const float4*>(w_out) + lane;
-            if (full_rows && col0 + TC <= ow) {
-#pragma unroll
-                for (int i = 0; i < TSTORES; ++i) *reinterpret_cast<float4*>(tile_g + st_goff[i]) = ot4[i * 32];
-            } else {
-                const int vbytes = min(TC, ow - col0) * 12;
-#pragma unroll
-                for (int i = 0; i < TSTORES; ++i) {
-                    const int f = i * 32 + lane, r = f / 24, c = (f - r * 24) * 16;
-                    if (row0 + r < oh && c < vbytes) *reinterpret_cast<float4*>(tile_g + st_goff[i]) = ot4[i * 32];
-                }
-            }
+        if (lane == 0) {
+            tma_store_3d(&maps.out, col0 * 3, row0, b, out_s);
+            bulk_commit();
         }
-        __syncwarp();     // the output tile and the staging buffer are rewritten by the next tile
+        out_pending = true;
     }
+    if (out_pending && lane == 0) bulk_wait_read0();   // shared memory must outlive the store's reads
 }
 
 // ---- host side ---------------------------------------------------------------------------------
 static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
-static int g_tile_stage = 6656;            // per-warp staging bytes (13 rows of 512 B)
 static int g_tile_target_ctas = 148 * 5 * 4;
+static int g_tile_dbg = 0;
 static int g_tile_minb = 5;                // resident CTAs per SM the kernel is compiled for (5 or 6)
 
 bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0) {
-    return C == 3 && W % 4 == 0 && ow % 4 == 0 && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
+    return C == 3 && W % 4 == 0 && ow % 4 == 0 && ow >= TC && oh >= TR && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
            (long long)H * W < (1LL << 28) && (long long)oh * ow < (1LL << 28) && pn_or_0 <= TKC;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// [B][rows][3*cols] fp32 tensor, box = bw floats x bh rows x 1 frame, zero fill outside the tensor
+static int encode_frames(CUtensorMap* m, const float* base, int B, int rows, int cols, int bw, int bh) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("tile kernel: cuTensorMapEncodeTiled is not available from this driver"); return DVSG_ERR_CUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols * 3, (cuuint64_t)rows, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 12, (cuuint64_t)rows * cols * 12};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tile kernel: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DVSG_ERR_CUDA; }
+    return DVSG_OK;
 }
 
 template <int MODE>
 static int launch_tile(TileParams p, cudaStream_t st) {
     if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
-    p.stage_bytes = g_tile_stage;
+    p.stage_bytes = TSTAGE_BYTES;
+    p.dbg = g_tile_dbg;
     p.n_tx = (p.ow + TC - 1) / TC;
     p.n_ty = (p.oh + TR - 1) / TR;
     const long long strips = (long long)p.B * p.n_ty;
@@ -536,16 +557,25 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     p.seg_len = (p.n_tx + segs - 1) / segs;
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
+    TileMaps maps;
+    for (int i = 0; i < NBOX; ++i) {
+        p.bw[i] = min(box_w(i), 3 * p.W);      // a box may not exceed the tensor (tiny frames)
+        p.bh[i] = min(box_h(i), p.H);
+        const int rc = encode_frames(&maps.src[i], p.src, p.B, p.H, p.W, p.bw[i], p.bh[i]);
+        if (rc) return rc;
+    }
+    const int rc = encode_frames(&maps.out, p.out, p.B, p.oh, p.ow, TC * 3, TR);
+    if (rc) return rc;
     const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)((p.pn + 3) & ~3) * sizeof(TpsRec) : 0);
     const dim3 grid((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B);
     if (g_tile_minb >= 6) {
         auto k = warp_fwd_tile_kernel<MODE, 6>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, TNT, smem, st>>>(p);
+        k<<<grid, TNT, smem, st>>>(p, maps);
     } else {
         auto k = warp_fwd_tile_kernel<MODE, 5>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, TNT, smem, st>>>(p);
+        k<<<grid, TNT, smem, st>>>(p, maps);
     }
     count_launch();
     return check_launch("warp_fwd_tile_kernel");
@@ -585,7 +615,7 @@ int tile_homog(const float* im, const float* theta, int projective, float* out, 
 }
 
 void tile_set_tuning(int stage_bytes, int target_ctas, int minb) {
-    if (stage_bytes >= 0) g_tile_stage = (stage_bytes + 127) & ~127;
+    if (stage_bytes >= 0 && stage_bytes < 16) g_tile_dbg = stage_bytes;      // debug mask (the staging buffer is sized by the largest TMA box)
     if (target_ctas > 0) g_tile_target_ctas = target_ctas;
     if (minb > 0) g_tile_minb = minb;
 }

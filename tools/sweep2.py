@@ -27,7 +27,7 @@ def main():
     if only in ('all', 'tps'):
         for amp in (0.2, 0.04, 0.0):
             U, coord, T = tps_case(B, H, W, 4, amp)
-            for stage, minb in ((6656, 5), (6144, 5), (5632, 6), (5120, 6), (7680, 4)):
+            for stage, minb in ((6656, 5),):
                 lib.dvsg_set_tile_tuning(stage, -1, minb)
                 ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
                 rec('tps720 4x4 amp=%.2f tile stage=%d ctas/sm=%d' % (amp, stage, minb), ms, px, 24)
@@ -71,7 +71,7 @@ def main():
         pxf = 16 * 1080 * 1920
         for fname, flow in (('smooth', smooth_flow(16, 1080, 1920)), ('random+-8', (torch.rand((16, 1080, 1920, 2), device=dev) - 0.5) * 16),
                             ('zero', torch.zeros((16, 1080, 1920, 2), device=dev))):
-            for stage, minb in ((6656, 5), (6144, 5), (5632, 6), (5120, 6), (7680, 4)):
+            for stage, minb in ((6656, 5),):
                 lib.dvsg_set_tile_tuning(stage, -1, minb)
                 ms = timeit(lambda: flow_call(im, flow, out, 0))
                 rec('flow1080 %s tile stage=%d ctas/sm=%d' % (fname, stage, minb), ms, pxf, 32)
