@@ -87,10 +87,8 @@ struct alignas(64) TileMaps {
     CUtensorMap out;         // output [B][oh][3ow] floats, box = one 96 x 8 tile
 };
 
-struct __align__(16) TpsRec {   // one control point, 64 B, read with broadcast LDS.32 / LDS.128
-    float2 npx;   // (-px, -px)
-    float2 pad;
-    float4 cf;    // (cx ln2, cx ln2, cy ln2, cy ln2)
+struct __align__(16) TpsRec {   // one control point, 48 B, read with three broadcast LDS.128
+    float4 pc;    // (-px, cx ln2, cy ln2, 0)
     float4 dya;   // (y_t(row0 + r) - py)^2, r = 0..3
     float4 dyb;   // r = 4..7
 };
@@ -287,7 +285,7 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
                 d[r] = real ? DVSG_MUL(dy, dy) : 1.0f;     // padding: d2 >= 1, weight 0 -> adds exactly 0
             }
             TpsRec rec;
-            rec.npx = f2(-px, -px); rec.pad = f2(0.f, 0.f); rec.cf = make_float4(cx, cx, cy, cy);
+            rec.pc = make_float4(-px, cx, cy, 0.0f);
             rec.dya = make_float4(d[0], d[1], d[2], d[3]); rec.dyb = make_float4(d[4], d[5], d[6], d[7]);
             wr[k] = rec;
         }
@@ -325,15 +323,14 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
             for (int k = 0; k < pn4; k += 4) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
-                    const float npx = *reinterpret_cast<const float*>(rp);
-                    const float4 cf = *reinterpret_cast<const float4*>(rp + 16);
-                    const float4 da = *reinterpret_cast<const float4*>(rp + 32);
-                    const float4 db = *reinterpret_cast<const float4*>(rp + 48);
+                    const float4 pc = *reinterpret_cast<const float4*>(rp);
+                    const float4 da = *reinterpret_cast<const float4*>(rp + 16);
+                    const float4 db = *reinterpret_cast<const float4*>(rp + 32);
                     // scalar, separately rounded (x_t - px)^2 as in the reference (a packed mul feeding the packed
-                    // add below would be contracted into FFMA2 by ptxas); FADD2 takes it as a broadcast operand
-                    const float dx = DVSG_ADD(xt, npx);
+                    // add below would be contracted into FFMA2 by ptxas); the packed ops take scalars as broadcast operands
+                    const float dx = DVSG_ADD(xt, pc.x);
                     const float2 dxx = f2dup(DVSG_MUL(dx, dx));
-                    const float2 cfx = f2(cf.x, cf.y), cfy = f2(cf.z, cf.w);
+                    const float2 cfx = f2dup(pc.y), cfy = f2dup(pc.z);
                     const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
 #pragma unroll
                     for (int j = 0; j < TR / 2; ++j) {
