@@ -224,7 +224,7 @@ def run_ours(args, wl):
             e1.record(stream)
             _lib.check(rc, 'dvsg_flow_warp_fwd')
             ev_pairs.append((e0, e1))
-        kernel_name = 'warp_fwd_kernel<MODE_FLOW, STAGED>'
+        kernel_name = 'warp_fwd_tile_kernel<TMODE_FLOW> (warp_fwd_tile.cu)'
         launches_per_step = 1
     else:
         m = wl['mesh']
@@ -248,7 +248,7 @@ def run_ours(args, wl):
                 gU, gT, _, _ = ops.tps_warp_bwd(U, coord, T, (H, W), g_out, None, None, need_grad_U=True, want_grid_grad=True)
                 ops.tps_solve_bwd(coord, gT)
             return res
-        kernel_name = 'warp_fwd_kernel<MODE_TPS, STAGED, PACK>'
+        kernel_name = 'warp_fwd_tile_kernel<TMODE_TPS> (warp_fwd_tile.cu)'
         launches_per_step = None
 
     def barrier():

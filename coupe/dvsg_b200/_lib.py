@@ -37,9 +37,7 @@ PROTOTYPES = {
 }
 # tuning knobs used by bench / profiling experiments (exported, but not in the public header)
 TUNING_PROTOTYPES = {
-    'dvsg_set_tuning': (c_int, [c_int, c_int]),
     'dvsg_set_bwd_tuning': (c_int, [c_int]),
-    'dvsg_set_strip_tuning': (c_int, [c_int, c_int]),
     'dvsg_set_tile_tuning': (c_int, [c_int, c_int, c_int]),
 }
 
@@ -66,8 +64,6 @@ def load():
             fn = getattr(lib, name)      # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
-    if os.environ.get('DVSG_STRIP_PIPE') in ('0', '1'):      # experiments: force the non-/pipelined strip kernel
-        lib.dvsg_set_strip_tuning(-1, int(os.environ['DVSG_STRIP_PIPE']))
     _lib = lib
     return lib
 

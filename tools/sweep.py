@@ -1,4 +1,4 @@
-"""Times kernel variants with CUDA events (tuning knobs of the library) -- run on the GPU box."""
+"""Times the forward kernel variants with CUDA events (tile kernel vs the generic direct kernel) -- run on the GPU box."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -39,73 +39,79 @@ def smooth_flow(B, H, W, amp=8.0, jitter=0.5):
     return f.permute(0, 2, 3, 1).contiguous()
 
 
+res = []
+
+
+def rec(name, ms, px, bpp):
+    gbs = px * bpp / ms / 1e6
+    res.append((name, ms, gbs))
+    print('%-56s %8.3f ms  %8.1f GB/s  %5.1f%%  %7.1f Gpix/s' % (name, ms, gbs, 100 * gbs / 6548.2, px / ms / 1e6), flush=True)
+
+
+def flow_call(im, flow, out, flags):
+    rc = lib.dvsg_flow_warp_fwd(im.data_ptr(), flow.data_ptr(), out.data_ptr(), im.shape[0], im.shape[1], im.shape[2], 3, flags, 0)
+    assert rc == 0, lib.dvsg_last_error()
+
+
 def main():
-    res = []
+    only = sys.argv[1] if len(sys.argv) > 1 else 'all'
     B, H, W = 64, 720, 1280
     px = B * H * W
-    U, coord, T = tps_case(B, H, W, 4)
-
-    def flow_call(im, flow, out, flags):
-        rc = lib.dvsg_flow_warp_fwd(im.data_ptr(), flow.data_ptr(), out.data_ptr(), im.shape[0], im.shape[1], im.shape[2], 3, flags, 0)
-        assert rc == 0, lib.dvsg_last_error()
-
-    for pipe in (1, 0):
-        lib.dvsg_set_strip_tuning(148 * 12, pipe)
-        for smem in (20, 28, 36):
-            lib.dvsg_set_tuning(smem * 1024, 1)
-            ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
-            res.append(('tps720 4x4 strip pipe=%d smem=%dK' % (pipe, smem), ms, px * 24 / ms / 1e6))
-        lib.dvsg_set_tuning(28 * 1024, 0)
-        ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
-        res.append(('tps720 4x4 strip pipe=%d nopack' % pipe, ms, px * 24 / ms / 1e6))
-        lib.dvsg_set_tuning(28 * 1024, 1)
-        for tc in (148 * 4, 148 * 24, 148 * 48):
-            lib.dvsg_set_strip_tuning(tc, pipe)
-            ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
-            res.append(('tps720 4x4 strip pipe=%d target_ctas=%d' % (pipe, tc), ms, px * 24 / ms / 1e6))
-        lib.dvsg_set_strip_tuning(148 * 12, pipe)
-        ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True))
-        res.append(('tps720 strip pipe=%d +xy' % pipe, ms, px * 32 / ms / 1e6))
-    for name, flags in (('legacy-staged', 2), ('direct', 1)):
-        ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, flags=flags))
-        res.append(('tps720 4x4 %s' % name, ms, px * 24 / ms / 1e6))
-    U5, c5, T5 = tps_case(B, H, W, 5)
-    for pipe in (1, 0):
-        lib.dvsg_set_strip_tuning(148 * 12, pipe)
+    if only in ('all', 'tps'):
+        for amp in (0.2, 0.04, 0.0):
+            U, coord, T = tps_case(B, H, W, 4, amp)
+            for minb in (5, 6):
+                lib.dvsg_set_tile_tuning(-1, -1, minb)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
+                rec('tps720 4x4 amp=%.2f tile (compiled for %d CTAs/SM)' % (amp, minb), ms, px, 24)
+            lib.dvsg_set_tile_tuning(-1, -1, 5)
+            if amp == 0.2:
+                for tc in (148 * 5 * 4, 148 * 5 * 24):
+                    lib.dvsg_set_tile_tuning(-1, tc, -1)
+                    ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
+                    rec('tps720 4x4 tile target_ctas=%d' % tc, ms, px, 24)
+                lib.dvsg_set_tile_tuning(-1, 148 * 5 * 4, -1)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True))
+                rec('tps720 4x4 tile +xy', ms, px, 32)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, want_mask=True))
+                rec('tps720 4x4 tile +mask', ms, px, 28)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, flags=1))
+                rec('tps720 4x4 generic direct kernel', ms, px, 24)
+        U5, c5, T5 = tps_case(B, H, W, 5)
         ms = timeit(lambda: ops.tps_warp_fwd(U5, c5, T5, (H, W), want_grid=False))
-        res.append(('tps720 5x5 strip pipe=%d' % pipe, ms, px * 24 / ms / 1e6))
-    del U, U5
-    Uc, cc, Tc = tps_case(4, 2160, 3840, 16)
-    for pipe in (1, 0):
-        lib.dvsg_set_strip_tuning(148 * 12, pipe)
+        rec('tps720 5x5 tile', ms, px, 24)
+        del U, U5
+        U8, c8, T8 = tps_case(64, 1080, 1920, 4)
+        ms = timeit(lambda: ops.tps_warp_fwd(U8, c8, T8, (1080, 1920), want_grid=False))
+        rec('tps1080 4x4 B=64 tile', ms, 64 * 1080 * 1920, 24)
+        del U8
+        Uc, cc, Tc = tps_case(4, 2160, 3840, 16)
         ms = timeit(lambda: ops.tps_warp_fwd(Uc, cc, Tc, (2160, 3840), want_grid=False), n=5, warm=1)
-        res.append(('tps4k 16x16 strip B=4 pipe=%d' % pipe, ms, 4 * 2160 * 3840 * 24 / ms / 1e6))
-    del Uc
-    Us, cs, Ts = tps_case(32, 288, 512, 4)
-    for pipe in (1, 0):
-        lib.dvsg_set_strip_tuning(148 * 12, pipe)
+        rec('tps4k 16x16 B=4 tile', ms, 4 * 2160 * 3840, 24)
+        del Uc
+        Us, cs, Ts = tps_case(32, 288, 512, 4)
         ms = timeit(lambda: ops.tps_warp_fwd(Us, cs, Ts, (288, 512), want_grid=True))
-        res.append(('tps 288x512 B=32 +xy (L2-resident) pipe=%d' % pipe, ms, 32 * 288 * 512 * 32 / ms / 1e6))
-    # flow
-    im = torch.rand((16, 1080, 1920, 3), device=dev)
-    out = torch.empty_like(im)
-    pxf = 16 * 1080 * 1920
-    for fname, flow in (('smooth', smooth_flow(16, 1080, 1920)), ('random+-8', (torch.rand((16, 1080, 1920, 2), device=dev) - 0.5) * 16)):
-        for pipe in (1, 0):
-            lib.dvsg_set_strip_tuning(148 * 12, pipe)
-            for smem in (20, 28, 40):
-                lib.dvsg_set_tuning(smem * 1024, 1)
-                ms = timeit(lambda: flow_call(im, flow, out, 0))
-                res.append(('flow1080 %s strip pipe=%d smem=%dK' % (fname, pipe, smem), ms, pxf * 32 / ms / 1e6))
-        lib.dvsg_set_tuning(28 * 1024, 1)
-        for name, flags in (('legacy-staged', 2), ('direct', 1)):
-            ms = timeit(lambda: flow_call(im, flow, out, flags))
-            res.append(('flow1080 %s %s' % (fname, name), ms, pxf * 32 / ms / 1e6))
-    ms = timeit(lambda: out.copy_(im))
-    res.append(('torch copy 398MB', ms, pxf * 24 / ms / 1e6))
-    for name, ms, gbs in res:
-        print('%-52s %8.3f ms  %8.1f GB/s  %5.1f%%' % (name, ms, gbs, 100 * gbs / 6548.2))
+        rec('tps 288x512 B=32 +xy (L2-resident) tile', ms, 32 * 288 * 512, 32)
+        U1, c1, T1 = tps_case(1, 288, 512, 4)
+        ms = timeit(lambda: ops.tps_warp_fwd(U1, c1, T1, (288, 512), want_grid=False))
+        rec('tps 288x512 B=1 tile (latency)', ms, 288 * 512, 24)
+    if only in ('all', 'flow'):
+        im = torch.rand((16, 1080, 1920, 3), device=dev)
+        out = torch.empty_like(im)
+        pxf = 16 * 1080 * 1920
+        for fname, flow in (('smooth', smooth_flow(16, 1080, 1920)), ('random+-8', (torch.rand((16, 1080, 1920, 2), device=dev) - 0.5) * 16),
+                            ('zero', torch.zeros((16, 1080, 1920, 2), device=dev))):
+            ms = timeit(lambda: flow_call(im, flow, out, 0))
+            rec('flow1080 %s tile' % fname, ms, pxf, 32)
+            for name, flags in (('generic direct kernel', 1),):
+                ms = timeit(lambda: flow_call(im, flow, out, flags))
+                rec('flow1080 %s %s' % (fname, name), ms, pxf, 32)
+        x = torch.rand(pxf, device=dev) * 2 - 1
+        y = torch.rand(pxf, device=dev) * 2 - 1
+        ms = timeit(lambda: ops.bilinear_interp(im, x, y, (1080, 1920)))
+        rec('bilinear1080 random xy tile', ms, pxf, 32)
+        ms = timeit(lambda: out.copy_(im))
+        rec('torch copy 398MB', ms, pxf, 24)
 
 
-if __name__ == "__main__":
-    main()
+main()
