@@ -151,7 +151,11 @@ def cpu_sample_plan(wl, threads):
     except Exception:
         budget = 16e9
     threads = max(1, min(threads, int(budget // max(mem_per_frame, 1))))
-    return threads, threads
+    # ~1 s per 720p frame and thread: several frames per thread so that a sample is 10-30 s of CPU work
+    per_thread = max(1, min(8, int(round(8 * 921600 / px))))
+    if wl['mesh'] > 8:
+        per_thread = 1
+    return threads, threads * per_thread
 
 
 def run_reference(args, wl):
@@ -236,6 +240,8 @@ def run_ours(args, wl):
         train = kind == 'tps_train'
         g_out = torch.rand((B, H, W, 3), device=dev, generator=g) if train else None
 
+        bwd_pairs = []
+
         def step():
             target = coord + vec
             T = ops.tps_solve(coord, target)
@@ -245,7 +251,12 @@ def run_ours(args, wl):
             e1.record(stream)
             ev_pairs.append((e0, e1))
             if train:
-                gU, gT, _, _ = ops.tps_warp_bwd(U, coord, T, (H, W), g_out, None, None, need_grad_U=True, want_grid_grad=True)
+                gU = torch.zeros_like(U)          # zero fill of grad_image: part of the step (counted in the 56 B/px)
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record(stream)
+                _, gT, _, _ = ops.tps_warp_bwd(U, coord, T, (H, W), g_out, None, None, need_grad_U=True, want_grid_grad=True, grad_U_out=gU)
+                b1.record(stream)
+                bwd_pairs.append((b0, b1))
                 ops.tps_solve_bwd(coord, gT)
             return res
         kernel_name = 'warp_fwd_tile_kernel<TMODE_TPS> (warp_fwd_tile.cu)'
@@ -260,6 +271,8 @@ def run_ours(args, wl):
         step()
     barrier()
     ev_pairs.clear()
+    if kind == 'tps_train':
+        bwd_pairs.clear()
     l0 = _lib.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -308,6 +321,14 @@ def run_ours(args, wl):
         value = world * pix_per_step * args.steps / (elapsed_ms * 1e-3) / 1e6
         fwd_bpp = 32 if kind in ('flow', 'tps_train') else 24
         achieved = pix_per_step * fwd_bpp / (kern_ms * 1e-3) / 1e9
+        extra = {}
+        if kind == 'tps_train':
+            # the dominant kernel of the training shape is the backward: 56 B/px (grad_out 12 + source 12 +
+            # grad_image zero fill 12 + grad_image accumulate 12 + grad_x,y 8)
+            bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_pairs) / max(len(bwd_pairs), 1)
+            extra = {'forward_kernel': {'kernel': kernel_name, 'kernel_ms': kern_ms, 'achieved': achieved, 'algorithmic_bytes_per_px': 32}}
+            kernel_name, kern_ms, fwd_bpp = 'warp_bwd_kernel<BMODE_TPS> (warp_bwd.cu)', bwd_ms, 56
+            achieved = pix_per_step * fwd_bpp / (kern_ms * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
@@ -324,7 +345,7 @@ def run_ours(args, wl):
                        if pix_per_step * fwd_bpp > 2.5e8 else 'working set %.0f MB fits L2: HBM fraction is an upper bound' % (pix_per_step * fwd_bpp / 1e6)},
             'roofline': {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_px': fwd_bpp, 'kernel_ms': kern_ms},
+                         'algorithmic_bytes_per_px': fwd_bpp, 'kernel_ms': kern_ms, **extra},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk.summary(),
         }
         if not args.no_cpu and world == 1:

@@ -106,7 +106,7 @@ def tps_warp_fwd(U, coord, T, out_size, want_grid=True, want_mask=False, flags=0
     return out, x, y, mask
 
 
-def tps_warp_bwd(U, coord, T, out_size, grad_out, grad_x=None, grad_y=None, need_grad_U=True, want_grid_grad=False):
+def tps_warp_bwd(U, coord, T, out_size, grad_out, grad_x=None, grad_y=None, need_grad_U=True, want_grid_grad=False, grad_U_out=None):
     lib = _lib.load()
     B, H, W, C = U.shape
     oh, ow = out_hw(out_size)
@@ -119,7 +119,8 @@ def tps_warp_bwd(U, coord, T, out_size, grad_out, grad_x=None, grad_y=None, need
         z = torch.zeros(B * oh * ow, dtype=torch.float32, device=dev)
         gx_in = z if gx_in is None else gx_in
         gy_in = z if gy_in is None else gy_in
-    gU = torch.zeros_like(U) if need_grad_U else None
+    # grad_U is accumulated into: the caller may pass a zero-filled (or partially accumulated) buffer
+    gU = (grad_U_out if grad_U_out is not None else torch.zeros_like(U)) if need_grad_U else None
     gT = torch.empty((B, 2, pn + 3), dtype=torch.float32, device=dev)
     gxs = torch.empty(B * oh * ow, dtype=torch.float32, device=dev) if want_grid_grad else None
     gys = torch.empty(B * oh * ow, dtype=torch.float32, device=dev) if want_grid_grad else None
