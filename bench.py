@@ -221,13 +221,15 @@ def run_ours(args, wl):
         out = torch.empty_like(U)
         stream = torch.cuda.current_stream(dev)
 
-        def step():
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+        def step(sample=False):
+            if sample:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
             rc = lib.dvsg_flow_warp_fwd(U.data_ptr(), flow.data_ptr(), out.data_ptr(), B, H, W, 3, 0, stream.cuda_stream)
-            e1.record(stream)
+            if sample:
+                e1.record(stream)
+                ev_pairs.append((e0, e1))
             _lib.check(rc, 'dvsg_flow_warp_fwd')
-            ev_pairs.append((e0, e1))
         kernel_name = 'warp_fwd_tile_kernel<TMODE_FLOW> (warp_fwd_tile.cu)'
         launches_per_step = 1
     else:
@@ -242,21 +244,25 @@ def run_ours(args, wl):
 
         bwd_pairs = []
 
-        def step():
+        def step(sample=False):
             target = coord + vec
             T = ops.tps_solve(coord, target)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+            if sample:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
             res = ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=train)
-            e1.record(stream)
-            ev_pairs.append((e0, e1))
+            if sample:
+                e1.record(stream)
+                ev_pairs.append((e0, e1))
             if train:
                 gU = torch.zeros_like(U)          # zero fill of grad_image: part of the step (counted in the 56 B/px)
-                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                b0.record(stream)
+                if sample:
+                    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    b0.record(stream)
                 _, gT, _, _ = ops.tps_warp_bwd(U, coord, T, (H, W), g_out, None, None, need_grad_U=True, want_grid_grad=True, grad_U_out=gU)
-                b1.record(stream)
-                bwd_pairs.append((b0, b1))
+                if sample:
+                    b1.record(stream)
+                    bwd_pairs.append((b0, b1))
                 ops.tps_solve_bwd(coord, gT)
             return res
         kernel_name = 'warp_fwd_tile_kernel<TMODE_TPS> (warp_fwd_tile.cu)'
@@ -278,8 +284,10 @@ def run_ours(args, wl):
     with ClockSampler(local) as clk:
         barrier()
         t0.record()
-        for _ in range(args.steps):
-            step()
+        # per-launch CUDA events on every 8th step only: an event pair between back-to-back kernels costs
+        # ~15 us of pipeline bubble, which would otherwise be charged to `value`
+        for i in range(args.steps):
+            step(sample=(i % 8 == 0))
         t1.record()
         barrier()
     elapsed_ms = t0.elapsed_time(t1)

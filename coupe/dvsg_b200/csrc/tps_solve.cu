@@ -10,8 +10,10 @@
 // 16x16 -- SURVEY.md H4); the fp64 elimination removes this kernel's share of that noise
 // at no measurable cost (the kernel is latency-bound).
 //
-//   N = pn+3 <= 32 : one warp per frame, augmented [A | rhs] in shared memory, lane i owns
-//                    row i; pivot search with warp shuffles.
+//   N = pn+3 <= 32 : mesh shared by the batch (the only way the reference is ever called, model.py:68):
+//                    one CTA eliminates [W | rhs of up to 32 frames] at once -- W is factorised once per
+//                    CTA instead of once per frame, all 256 threads work on every elimination step;
+//                    per-frame meshes: one warp per frame, lane i owns row i, pivot search with shuffles.
 //   N  > 32        : one CTA per DISTINCT system (1 when the mesh is shared by the batch --
 //                    SURVEY.md H6) runs Gauss-Jordan on [W | I] in a global-memory workspace,
 //                    then a second kernel applies W^-1 (or its transpose) to every frame.
@@ -111,6 +113,89 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) tps_solve_warp_kernel(const 
         for (int i = lane; i < 2 * pn; i += 32) out[(size_t)b * pn * 2 + i] = (float)a[(i >> 1) * SMALL_LD + N + (i & 1)];
     } else {
         for (int i = lane; i < 2 * N; i += 32) out[(size_t)b * 2 * N + i] = (float)a[(i % N) * SMALL_LD + N + (i / N)];
+    }
+}
+
+// ---- shared mesh, N <= 32: one CTA eliminates [A | rhs columns of SH_FRAMES frames] -----------------
+// Thread j owns COLUMN j of the augmented matrix for the whole elimination, so the update of a step touches
+// only thread-private data; warp 0 does the pivot search of the next column in parallel over rows.  Two CTA
+// barriers per elimination step.
+constexpr int SH_FRAMES = 32;                 // frames per CTA -> 64 right-hand-side columns
+constexpr int SH_THREADS = 128;               // >= SMALL_N + 2*SH_FRAMES columns
+constexpr int SH_LD = SMALL_N + 2 * SH_FRAMES + 1;   // odd pitch (doubles)
+
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(SH_THREADS) tps_solve_shared_kernel(const float* __restrict__ coord, const float* __restrict__ rhs_in,
+                                                                      float* __restrict__ out, int B, int pn) {
+    __shared__ double s_a[SMALL_N * SH_LD];
+    __shared__ double s_col[SMALL_N];
+    __shared__ double s_inv;
+    __shared__ float s_c[2 * SMALL_N];
+    __shared__ int s_piv;
+    const int tid = threadIdx.x;
+    const int N = pn + 3;
+    const int b0 = blockIdx.x * SH_FRAMES;
+    const int nf = min(SH_FRAMES, B - b0);
+    const int NC = N + 2 * nf;                  // columns: A, then (frame, component) pairs
+    for (int i = tid; i < 2 * pn; i += SH_THREADS) s_c[i] = coord[i];
+    __syncthreads();
+    if (tid < NC) {                             // thread = column
+        const int j = tid;
+        for (int i = 0; i < N; ++i) {
+            double v;
+            if (j < N) {
+                v = TRANSPOSED ? (double)tps_w_entry(s_c, pn, j, i) : (double)tps_w_entry(s_c, pn, i, j);
+            } else {
+                const int f = (j - N) >> 1, cc = (j - N) & 1, b = b0 + f;
+                if (TRANSPOSED) v = (double)rhs_in[((size_t)b * 2 + cc) * N + i];                  // grad_T[b][cc][i]
+                else v = i < pn ? (double)rhs_in[((size_t)b * pn + i) * 2 + cc] : 0.0;             // pad(target)
+            }
+            s_a[i * SH_LD + j] = v;
+        }
+    }
+    // Gauss-Jordan with partial pivoting (same pivot rule and operation order as the per-frame kernel)
+    for (int k = 0; k < N; ++k) {
+        __syncthreads();                        // column k is final
+        if (tid < 32) {
+            const double ck = tid < N ? s_a[tid * SH_LD + k] : 0.0;
+            double mag = (tid >= k && tid < N) ? fabs(ck) : -1.0;
+            int piv = tid;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double om = __shfl_xor_sync(0xffffffffu, mag, off);
+                const int op = __shfl_xor_sync(0xffffffffu, piv, off);
+                if (om > mag || (om == mag && op < piv)) { mag = om; piv = op; }
+            }
+            // factors of the rows AFTER the swap k <-> piv: row k's old value moves to slot piv
+            const double cpiv = __shfl_sync(0xffffffffu, ck, piv), ckk = __shfl_sync(0xffffffffu, ck, k);
+            if (tid < N) s_col[tid] = tid == k ? 0.0 : (tid == piv ? ckk : ck);
+            if (tid == 0) { s_piv = piv; s_inv = 1.0 / cpiv; }
+        }
+        __syncthreads();
+        if (tid >= k && tid < NC) {
+            const int j = tid, piv = s_piv;
+            const double inv = s_inv;
+            const double rowk_old = s_a[k * SH_LD + j];
+            const double pr = s_a[piv * SH_LD + j] * inv;      // scaled pivot row entry
+            if (piv != k) s_a[piv * SH_LD + j] = rowk_old;     // swap
+            s_a[k * SH_LD + j] = pr;
+            for (int i = 0; i < N; ++i) {
+                if (i != k) s_a[i * SH_LD + j] -= s_col[i] * pr;
+            }
+        }
+    }
+    __syncthreads();
+    // solution X[i][f][cc] = a[i][N + 2f + cc]
+    if (TRANSPOSED) {
+        for (int e = tid; e < nf * 2 * pn; e += SH_THREADS) {
+            const int f = e / (2 * pn), r = e - f * 2 * pn;          // r = i*2 + cc
+            out[(size_t)(b0 + f) * pn * 2 + r] = (float)s_a[(r >> 1) * SH_LD + N + 2 * f + (r & 1)];
+        }
+    } else {
+        for (int e = tid; e < nf * 2 * N; e += SH_THREADS) {
+            const int f = e / (2 * N), r = e - f * 2 * N;            // r = cc*N + i
+            out[(size_t)(b0 + f) * 2 * N + r] = (float)s_a[(r % N) * SH_LD + N + 2 * f + (r / N)];
+        }
     }
 }
 
@@ -230,6 +315,11 @@ static int solve_impl(const float* coord, long long stride, const float* rhs, fl
     DVSG_REQUIRE(coord && rhs && out, "%s: null pointer", what);
     DVSG_REQUIRE(stride == 0 || stride >= 2LL * pn, "%s: coord stride %lld < 2*pn", what, stride);
     const int N = pn + 3;
+    if (N <= SMALL_N && stride == 0) {
+        tps_solve_shared_kernel<TRANSPOSED><<<(B + SH_FRAMES - 1) / SH_FRAMES, SH_THREADS, 0, st>>>(coord, rhs, out, B, pn);
+        count_launch();
+        return check_launch("tps_solve_shared_kernel");
+    }
     if (N <= SMALL_N) {
         tps_solve_warp_kernel<TRANSPOSED><<<(B + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, st>>>(coord, stride, rhs, out, B, pn);
         count_launch();

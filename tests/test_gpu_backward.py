@@ -181,3 +181,20 @@ def test_backward_linearity_at_training_shape():
     gU = ops.tps_warp_bwd(U, coord, T, (H, W), ones, None, None)[0]
     _, _, _, mask = ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, want_mask=True)
     assert abs(float(gU.double().sum()) - 3 * float(mask.double().sum())) <= 1e-5 * 3 * float(mask.double().sum())
+
+
+def test_tps_solve_bwd_shared_mesh_matches_per_frame_solve():
+    """The batched shared-mesh kernel (one CTA eliminates [W^T | grad_T of 32 frames]) and the
+    one-warp-per-frame kernel run the same fp64 Gauss-Jordan: identical results."""
+    from coupe.dvsg_b200 import ops
+    rng = np.random.default_rng(5)
+    for n, B in ((4, 70), (5, 3)):
+        coord = tiled_mesh(n, n, B)
+        gT = rng.standard_normal((B, 2, n * n + 3)).astype(np.float32)
+        dense = ops.tps_solve_bwd(cu(coord), cu(gT)).cpu().numpy()
+        shared = ops.tps_solve_bwd(cu(coord[0]).unsqueeze(0).expand(B, -1, -1), cu(gT)).cpu().numpy()
+        assert np.abs(dense - shared).max() <= 1e-6 * np.abs(dense).max()
+        target = (coord + rng.uniform(-0.1, 0.1, coord.shape)).astype(np.float32)
+        Td = ops.tps_solve(cu(coord), cu(target)).cpu().numpy()
+        Ts = ops.tps_solve(cu(coord[0]).unsqueeze(0).expand(B, -1, -1), cu(target)).cpu().numpy()
+        assert np.abs(Td - Ts).max() <= 1e-6
