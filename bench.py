@@ -54,6 +54,7 @@ class ClockSampler(object):
 
     def __init__(self, device_index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period = float(os.environ.get("DVSG_CLOCK_PERIOD", "0.02"))
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -84,7 +85,7 @@ class ClockSampler(object):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def __enter__(self):
         if self.nv is not None:
@@ -302,7 +303,7 @@ def run_ours(args, wl):
     e2e = None
     if kind == 'tps' and wl['mesh'] ** 2 + 3 <= 32 and not args.no_e2e:
         Be = min(B, args.e2e_frames)
-        pipe = ops.HostPipeline(H, W, 3, wl['mesh'] ** 2, frames_per_chunk=max(1, min(8, Be // 4 or 1)), n_slots=3, device=local)
+        pipe = ops.HostPipeline(H, W, 3, wl['mesh'] ** 2, frames_per_chunk=max(1, min(args.e2e_chunk, Be)), n_slots=args.e2e_slots, device=local)
         U_h = torch.empty((Be, H, W, 3), dtype=torch.float32).pin_memory()
         U_h.copy_(U[:Be])
         out_h = torch.empty_like(U_h).pin_memory()
@@ -377,6 +378,8 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--e2e-frames', type=int, default=64)
+    ap.add_argument('--e2e-chunk', type=int, default=2, help='frames per staging chunk of the host pipeline')
+    ap.add_argument('--e2e-slots', type=int, default=4, help='device staging slots (streams) of the host pipeline')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

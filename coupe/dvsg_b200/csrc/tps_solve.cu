@@ -117,11 +117,13 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) tps_solve_warp_kernel(const 
 }
 
 // ---- shared mesh, N <= 32: one CTA eliminates [A | rhs columns of SH_FRAMES frames] -----------------
-// Thread j owns COLUMN j of the augmented matrix for the whole elimination, so the update of a step touches
-// only thread-private data; warp 0 does the pivot search of the next column in parallel over rows.  Two CTA
-// barriers per elimination step.
+// The kernel is latency-bound (a few thousand dependent instructions per warp), so the elimination update
+// is spread over SH_ROWG x 128 threads: thread (g, j) owns column j for the rows i = g, g+SH_ROWG, ...;
+// warp 0 does the pivot search of the next column in parallel over rows.  Three CTA barriers per step.
 constexpr int SH_FRAMES = 32;                 // frames per CTA -> 64 right-hand-side columns
-constexpr int SH_THREADS = 128;               // >= SMALL_N + 2*SH_FRAMES columns
+constexpr int SH_COLS = 128;                  // >= SMALL_N + 2*SH_FRAMES columns
+constexpr int SH_ROWG = 8;                    // row groups
+constexpr int SH_THREADS = SH_COLS * SH_ROWG;
 constexpr int SH_LD = SMALL_N + 2 * SH_FRAMES + 1;   // odd pitch (doubles)
 
 template <bool TRANSPOSED>
@@ -138,49 +140,73 @@ __global__ void __launch_bounds__(SH_THREADS) tps_solve_shared_kernel(const floa
     const int nf = min(SH_FRAMES, B - b0);
     const int NC = N + 2 * nf;                  // columns: A, then (frame, component) pairs
     for (int i = tid; i < 2 * pn; i += SH_THREADS) s_c[i] = coord[i];
-    __syncthreads();
-    if (tid < NC) {                             // thread = column
-        const int j = tid;
-        for (int i = 0; i < N; ++i) {
-            double v;
-            if (j < N) {
-                v = TRANSPOSED ? (double)tps_w_entry(s_c, pn, j, i) : (double)tps_w_entry(s_c, pn, i, j);
-            } else {
-                const int f = (j - N) >> 1, cc = (j - N) & 1, b = b0 + f;
-                if (TRANSPOSED) v = (double)rhs_in[((size_t)b * 2 + cc) * N + i];                  // grad_T[b][cc][i]
-                else v = i < pn ? (double)rhs_in[((size_t)b * pn + i) * 2 + cc] : 0.0;             // pad(target)
-            }
-            s_a[i * SH_LD + j] = v;
+    // right-hand sides: one coalesced pass over the contiguous block of this CTA's frames (independent loads
+    // in flight together, instead of N dependent global loads per column)
+    if (TRANSPOSED) {
+        const float* g = rhs_in + (size_t)b0 * 2 * N;                     // grad_T[b][cc][i]
+        for (int e = tid; e < nf * 2 * N; e += SH_THREADS) {
+            const int f = e / (2 * N), r = e - f * 2 * N, cc = r / N, i = r - cc * N;
+            s_a[i * SH_LD + N + 2 * f + cc] = (double)g[e];
         }
+    } else {
+        const float* g = rhs_in + (size_t)b0 * pn * 2;                    // target[b][i][cc], rows pn..N-1 are the zero pad
+        for (int e = tid; e < nf * 2 * N; e += SH_THREADS) {
+            const int f = e / (2 * N), r = e - f * 2 * N, i = r >> 1, cc = r & 1;
+            s_a[i * SH_LD + N + 2 * f + cc] = i < pn ? (double)g[(size_t)f * pn * 2 + r] : 0.0;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < N * N; e += SH_THREADS) {                       // the system matrix, all threads
+        const int i = e / N, j = e - i * N;
+        s_a[i * SH_LD + j] = TRANSPOSED ? (double)tps_w_entry(s_c, pn, j, i) : (double)tps_w_entry(s_c, pn, i, j);
     }
     // Gauss-Jordan with partial pivoting (same pivot rule and operation order as the per-frame kernel)
     for (int k = 0; k < N; ++k) {
         __syncthreads();                        // column k is final
         if (tid < 32) {
             const double ck = tid < N ? s_a[tid * SH_LD + k] : 0.0;
-            double mag = (tid >= k && tid < N) ? fabs(ck) : -1.0;
+            // pivot = largest |.| of column k (lowest row on ties); magnitudes compared in fp32: candidates that
+            // tie to fp32 precision are equally good pivots
+            float mag = (tid >= k && tid < N) ? fabsf((float)ck) : -1.0f;
             int piv = tid;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                const double om = __shfl_xor_sync(0xffffffffu, mag, off);
+                const float om = __shfl_xor_sync(0xffffffffu, mag, off);
                 const int op = __shfl_xor_sync(0xffffffffu, piv, off);
                 if (om > mag || (om == mag && op < piv)) { mag = om; piv = op; }
             }
             // factors of the rows AFTER the swap k <-> piv: row k's old value moves to slot piv
             const double cpiv = __shfl_sync(0xffffffffu, ck, piv), ckk = __shfl_sync(0xffffffffu, ck, k);
             if (tid < N) s_col[tid] = tid == k ? 0.0 : (tid == piv ? ckk : ck);
-            if (tid == 0) { s_piv = piv; s_inv = 1.0 / cpiv; }
+            if (tid == 0) {
+                // 1/pivot: fp32 reciprocal + two Newton steps in fp64 (full double precision without the
+                // ~100-instruction IEEE division on the critical path of every elimination step)
+                double r = (double)(1.0f / (float)cpiv);
+                r = r * (2.0 - cpiv * r);
+                r = r * (2.0 - cpiv * r);
+                r = r * (2.0 - cpiv * r);
+                s_piv = piv; s_inv = cpiv != 0.0 ? r : 1.0 / cpiv;
+            }
         }
         __syncthreads();
-        if (tid >= k && tid < NC) {
-            const int j = tid, piv = s_piv;
-            const double inv = s_inv;
-            const double rowk_old = s_a[k * SH_LD + j];
-            const double pr = s_a[piv * SH_LD + j] * inv;      // scaled pivot row entry
-            if (piv != k) s_a[piv * SH_LD + j] = rowk_old;     // swap
-            s_a[k * SH_LD + j] = pr;
-            for (int i = 0; i < N; ++i) {
-                if (i != k) s_a[i * SH_LD + j] -= s_col[i] * pr;
+        const int j = tid & (SH_COLS - 1), g = tid / SH_COLS;
+        const int piv = s_piv;
+        const bool act = j >= k && j < NC;
+        double pr = 0.0, rowk_old = 0.0;
+        if (act) {
+            rowk_old = s_a[k * SH_LD + j];
+            pr = s_a[piv * SH_LD + j] * s_inv;                 // scaled pivot row entry
+        }
+        __syncthreads();                                       // every row group has read rows k and piv
+        if (act) {
+            if (g == 0) {
+                if (piv != k) s_a[piv * SH_LD + j] = rowk_old; // swap
+                s_a[k * SH_LD + j] = pr;
+            }
+            for (int i = g; i < N; i += SH_ROWG) {
+                if (i == k) continue;
+                const double base = (i == piv && piv != k) ? rowk_old : s_a[i * SH_LD + j];
+                s_a[i * SH_LD + j] = base - s_col[i] * pr;
             }
         }
     }
