@@ -336,7 +336,7 @@ def run_ours(args, wl):
             # grad_image zero fill 12 + grad_image accumulate 12 + grad_x,y 8)
             bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_pairs) / max(len(bwd_pairs), 1)
             extra = {'forward_kernel': {'kernel': kernel_name, 'kernel_ms': kern_ms, 'achieved': achieved, 'algorithmic_bytes_per_px': 32}}
-            kernel_name, kern_ms, fwd_bpp = 'warp_bwd_kernel<BMODE_TPS> (warp_bwd.cu)', bwd_ms, 56
+            kernel_name, kern_ms, fwd_bpp = 'warp_bwd_tile_kernel<TMODE_TPS> (warp_bwd_tile.cu)', bwd_ms, 56
             achieved = pix_per_step * fwd_bpp / (kern_ms * 1e-3) / 1e9
         traffic = None
         try:

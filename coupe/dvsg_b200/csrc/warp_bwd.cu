@@ -323,6 +323,17 @@ __global__ void __launch_bounds__(BNT, 3) warp_bwd_kernel(const BwdParams p) {
 
 static float lin_step_b(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 static int g_bwd_merge = 1;
+static int g_bwd_notile = 0;   // experiments: force this generic kernel
+
+// fast path (warp_bwd_tile.cu): warp-autonomous 32x8 tiles, TMA staging + TMA reduce-add
+bool bwd_tile_path_ok(const void* src, const void* grad_src, int H, int W, int C, int oh, int ow, int pn_or_0);
+int bwd_tile_tps(const float* U, const float* coord, long long cstride, const float* T, const float* grad_out, const float* grad_x_in,
+                 const float* grad_y_in, float* grad_U, float* grad_T, float* grad_xs, float* grad_ys, int B, int H, int W, int oh, int ow,
+                 int pn, cudaStream_t st);
+int bwd_tile_given(const float* im, const float* x, const float* y, const float* grad_out, float* grad_im, float* grad_x, float* grad_y,
+                   int B, int H, int W, int oh, int ow, cudaStream_t st);
+int bwd_tile_flow(const float* im, const float* flow, const float* grad_out, float* grad_im, float* grad_flow, int B, int H, int W,
+                  cudaStream_t st);
 
 template <int MODE>
 static int launch_bwd(BwdParams p, cudaStream_t st) {
@@ -342,7 +353,7 @@ static int launch_bwd(BwdParams p, cudaStream_t st) {
 using namespace dvsg;
 
 extern "C" int dvsg_set_bwd_tuning(int merge) {
-    if (merge >= 0) g_bwd_merge = merge;
+    if (merge >= 0) { g_bwd_merge = merge & 1; g_bwd_notile = (merge >> 1) & 1; }   // bit 0: shuffle merge of the generic kernel, bit 1: force the generic kernel
     return DVSG_OK;
 }
 
@@ -363,6 +374,9 @@ extern "C" int dvsg_tps_warp_bwd(const float* U, const float* coord, long long c
             return DVSG_ERR_CUDA;
         }
     }
+    if (!g_bwd_notile && bwd_tile_path_ok(U, grad_U, H, W, C, oh, ow, pn))
+        return B == 0 ? DVSG_OK : bwd_tile_tps(U, coord, coord_batch_stride, T, grad_out, grad_x_in, grad_y_in, grad_U, grad_T, grad_xs, grad_ys,
+                                               B, H, W, oh, ow, pn, st);
     BwdParams p = {};
     p.src = U; p.grad_out = grad_out; p.grad_src = grad_U; p.grad_x = grad_xs; p.grad_y = grad_ys;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow;
@@ -378,6 +392,8 @@ extern "C" int dvsg_bilinear_bwd(const float* im, const float* x, const float* y
     DVSG_REQUIRE(B == 0 || (im && x && y && grad_out), "bilinear_bwd: null pointer");
     DVSG_REQUIRE((grad_x == nullptr) == (grad_y == nullptr), "bilinear_bwd: grad_x and grad_y go together");
     DVSG_REQUIRE((long long)(H + 2) * (W + 2) < (1LL << 31) / C, "bilinear_bwd: frame too large for int32 indexing");
+    if (!g_bwd_notile && bwd_tile_path_ok(im, grad_im, H, W, C, oh, ow, 0))
+        return B == 0 ? DVSG_OK : bwd_tile_given(im, x, y, grad_out, grad_im, grad_x, grad_y, B, H, W, oh, ow, (cudaStream_t)stream);
     BwdParams p = {};
     p.src = im; p.grad_out = grad_out; p.grad_src = grad_im; p.grad_x = grad_x; p.grad_y = grad_y;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow; p.x_in = x; p.y_in = y;
@@ -391,6 +407,8 @@ extern "C" int dvsg_flow_warp_bwd(const float* im, const float* flow, const floa
     DVSG_REQUIRE((reinterpret_cast<uintptr_t>(flow) & 7u) == 0 && (reinterpret_cast<uintptr_t>(grad_flow) & 7u) == 0,
                  "flow_warp_bwd: flow / grad_flow must be 8-byte aligned");
     DVSG_REQUIRE((long long)(H + 2) * (W + 2) < (1LL << 31) / C, "flow_warp_bwd: frame too large for int32 indexing");
+    if (!g_bwd_notile && bwd_tile_path_ok(im, grad_im, H, W, C, H, W, 0))
+        return B == 0 ? DVSG_OK : bwd_tile_flow(im, flow, grad_out, grad_im, grad_flow, B, H, W, (cudaStream_t)stream);
     BwdParams p = {};
     p.src = im; p.grad_out = grad_out; p.grad_src = grad_im; p.flow = flow; p.grad_flow = grad_flow;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = H; p.ow = W;

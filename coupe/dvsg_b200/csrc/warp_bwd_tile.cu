@@ -1,0 +1,576 @@
+// warp_bwd_tile.cu -- the sm_100a fast path of the backward warp (C == 3, 16-B aligned rows).
+//
+// Same skeleton as warp_fwd_tile.cu: every WARP is an autonomous pipeline over 32x8-pixel output
+// tiles (lane = column, 8 rows per thread) and recomputes the sampling coordinates (the TPS basis
+// was never stored).  What TF autodiff derives for the reference graphs:
+//
+//   grad x,y   d out / d x_pix from the four corners (read from the TMA-staged source footprint),
+//              chained to the caller's coordinates (A4: *W/2; ZP: *(W-1)/2 or 1, and the float
+//              clip_by_value mask -1 <= x_pix <= W)
+//   grad_im    scatter-add of w_k * grad_out over the four corners.  Float atomics on shared memory
+//              are CAS loops on this architecture, so the warp accumulates into a PRIVATE shared
+//              buffer shaped like its staged footprint with plain read-modify-write rounds: one
+//              round per (pixel row, corner class), inside a round every address is touched by one
+//              lane only (contributions of adjacent lanes that hit the same source pixel are merged
+//              with one shuffle first).  The buffer then goes to global memory with ONE TMA tensor
+//              reduce-add (cp.reduce.async.bulk.tensor .add.f32); out-of-frame parts -- the zero
+//              padding of the padded samplers -- are dropped by the hardware.
+//   grad_T     sum over pixels of grad(x_s, y_s) * basis: a second pass over the basis multiplies
+//              it with the per-pixel gradients in packed fp32x2, 8 control points x (x, y) = 16
+//              partial sums per lane are reduced across the warp with a 16-shuffle transpose
+//              reduction, accumulated per warp in shared memory, and issued as red.global once per
+//              warp at the end of its strip.
+// Tiles whose footprint does not fit a box, TPS tiles at the frame border and mappings that fold
+// (source columns not monotone along a row) take a per-pixel path with global gathers and
+// red.global.add.f32.  Atomic ordering makes grad_im reproducible to rounding only.
+#include "tile_common.cuh"
+
+namespace dvsg {
+
+struct BwdTileParams {
+    const float* src;        // [B,H,W,3]
+    const float* grad_out;   // [B,oh,ow,3]
+    float* grad_src;         // [B,H,W,3] accumulated (may be null)
+    float* grad_x;           // flat [B*oh*ow] w.r.t. the caller's coordinates (may be null)
+    float* grad_y;
+    float* grad_flow;        // [B,H,W,2] (FLOW, may be null)
+    int B, H, W, oh, ow;
+    const float* coord;
+    long long coord_stride;
+    const float* T;
+    const float* grad_x_in;  // optional upstream gradient on the returned x, y (TPS)
+    const float* grad_y_in;
+    float* grad_T;           // [B,2,pn+3], pre-zeroed by the launcher (may be null)
+    int pn;
+    float step_x, step_y;
+    const float* x_in;
+    const float* y_in;
+    const float* flow;
+    int n_tx, n_ty, segs, seg_len;
+    int bw[3], bh[3];
+};
+
+struct alignas(64) BwdTileMaps {
+    CUtensorMap src[NBOX];    // source frames, one map per box shape
+    CUtensorMap gsrc[NBOX];   // grad_src frames, same shapes (targets of the reduce-add)
+};
+
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, int x, int y, int z, uint32_t src_smem) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tmap), "r"(x), "r"(y), "r"(z), "r"(src_smem) : "memory");
+}
+
+// 16 partial sums per lane -> lane l ends with the warp total of v[(l >> 1) & 15] (16 shuffles)
+__device__ __forceinline__ float reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ---- per-pixel general path: global gathers, red.global scatter (full reference semantics) ---------
+template <int MODE>
+__device__ __noinline__ void bwd_general_pixel(float xp, float yp, int W, int H, const float* __restrict__ srcb, float* __restrict__ gsrcb,
+                                               float g0, float g1, float g2, float& dxp, float& dyp) {
+    int x0, x1, y0, y1;
+    float ax0, ax1, ay0, ay1;
+    bool v00 = true, v01 = true, v10 = true, v11 = true;   // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
+    if (MODE == TMODE_TPS) {
+        const int fx = t_floor_i32(xp), fy = t_floor_i32(yp);
+        x0 = min(max(fx, 0), W - 1);
+        x1 = min(max((int)((unsigned)fx + 1u), 0), W - 1);
+        y0 = min(max(fy, 0), H - 1);
+        y1 = min(max((int)((unsigned)fy + 1u), 0), H - 1);
+        ax1 = DVSG_SUB(t_u2f((unsigned)x1), xp); ax0 = DVSG_SUB(xp, t_u2f((unsigned)x0));
+        ay1 = DVSG_SUB(t_u2f((unsigned)y1), yp); ay0 = DVSG_SUB(yp, t_u2f((unsigned)y0));
+    } else {
+        const int qx0 = __float2int_rd(xp), qy0 = __float2int_rd(yp);     // in [0, W+1] / [0, H+1]
+        const int qx1 = min(qx0 + 1, W + 1), qy1 = min(qy0 + 1, H + 1);
+        const float x0f = t_u2f((unsigned)qx0), y0f = t_u2f((unsigned)qy0);
+        ax1 = DVSG_SUB(DVSG_ADD(x0f, 1.0f), xp); ax0 = DVSG_SUB(xp, x0f);
+        ay1 = DVSG_SUB(DVSG_ADD(y0f, 1.0f), yp); ay0 = DVSG_SUB(yp, y0f);
+        const bool vx0 = zp_valid(qx0, W), vx1 = zp_valid(qx1, W), vy0 = zp_valid(qy0, H), vy1 = zp_valid(qy1, H);
+        v00 = vx0 && vy0; v01 = vx1 && vy0; v10 = vx0 && vy1; v11 = vx1 && vy1;
+        x0 = min(max(qx0, 1) - 1, W - 1); x1 = max(min(qx1, W) - 1, 0);   // keep addresses legal
+        y0 = min(max(qy0, 1) - 1, H - 1); y1 = max(min(qy1, H) - 1, 0);
+    }
+    const float w00 = DVSG_MUL(ax1, ay1), w01 = DVSG_MUL(ax0, ay1), w10 = DVSG_MUL(ax1, ay0), w11 = DVSG_MUL(ax0, ay0);
+    const int a00 = (y0 * W + x0) * 3, a01 = (y0 * W + x1) * 3, a10 = (y1 * W + x0) * 3, a11 = (y1 * W + x1) * 3;
+    const float g[3] = {g0, g1, g2};
+    dxp = 0.0f; dyp = 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float i00 = v00 ? __ldg(srcb + a00 + ch) : 0.0f, i01 = v01 ? __ldg(srcb + a01 + ch) : 0.0f;
+        const float i10 = v10 ? __ldg(srcb + a10 + ch) : 0.0f, i11 = v11 ? __ldg(srcb + a11 + ch) : 0.0f;
+        dxp += g[ch] * (ay1 * (i01 - i00) + ay0 * (i11 - i10));
+        dyp += g[ch] * (ax1 * (i10 - i00) + ax0 * (i11 - i01));
+        if (gsrcb) {
+            if (v00) atomicAdd(gsrcb + a00 + ch, w00 * g[ch]);
+            if (v10) atomicAdd(gsrcb + a10 + ch, w10 * g[ch]);
+            if (v01) atomicAdd(gsrcb + a01 + ch, w01 * g[ch]);
+            if (v11) atomicAdd(gsrcb + a11 + ch, w11 * g[ch]);
+        }
+    }
+}
+
+// one read-modify-write round of the private accumulation buffer: contribution c (3 channels) of every lane
+// to address q; `dupn` lanes first hand their contribution to... receive the contribution of the next lane,
+// only run heads write
+__device__ __forceinline__ void rmw_round(float* __restrict__ q, float c0, float c1, float c2, bool head, bool dupn) {
+    const float n0 = __shfl_down_sync(0xffffffffu, c0, 1), n1 = __shfl_down_sync(0xffffffffu, c1, 1), n2 = __shfl_down_sync(0xffffffffu, c2, 1);
+    if (dupn) { c0 += n0; c1 += n1; c2 += n2; }
+    if (head) {
+        const float o0 = q[0], o1 = q[1], o2 = q[2];
+        q[0] = o0 + c0; q[1] = o1 + c1; q[2] = o2 + c2;
+    }
+    __syncwarp();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTileParams p, const __grid_constant__ BwdTileMaps maps) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long s_mbar[TNW];
+    __shared__ float s_lin[12];
+    __shared__ __align__(16) float s_yt[TR];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.H, W = p.W, oh = p.oh, ow = p.ow;
+    const int seg = blockIdx.x, b = blockIdx.z;
+    const int row0 = blockIdx.y * TR;
+    const int t_begin = seg * p.seg_len, t_end = min(t_begin + p.seg_len, p.n_tx);
+    const int pn4 = (p.pn + 3) & ~3, pn8 = (p.pn + 7) & ~7;
+    const bool want_gT = MODE == TMODE_TPS && p.grad_T != nullptr;
+
+    unsigned char* w_stage = smem + (size_t)warp * (2 * TSTAGE_BYTES);
+    unsigned char* w_acc = w_stage + TSTAGE_BYTES;
+    const unsigned char* recs = smem + (size_t)TNW * (2 * TSTAGE_BYTES);
+    float* w_gt = reinterpret_cast<float*>(smem + (size_t)TNW * (2 * TSTAGE_BYTES) + (size_t)pn8 * sizeof(TpsRec)) + warp * (2 * pn8 + 16);
+    const uint32_t stage_s = smem_u32(w_stage), acc_s = smem_u32(w_acc), mbar = smem_u32(&s_mbar[warp]);
+
+    // ---- prologue -----------------------------------------------------------------------------------
+    if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    if (tid < TR) s_yt[tid] = lin_coord(min(row0 + tid, oh - 1), p.step_y);
+    if (MODE == TMODE_TPS) {
+        const int N = p.pn + 3;
+        const float* Tb = p.T + (size_t)b * 2 * N;
+        const float* cb = p.coord + (size_t)b * p.coord_stride;
+        if (tid < 6) s_lin[tid] = __ldg(Tb + (tid < 3 ? tid : N + tid - 3));
+        TpsRec* wr = reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (2 * TSTAGE_BYTES));
+        for (int k = tid; k < pn8; k += TNT) {
+            const bool real = k < p.pn;
+            const float px = real ? __ldg(cb + 2 * k) : 0.0f, py = real ? __ldg(cb + 2 * k + 1) : 0.0f;
+            const float cx = real ? __ldg(Tb + 3 + k) * TLN2 : 0.0f, cy = real ? __ldg(Tb + N + 3 + k) * TLN2 : 0.0f;
+            float d[TR];
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+                const float dy = DVSG_SUB(lin_coord(min(row0 + r, oh - 1), p.step_y), py);
+                d[r] = real ? DVSG_MUL(dy, dy) : 1.0f;
+            }
+            TpsRec rec;
+            rec.pc = make_float4(-px, cx, cy, 0.0f);
+            rec.dya = make_float4(d[0], d[1], d[2], d[3]); rec.dyb = make_float4(d[4], d[5], d[6], d[7]);
+            wr[k] = rec;
+        }
+        if (want_gT) for (int i = lane; i < 2 * pn8 + 16; i += 32) w_gt[i] = 0.0f;
+    }
+    __syncthreads();
+
+    const float* srcb = p.src + (size_t)b * H * W * 3;
+    float* gsrcb = p.grad_src ? p.grad_src + (size_t)b * H * W * 3 : nullptr;
+    const float2 one2 = f2dup(1.0f);
+    unsigned phase = 0;
+    bool red_pending = false;
+
+    for (int t = t_begin + warp; t < t_end; t += TNW) {
+        const int col0 = t * TC;
+        const int col = min(col0 + lane, ow - 1);
+        const bool col_ok = col0 + lane < ow;
+        const float xt = lin_coord(col, p.step_x);
+
+        // grad_out of the thread's 8 pixels: issued first, the global-memory latency hides behind the basis
+        float gq[TR][3];
+#pragma unroll
+        for (int q = 0; q < TR; ++q) {
+            const int row = row0 + q;
+            const bool ok = col_ok && row < oh;
+            const float* gp = p.grad_out + (((size_t)b * oh + min(row, oh - 1)) * ow + col) * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) gq[q][ch] = ok ? __ldg(gp + ch) : 0.0f;
+        }
+
+        // ================= A: coordinates (identical arithmetic to the forward kernel) =================
+        float2 XP[TR / 2], YP[TR / 2];
+        unsigned clipmask = 0;      // padded modes: bit q = x inside the clip range, bit 8+q = y inside
+        if (MODE == TMODE_TPS) {
+            const float bx = fmaf(s_lin[1], xt, s_lin[0]), by = fmaf(s_lin[4], xt, s_lin[3]);
+            const float2 l2 = f2dup(s_lin[2]), l5 = f2dup(s_lin[5]);
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
+                XP[j] = __ffma2_rn(l2, ytp, f2dup(bx));
+                YP[j] = __ffma2_rn(l5, ytp, f2dup(by));
+            }
+            const float2 eps = f2dup(1e-6f);
+            const unsigned char* rp = recs;
+            for (int k = 0; k < pn4; k += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
+                    const float4 pc = *reinterpret_cast<const float4*>(rp);
+                    const float4 da = *reinterpret_cast<const float4*>(rp + 16);
+                    const float4 db = *reinterpret_cast<const float4*>(rp + 32);
+                    const float dx = DVSG_ADD(xt, pc.x);
+                    const float2 dxx = f2dup(DVSG_MUL(dx, dx));
+                    const float2 cfx = f2dup(pc.y), cfy = f2dup(pc.z);
+                    const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
+#pragma unroll
+                    for (int j = 0; j < TR / 2; ++j) {
+                        const float2 d2 = __fadd2_rn(dxx, dy[j]);
+                        const float2 tt = __fadd2_rn(d2, eps);
+                        const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
+                        XP[j] = __ffma2_rn(cfx, r, XP[j]);
+                        YP[j] = __ffma2_rn(cfy, r, YP[j]);
+                    }
+                }
+            }
+            const float2 wf = f2dup((float)W), hf = f2dup((float)H), half2 = f2dup(0.5f);
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                XP[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(XP[j], one2), wf), half2);
+                YP[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(YP[j], one2), hf), half2);
+            }
+        } else {
+            float xs[TR], ys[TR];
+#pragma unroll
+            for (int q = 0; q < TR; ++q) {
+                const int row = min(row0 + q, oh - 1);
+                const size_t i = ((size_t)b * oh + row) * ow + col;
+                if (MODE == TMODE_GIVEN) { xs[q] = __ldg(p.x_in + i); ys[q] = __ldg(p.y_in + i); }
+                else { const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + i); xs[q] = f.x; ys[q] = f.y; }
+            }
+            const float wf = (float)W, hf = (float)H;
+#pragma unroll
+            for (int q = 0; q < TR; ++q) {
+                if (MODE == TMODE_GIVEN) { xs[q] = zp_pix_from_norm(xs[q], W); ys[q] = zp_pix_from_norm(ys[q], H); }
+                else { xs[q] = DVSG_ADD((float)col, xs[q]); ys[q] = DVSG_ADD((float)min(row0 + q, oh - 1), ys[q]); }
+                // clip_by_value passes gradient on -1 <= x_pix <= W (inclusive)
+                if (xs[q] >= -1.0f && xs[q] <= wf) clipmask |= 1u << q;
+                if (ys[q] >= -1.0f && ys[q] <= hf) clipmask |= 256u << q;
+            }
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                XP[j] = f2(DVSG_ADD(fminf(fmaxf(xs[2 * j], -1.0f), wf), 1.0f), DVSG_ADD(fminf(fmaxf(xs[2 * j + 1], -1.0f), wf), 1.0f));
+                YP[j] = f2(DVSG_ADD(fminf(fmaxf(ys[2 * j], -1.0f), hf), 1.0f), DVSG_ADD(fminf(fmaxf(ys[2 * j + 1], -1.0f), hf), 1.0f));
+            }
+        }
+
+        // ================= F: footprint =================
+        const float xmn = min8n(XP), xmx = max8n(XP), ymn = min8n(YP), ymx = max8n(YP);
+        const bool sane = (fabsf(xmn) + fabsf(xmx)) + (fabsf(ymn) + fabsf(ymx)) < 4.0e6f;
+        int x_lo = sane ? floor_small(xmn) : -(1 << 30), x_hi = sane ? floor_small(xmx) + 1 : (1 << 30);
+        int y_lo = sane ? floor_small(ymn) : -(1 << 30), y_hi = sane ? floor_small(ymx) + 1 : (1 << 30);
+        x_lo = __reduce_min_sync(0xffffffffu, x_lo); x_hi = __reduce_max_sync(0xffffffffu, x_hi);
+        y_lo = __reduce_min_sync(0xffffffffu, y_lo); y_hi = __reduce_max_sync(0xffffffffu, y_hi);
+        const bool all_sane = x_lo > -(1 << 30);
+        bool interior;
+        int fx_lo, fx_hi, fy_lo, fy_hi;
+        if (MODE == TMODE_TPS) {
+            interior = x_lo >= 0 && x_hi <= W - 1 && y_lo >= 0 && y_hi <= H - 1;
+            fx_lo = x_lo; fx_hi = x_hi; fy_lo = y_lo; fy_hi = y_hi;
+        } else {
+            fx_lo = x_lo - 1; fx_hi = x_hi - 1; fy_lo = y_lo - 1; fy_hi = y_hi - 1;
+            // frame-border tiles (footprint reaching into the zero padding) take the per-pixel path: the TMA
+            // reduce-add faults on boxes that start outside the tensor
+            interior = fx_lo >= 0 && fy_lo >= 0 && fx_hi <= W - 1 && fy_hi <= H - 1;
+        }
+        const int fx0 = (fx_lo * 3) & ~3;
+        const int fw = (fx_hi + 1) * 3 - fx0, nrows = fy_hi - fy_lo + 1;
+        int box = -1;
+        if (fw <= p.bw[0]) box = nrows <= p.bh[0] ? 0 : (nrows <= p.bh[1] ? 1 : -1);
+        else if (fw <= p.bw[2] && nrows <= p.bh[2]) box = 2;
+        const int pitch = (box == 2 ? p.bw[2] : p.bw[0]) * 4;
+        const int box_rows = box == 0 ? p.bh[0] : (box == 1 ? p.bh[1] : p.bh[2]);
+        bool staged = box >= 0 && all_sane && interior && (long long)(fy_hi + 3) * pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
+        // the read-modify-write rounds need source columns that do not decrease along a row and never repeat
+        // more than twice (x scale >= 0.5, no fold): otherwise this tile takes the per-pixel path
+        float2 X0F[TR / 2], Y0F[TR / 2];
+        if (staged) {
+            bool mono = true;
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                X0F[j] = floor2_pos(XP[j]); Y0F[j] = floor2_pos(YP[j]);
+                const float a1 = __shfl_down_sync(0xffffffffu, X0F[j].x, 1), a2 = __shfl_down_sync(0xffffffffu, X0F[j].x, 2);
+                const float b1 = __shfl_down_sync(0xffffffffu, X0F[j].y, 1), b2 = __shfl_down_sync(0xffffffffu, X0F[j].y, 2);
+                mono = mono && (lane == 31 || (a1 >= X0F[j].x && b1 >= X0F[j].y)) && (lane >= 30 || (a2 > X0F[j].x && b2 > X0F[j].y));
+            }
+            staged = __all_sync(0xffffffffu, mono);
+        }
+
+        // ================= L: stage the source footprint, clear the accumulation buffer =================
+        if (red_pending) {                 // the previous tile's reduce-add must have read the accumulation buffer
+            if (lane == 0) bulk_wait_read0();
+            red_pending = false;
+        }
+        __syncwarp();
+        if (staged) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(mbar, (unsigned)(pitch * box_rows));
+                tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
+            }
+            if (gsrcb) {
+                float4* z = reinterpret_cast<float4*>(w_acc);
+                const int n16 = pitch * box_rows / 16;
+                for (int i = lane; i < n16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            mbar_wait(mbar, phase); phase ^= 1u;
+        }
+
+        // ================= G: d out / d coordinates, scatter of grad_im =================
+        float2 GX[TR / 2], GY[TR / 2];     // gradient w.r.t. the sampler's pixel-space coordinate, then chained
+        if (staged) {
+            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
+            const float2 m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                const float2 xp = XP[j], yp = YP[j], x0f = X0F[j], y0f = Y0F[j];
+                const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
+                const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
+                const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
+                const float2 o00 = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
+                const int ka = __float_as_int(o00.x) & 0x7fffff, kb = __float_as_int(o00.y) & 0x7fffff;
+                const float* __restrict__ pa = reinterpret_cast<const float*>(sb + ka);
+                const float* __restrict__ pb = reinterpret_cast<const float*>(sb + kb);
+                const float* __restrict__ qa = reinterpret_cast<const float*>(sb + ka + pitch);
+                const float* __restrict__ qb = reinterpret_cast<const float*>(sb + kb + pitch);
+                float2 g[3], dx = f2dup(0.0f), dy = f2dup(0.0f);
+                float2 c00[3], c01[3], c10[3], c11[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    g[ch] = f2(gq[2 * j][ch], gq[2 * j + 1][ch]);
+                    const float2 i00 = f2(pa[ch], pb[ch]), i01 = f2(pa[3 + ch], pb[3 + ch]);
+                    const float2 i10 = f2(qa[ch], qb[ch]), i11 = f2(qa[3 + ch], qb[3 + ch]);
+                    const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
+                    const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
+                    dx = __ffma2_rn(g[ch], ux, dx);
+                    dy = __ffma2_rn(g[ch], uy, dy);
+                    c00[ch] = __fmul2_rn(w00, g[ch]); c01[ch] = __fmul2_rn(w01, g[ch]);
+                    c10[ch] = __fmul2_rn(w10, g[ch]); c11[ch] = __fmul2_rn(w11, g[ch]);
+                }
+                GX[j] = dx; GY[j] = dy;
+                if (gsrcb) {
+                    // accumulation buffer = staging buffer + TSTAGE_BYTES, same layout
+                    float* __restrict__ aa = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pa) + TSTAGE_BYTES));
+                    float* __restrict__ ab = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pb) + TSTAGE_BYTES));
+                    float* __restrict__ ca = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(qa) + TSTAGE_BYTES));
+                    float* __restrict__ cb2 = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(qb) + TSTAGE_BYTES));
+                    {   // row a: the four corner classes share one duplicate pattern (x1 = x0+1, y1 = y0+1)
+                        const int nk = __shfl_down_sync(0xffffffffu, ka, 1), pk = __shfl_up_sync(0xffffffffu, ka, 1);
+                        const bool head = lane == 0 || pk != ka, dupn = lane != 31 && nk == ka;
+                        rmw_round(aa, c00[0].x, c00[1].x, c00[2].x, head, dupn);
+                        rmw_round(aa + 3, c01[0].x, c01[1].x, c01[2].x, head, dupn);
+                        rmw_round(ca, c10[0].x, c10[1].x, c10[2].x, head, dupn);
+                        rmw_round(ca + 3, c11[0].x, c11[1].x, c11[2].x, head, dupn);
+                    }
+                    {   // row b
+                        const int nk = __shfl_down_sync(0xffffffffu, kb, 1), pk = __shfl_up_sync(0xffffffffu, kb, 1);
+                        const bool head = lane == 0 || pk != kb, dupn = lane != 31 && nk == kb;
+                        rmw_round(ab, c00[0].y, c00[1].y, c00[2].y, head, dupn);
+                        rmw_round(ab + 3, c01[0].y, c01[1].y, c01[2].y, head, dupn);
+                        rmw_round(cb2, c10[0].y, c10[1].y, c10[2].y, head, dupn);
+                        rmw_round(cb2 + 3, c11[0].y, c11[1].y, c11[2].y, head, dupn);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < TR; ++q) {
+                const float xp = (q & 1) ? XP[q >> 1].y : XP[q >> 1].x, yp = (q & 1) ? YP[q >> 1].y : YP[q >> 1].x;
+                const int row = row0 + q;
+                const bool ok = col_ok && row < oh;
+                float dxp = 0.0f, dyp = 0.0f;
+                if (ok) bwd_general_pixel<MODE>(xp, yp, W, H, srcb, gsrcb, gq[q][0], gq[q][1], gq[q][2], dxp, dyp);
+                if (q & 1) { GX[q >> 1].y = dxp; GY[q >> 1].y = dyp; } else { GX[q >> 1].x = dxp; GY[q >> 1].x = dyp; }
+            }
+        }
+
+        // ================= chain to the caller's coordinates, write grad x / y / flow =================
+#pragma unroll
+        for (int j = 0; j < TR / 2; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = 2 * j + h, row = row0 + q;
+                const bool ok = col_ok && row < oh;
+                const size_t opix = ((size_t)b * oh + min(row, oh - 1)) * ow + col;
+                float gx = h ? GX[j].y : GX[j].x, gy = h ? GY[j].y : GY[j].x;
+                if (MODE == TMODE_TPS) {
+                    gx = gx * (float)W * 0.5f;                     // x_pix = (x+1)*W/2
+                    gy = gy * (float)H * 0.5f;
+                    if (ok && p.grad_x_in) { gx += __ldg(p.grad_x_in + opix); gy += __ldg(p.grad_y_in + opix); }
+                    if (!ok) { gx = 0.0f; gy = 0.0f; }
+                    if (ok && p.grad_x) { p.grad_x[opix] = gx; p.grad_y[opix] = gy; }
+                    if (h) { GX[j].y = gx; GY[j].y = gy; } else { GX[j].x = gx; GY[j].x = gy; }
+                } else {
+                    gx = (clipmask >> q) & 1u ? gx : 0.0f;
+                    gy = (clipmask >> (8 + q)) & 1u ? gy : 0.0f;
+                    if (ok) {
+                        if (MODE == TMODE_GIVEN) {
+                            if (p.grad_x) {
+                                p.grad_x[opix] = gx * ((float)W - 1.0f) * 0.5f;   // x_pix = (x+1)/2*(W-1)
+                                p.grad_y[opix] = gy * ((float)H - 1.0f) * 0.5f;
+                            }
+                        } else if (p.grad_flow) {
+                            reinterpret_cast<float2*>(p.grad_flow)[opix] = make_float2(gx, gy);
+                        }
+                    }
+                }
+            }
+        }
+
+        // ================= S: accumulation buffer -> grad_im with one TMA tensor reduce-add =================
+        if (staged && gsrcb) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_reduce_add_3d(&maps.gsrc[box], fx0, fy_lo, b, acc_s);
+                bulk_commit();
+            }
+            red_pending = true;
+        }
+
+        // ================= P2: grad_T = sum over pixels of grad(x_s, y_s) * (1, x_t, y_t, r_1..r_pn) =================
+        if (want_gT) {
+            const float2 eps = f2dup(1e-6f);
+            const unsigned char* rp = recs;
+            for (int k = 0; k < pn8; k += 8) {
+                float v[16];
+#pragma unroll
+                for (int u = 0; u < 8; ++u, rp += sizeof(TpsRec)) {
+                    const float4 pc = *reinterpret_cast<const float4*>(rp);
+                    const float4 da = *reinterpret_cast<const float4*>(rp + 16);
+                    const float4 db = *reinterpret_cast<const float4*>(rp + 32);
+                    const float dx = DVSG_ADD(xt, pc.x);
+                    const float2 dxx = f2dup(DVSG_MUL(dx, dx));
+                    const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
+                    float2 sx = f2dup(0.0f), sy = f2dup(0.0f);
+#pragma unroll
+                    for (int j = 0; j < TR / 2; ++j) {
+                        const float2 d2 = __fadd2_rn(dxx, dy[j]);
+                        const float2 tt = __fadd2_rn(d2, eps);
+                        const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
+                        sx = __ffma2_rn(GX[j], r, sx);
+                        sy = __ffma2_rn(GY[j], r, sy);
+                    }
+                    v[2 * u] = sx.x + sx.y;
+                    v[2 * u + 1] = sy.x + sy.y;
+                }
+                const float tot = reduce16(v, lane);                  // lane l: entry (l >> 1) of this chunk
+                if ((lane & 1) == 0) w_gt[2 * k + (lane >> 1)] += tot;
+            }
+            {   // affine part: (1, x_t, y_t)
+                float v[16];
+                float2 sx = f2dup(0.0f), sy = f2dup(0.0f), sxy = f2dup(0.0f), syy = f2dup(0.0f);
+#pragma unroll
+                for (int j = 0; j < TR / 2; ++j) {
+                    const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
+                    sx = __fadd2_rn(sx, GX[j]); sy = __fadd2_rn(sy, GY[j]);
+                    sxy = __ffma2_rn(GX[j], ytp, sxy); syy = __ffma2_rn(GY[j], ytp, syy);
+                }
+                const float ax = sx.x + sx.y, ay = sy.x + sy.y;
+                v[0] = ax; v[1] = ax * xt; v[2] = sxy.x + sxy.y; v[3] = ay; v[4] = ay * xt; v[5] = syy.x + syy.y;
+#pragma unroll
+                for (int i = 6; i < 16; ++i) v[i] = 0.0f;
+                const float tot = reduce16(v, lane);
+                if ((lane & 1) == 0) w_gt[2 * pn8 + (lane >> 1)] += tot;
+            }
+            __syncwarp();
+        }
+    }
+    if (red_pending && lane == 0) bulk_wait_read0();   // shared memory must outlive the reduce's reads
+
+    // ---- grad_T of this warp's tiles -> global ---------------------------------------------------------
+    if (want_gT) {
+        __syncwarp();
+        const int N = p.pn + 3;
+        float* gTb = p.grad_T + (size_t)b * 2 * N;
+        for (int i = lane; i < 2 * pn8; i += 32) {
+            const int k = i >> 1, xy = i & 1;               // entry 2*k + xy
+            if (k < p.pn) atomicAdd(gTb + xy * N + 3 + k, w_gt[i] * TLN2);
+        }
+        if (lane < 6) atomicAdd(gTb + (lane / 3) * N + lane % 3, w_gt[2 * pn8 + lane]);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+static float btile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
+
+bool bwd_tile_path_ok(const void* src, const void* grad_src, int H, int W, int C, int oh, int ow, int pn_or_0) {
+    return C == 3 && W % 4 == 0 && ow >= TC && oh >= TR && aligned16(src) && (grad_src == nullptr || aligned16(grad_src)) &&
+           W < (1 << 20) && H < (1 << 20) && (long long)H * W < (1LL << 28) && (long long)oh * ow < (1LL << 28) && pn_or_0 <= TKC;
+}
+
+template <int MODE>
+static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
+    if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
+    p.n_tx = (p.ow + TC - 1) / TC;
+    p.n_ty = (p.oh + TR - 1) / TR;
+    const long long strips = (long long)p.B * p.n_ty;
+    const int target = 148 * 4 * 4;
+    int segs = 1;
+    if (strips < target) segs = (int)min((long long)max(p.n_tx / TNW, 1), (target + strips - 1) / strips);
+    p.seg_len = (p.n_tx + segs - 1) / segs;
+    p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
+    DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "bwd tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
+    BwdTileMaps maps;
+    for (int i = 0; i < NBOX; ++i) {
+        p.bw[i] = min(box_w(i), 3 * p.W);
+        p.bh[i] = min(box_h(i), p.H);
+        int rc = encode_frames(&maps.src[i], p.src, p.B, p.H, p.W, p.bw[i], p.bh[i]);
+        if (rc) return rc;
+        rc = encode_frames(&maps.gsrc[i], p.grad_src ? p.grad_src : p.src, p.B, p.H, p.W, p.bw[i], p.bh[i]);
+        if (rc) return rc;
+    }
+    const int pn8 = MODE == TMODE_TPS ? (p.pn + 7) & ~7 : 0;
+    const size_t smem = (size_t)TNW * 2 * TSTAGE_BYTES + (size_t)pn8 * sizeof(TpsRec) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float);
+    auto k = warp_bwd_tile_kernel<MODE>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<dim3((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B), TNT, smem, st>>>(p, maps);
+    count_launch();
+    return check_launch("warp_bwd_tile_kernel");
+}
+
+int bwd_tile_tps(const float* U, const float* coord, long long cstride, const float* T, const float* grad_out, const float* grad_x_in,
+                 const float* grad_y_in, float* grad_U, float* grad_T, float* grad_xs, float* grad_ys, int B, int H, int W, int oh, int ow,
+                 int pn, cudaStream_t st) {
+    BwdTileParams p = {};
+    p.src = U; p.grad_out = grad_out; p.grad_src = grad_U; p.grad_x = grad_xs; p.grad_y = grad_ys;
+    p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow;
+    p.coord = coord; p.coord_stride = cstride; p.T = T; p.pn = pn;
+    p.grad_x_in = grad_x_in; p.grad_y_in = grad_y_in; p.grad_T = grad_T;
+    p.step_x = btile_lin_step(ow); p.step_y = btile_lin_step(oh);
+    return launch_bwd_tile<TMODE_TPS>(p, st);
+}
+
+int bwd_tile_given(const float* im, const float* x, const float* y, const float* grad_out, float* grad_im, float* grad_x, float* grad_y,
+                   int B, int H, int W, int oh, int ow, cudaStream_t st) {
+    BwdTileParams p = {};
+    p.src = im; p.grad_out = grad_out; p.grad_src = grad_im; p.grad_x = grad_x; p.grad_y = grad_y;
+    p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow; p.x_in = x; p.y_in = y;
+    return launch_bwd_tile<TMODE_GIVEN>(p, st);
+}
+
+int bwd_tile_flow(const float* im, const float* flow, const float* grad_out, float* grad_im, float* grad_flow, int B, int H, int W,
+                  cudaStream_t st) {
+    BwdTileParams p = {};
+    p.src = im; p.grad_out = grad_out; p.grad_src = grad_im; p.flow = flow; p.grad_flow = grad_flow;
+    p.B = B; p.H = H; p.W = W; p.oh = H; p.ow = W;
+    return launch_bwd_tile<TMODE_FLOW>(p, st);
+}
+
+}  // namespace dvsg

@@ -30,108 +30,9 @@
 //             global memory: footprints larger than the biggest box, non-finite coordinates
 // Nothing but the frames themselves touches HBM: the [B, pn+3, h*w] basis and the sampling
 // grid of the reference never exist (x, y are written only when the caller asks).
-#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
-
-#include "dvsg_common.cuh"
-#include "sampler_math.cuh"
+#include "tile_common.cuh"
 
 namespace dvsg {
-
-enum { TMODE_TPS = 0, TMODE_GIVEN = 1, TMODE_FLOW = 2, TMODE_HOMOG = 3 };
-
-constexpr int TR = 8;                         // rows per tile = pixels per thread
-constexpr int TC = 32;                        // columns per tile = lanes
-constexpr int TNW = 4;                        // warps per CTA
-constexpr int TNT = TNW * 32;
-constexpr int TKC = 256;                      // control points resident in shared memory
-constexpr int TOUT_BYTES = TR * TC * 12;      // output tile, 3072 B
-constexpr float TLN2 = 0.6931471805599453f;
-constexpr float MAGIC23 = 8388608.0f;         // 2^23
-constexpr float MAGIC15 = 12582912.0f;        // 1.5 * 2^23
-
-struct TileParams {
-    const float* src;
-    float* out;
-    float* x_out;
-    float* y_out;
-    float* mask_out;
-    int B, H, W, oh, ow;
-    const float* coord;
-    long long coord_stride;
-    const float* T;
-    int pn;
-    float step_x, step_y;
-    const float* x_in;
-    const float* y_in;
-    const float* flow;
-    const float* theta;
-    int projective;
-    int stage_bytes;      // per-warp staging buffer
-    int dbg;
-    int bw[3], bh[3];     // staging boxes (floats x rows) of the three source tensor maps, clamped to the frame
-    int n_tx, n_ty;       // tiles per strip / strips per frame
-    int segs, seg_len;    // CTAs per strip, tiles per CTA
-};
-
-// staging boxes (floats wide x rows): pitch = 512 or 640 B keeps the row pitch a multiple of 128 B, so the
-// bank of a corner depends on its column only (3*x mod 32), whatever row each lane reads
-constexpr int NBOX = 3;
-constexpr int BOX_W0 = 128, BOX_W2 = 160;     // box 0: 128 x 10, box 1: 128 x 13, box 2: 160 x 10
-constexpr int BOX_H0 = 10, BOX_H1 = 13, BOX_H2 = 10;
-constexpr int TSTAGE_BYTES = 6656;            // largest box
-__host__ __device__ constexpr int box_w(int i) { return i == 2 ? BOX_W2 : BOX_W0; }
-__host__ __device__ constexpr int box_h(int i) { return i == 0 ? BOX_H0 : (i == 1 ? BOX_H1 : BOX_H2); }
-
-struct alignas(64) TileMaps {
-    CUtensorMap src[NBOX];   // source [B][H][3W] floats, one map per box shape
-    CUtensorMap out;         // output [B][oh][3ow] floats, box = one 96 x 8 tile
-};
-
-struct __align__(16) TpsRec {   // one control point, 48 B, read with three broadcast LDS.128
-    float4 pc;    // (-px, cx ln2, cy ln2, 0)
-    float4 dya;   // (y_t(row0 + r) - py)^2, r = 0..3
-    float4 dyb;   // r = 4..7
-};
-
-// ---- small helpers -----------------------------------------------------------------------------
-__device__ __forceinline__ float t_lds(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void t_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ float min3n(float a, float b, float c) { float r; asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
-__device__ __forceinline__ float max3n(float a, float b, float c) { float r; asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
-__device__ __forceinline__ float min2n(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float max2n(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 f2dup(float a) { return make_float2(a, a); }
-__device__ __forceinline__ float min8n(const float2 (&v)[4]) { return min2n(min3n(v[0].x, v[0].y, v[1].x), min3n(v[1].y, v[2].x, min3n(v[2].y, v[3].x, v[3].y))); }
-__device__ __forceinline__ float max8n(const float2 (&v)[4]) { return max2n(max3n(v[0].x, v[0].y, v[1].x), max3n(v[1].y, v[2].x, max3n(v[2].y, v[3].x, v[3].y))); }
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }   // per-lane IEEE a - b
-// ptxas (CUDA 12.9) contracts mul.rn.f32x2 feeding add/fma.rn.f32x2 into one FFMA2 although both carry
-// .rn, which would fuse roundings the reference keeps apart: sums of products use scalar rounded adds.
-__device__ __forceinline__ float2 add2s(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-// per-lane add rounded toward -infinity (FADD2.RM): x +rm 2^23 drops the fraction downwards = floor
-__device__ __forceinline__ float2 add2_rm(float2 a, float2 b) {
-    float2 r;
-    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rm.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 floor2_pos(float2 x) { return __fadd2_rn(add2_rm(x, f2dup(MAGIC23)), f2dup(-MAGIC23)); }   // 0 <= x < 2^22
-__device__ __forceinline__ float2 floor2_any(float2 x) { return __fadd2_rn(add2_rm(x, f2dup(MAGIC15)), f2dup(-MAGIC15)); }   // |x| < 2^22
-__device__ __forceinline__ int floor_small(float x) { return __float_as_int(__fadd_rd(x, MAGIC15)) - 0x4B400000; }             // |x| < 2^22
-__device__ __forceinline__ float t_u2f(unsigned v) { return __uint_as_float(0x4B000000u | v) - MAGIC23; }   // v < 2^23, exact
-__device__ __forceinline__ int t_floor_i32(float f) {
-    // floor + the reference's CPU cast semantics (out-of-range / NaN -> INT_MIN)
-    const int v = __float2int_rd(f);
-    return fabsf(f) < 2147483648.0f ? v : (int)0x80000000;
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int x, int y, int z, uint32_t mbar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst_smem), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const void* tmap, int x, int y, int z, uint32_t src_smem) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
-                 ::"l"(tmap), "r"(x), "r"(y), "r"(z), "r"(src_smem) : "memory");
-}
 
 // ---- per-pixel general gather: full reference semantics --------------------------------------------
 // xp, yp: TPS -> pixel-space coordinate of the A4 sampler; other modes -> clipped+1 coordinate in the
@@ -509,35 +410,6 @@ static int g_tile_minb = 5;                // resident CTAs per SM the kernel is
 bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0) {
     return C == 3 && W % 4 == 0 && ow % 4 == 0 && ow >= TC && oh >= TR && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
            (long long)H * W < (1LL << 28) && (long long)oh * ow < (1LL << 28) && pn_or_0 <= TKC;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return reinterpret_cast<EncodeTiledFn>(f);
-    }();
-    return fn;
-}
-
-// [B][rows][3*cols] fp32 tensor, box = bw floats x bh rows x 1 frame, zero fill outside the tensor
-static int encode_frames(CUtensorMap* m, const float* base, int B, int rows, int cols, int bw, int bh) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { set_error("tile kernel: cuTensorMapEncodeTiled is not available from this driver"); return DVSG_ERR_CUDA; }
-    const cuuint64_t dims[3] = {(cuuint64_t)cols * 3, (cuuint64_t)rows, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)cols * 12, (cuuint64_t)rows * cols * 12};
-    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("tile kernel: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DVSG_ERR_CUDA; }
-    return DVSG_OK;
 }
 
 template <int MODE>

@@ -114,4 +114,5 @@ def main():
         rec('torch copy 398MB', ms, pxf, 24)
 
 
-main()
+if __name__ == '__main__':
+    main()
