@@ -38,7 +38,7 @@ namespace dvsg {
 // xp, yp: TPS -> pixel-space coordinate of the A4 sampler; other modes -> clipped+1 coordinate in the
 // zero-padded frame.  Corners come straight from global memory.
 template <int MODE>
-__device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, const float* __restrict__ srcb, uint32_t oaddr, float* mask_ptr) {
+__device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, const float* __restrict__ srcb, float* __restrict__ optr, float* mask_ptr) {
     int x0, x1, y0, y1;
     float ax0, ax1, ay0, ay1;
     bool v00 = true, v01 = true, v10 = true, v11 = true;   // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
@@ -81,7 +81,7 @@ __device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, con
         float o;
         if (MODE == TMODE_TPS) o = DVSG_ADD(DVSG_ADD(DVSG_ADD(t00, t10), t01), t11);   // ThinPlateSpline.py:89
         else o = DVSG_ADD(DVSG_ADD(DVSG_ADD(t00, t01), t10), t11);                       // spatial_transformer.py:562
-        t_sts(oaddr + 4 * ch, o);
+        optr[ch] = o;
     }
 }
 
@@ -147,6 +147,26 @@ __device__ __forceinline__ void gather_pair(const float2 xp, const float2 yp, co
     }
 }
 
+// gather + blend of rows (2J, 2J+1) of the thread's column, whichever variant the tile takes (warp-uniform)
+template <int MODE, int J>
+__device__ __forceinline__ void tile_pair(const bool staged, const bool interior, const float2 xp, const float2 yp, const int pitch,
+                                          const unsigned char* __restrict__ sb, float* __restrict__ ot, const float wm1, const float hm1,
+                                          const int W, const int H, const float* __restrict__ srcb, float* mask_col, const int ow,
+                                          const bool ok_a, const bool ok_b) {
+    if (staged) {
+        float2 ms = f2dup(0.0f);
+        if (interior) gather_pair<MODE, false, J>(xp, yp, pitch, sb, ot, ms, wm1, hm1);
+        else if (MODE == TMODE_TPS) gather_pair<MODE, true, J>(xp, yp, pitch, sb, ot, ms, wm1, hm1);
+        if (MODE == TMODE_TPS && mask_col) {
+            if (ok_a) mask_col[(2 * J) * ow] = ms.x;
+            if (ok_b) mask_col[(2 * J + 1) * ow] = ms.y;
+        }
+    } else {
+        general_pixel<MODE>(xp.x, yp.x, W, H, srcb, ot + (2 * J) * TC * 3, (mask_col && ok_a) ? mask_col + (2 * J) * ow : nullptr);
+        general_pixel<MODE>(xp.y, yp.y, W, H, srcb, ot + (2 * J + 1) * TC * 3, (mask_col && ok_b) ? mask_col + (2 * J + 1) * ow : nullptr);
+    }
+}
+
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TileParams p, const __grid_constant__ TileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -164,7 +184,7 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
     unsigned char* w_stage = w_out + TOUT_BYTES;
     const unsigned char* recs = smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes);
     const uint32_t out_s = smem_u32(w_out), stage_s = smem_u32(w_stage), mbar = smem_u32(&s_mbar[warp]);
-    const int pn4 = (p.pn + 3) & ~3;                 // table padded with zero-weight records to a multiple of 4
+    const int pn8 = (p.pn + 7) & ~7;                 // table padded with zero-weight records to a multiple of 8
 
     // ---- prologue: mbarriers, per-strip tables (the only CTA barrier of the kernel) -----------------
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
@@ -175,7 +195,7 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
         const float* cb = p.coord + (size_t)b * p.coord_stride;
         if (tid < 6) s_lin[tid] = __ldg(Tb + (tid < 3 ? tid : N + tid - 3));
         TpsRec* wr = reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes));
-        for (int k = tid; k < pn4; k += TNT) {
+        for (int k = tid; k < pn8; k += TNT) {
             const bool real = k < p.pn;
             const float px = real ? __ldg(cb + 2 * k) : 0.0f, py = real ? __ldg(cb + 2 * k + 1) : 0.0f;
             const float cx = real ? __ldg(Tb + 3 + k) * TLN2 : 0.0f, cy = real ? __ldg(Tb + N + 3 + k) * TLN2 : 0.0f;
@@ -198,84 +218,103 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
 
     const float* srcb = p.src + (size_t)b * H * W * 3;
     const float2 one2 = f2dup(1.0f);
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const bool want_mask = MODE == TMODE_TPS && p.mask_out != nullptr;
+    float* const ot = reinterpret_cast<float*>(w_out) + lane * 3;      // this lane's column of the output tile
     unsigned phase = 0;
     bool out_pending = false;
 
-    for (int t = t_begin + warp; t < t_end; t += TNW) {
-        const int col0 = t * TC;
-        const int col = min(col0 + lane, ow - 1);      // columns / rows past the edge are duplicates of the edge pixel
-        const bool col_ok = col0 + lane < ow;
+    struct Tile {               // warp-uniform description of a tile whose coordinates are known
+        int col0, col;
+        bool col_ok, staged, interior;
+        int pitch;
+        const unsigned char* sb;
+    };
 
-        // ================= A: coordinates of the thread's 8 pixels =================
-        // XP/YP[j] = rows (2j, 2j+1).  TPS: A4 pixel-space coordinate.  Others: clipped+1 padded-frame coordinate.
-        float2 XP[TR / 2], YP[TR / 2];
+    // ---- pieces of the per-tile work -----------------------------------------------------------------
+    // TPS basis of all (padded) control points, accumulated into X, Y (rows (2j, 2j+1) in lane pairs)
+    auto basis = [&](const float xt, float2 (&X)[TR / 2], float2 (&Y)[TR / 2]) {
+        const float2 eps = f2dup(1e-6f);
+        const unsigned char* rp = recs;
+        for (int k = 0; k < pn8; k += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
+                const float4 pc = *reinterpret_cast<const float4*>(rp);
+                const float4 da = *reinterpret_cast<const float4*>(rp + 16);
+                const float4 db = *reinterpret_cast<const float4*>(rp + 32);
+                // scalar, separately rounded (x_t - px)^2 as in the reference (a packed mul feeding the packed
+                // add below would be contracted into FFMA2 by ptxas); the packed ops take scalars as broadcast operands
+                const float dx = DVSG_ADD(xt, pc.x);
+                const float2 dxx = f2dup(DVSG_MUL(dx, dx));
+                const float2 cfx = f2dup(pc.y), cfy = f2dup(pc.z);
+                const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
+#pragma unroll
+                for (int j = 0; j < TR / 2; ++j) {
+                    const float2 d2 = __fadd2_rn(dxx, dy[j]);
+                    const float2 tt = __fadd2_rn(d2, eps);
+                    const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
+                    X[j] = __ffma2_rn(cfx, r, X[j]);
+                    Y[j] = __ffma2_rn(cfy, r, Y[j]);
+                }
+            }
+        }
+    };
+
+    // coordinates, part 1.  TPS: affine part + basis.  GIVEN / FLOW: the raw loads only (consumed after the
+    // current tile's gather, so their latency hides behind it).
+    auto coords_begin = [&](const int tt, Tile& T, float& xt, float2 (&X)[TR / 2], float2 (&Y)[TR / 2], float (&rx)[TR], float (&ry)[TR]) {
+        T.col0 = tt * TC;
+        T.col = min(T.col0 + lane, ow - 1);          // columns / rows past the edge are duplicates of the edge pixel
+        T.col_ok = T.col0 + lane < ow;
+        xt = lin_coord(T.col, p.step_x);
         if (MODE == TMODE_TPS) {
-            const float xt = lin_coord(col, p.step_x);
             const float bx = fmaf(s_lin[1], xt, s_lin[0]), by = fmaf(s_lin[4], xt, s_lin[3]);
             const float2 l2 = f2dup(s_lin[2]), l5 = f2dup(s_lin[5]);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
                 const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
-                XP[j] = __ffma2_rn(l2, ytp, f2dup(bx));
-                YP[j] = __ffma2_rn(l5, ytp, f2dup(by));
+                X[j] = __ffma2_rn(l2, ytp, f2dup(bx));
+                Y[j] = __ffma2_rn(l5, ytp, f2dup(by));
             }
-            const float2 eps = f2dup(1e-6f);
-            const unsigned char* rp = recs;
-            for (int k = 0; k < pn4; k += 4) {
+            basis(xt, X, Y);
+        } else if (MODE == TMODE_GIVEN || MODE == TMODE_FLOW) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
-                    const float4 pc = *reinterpret_cast<const float4*>(rp);
-                    const float4 da = *reinterpret_cast<const float4*>(rp + 16);
-                    const float4 db = *reinterpret_cast<const float4*>(rp + 32);
-                    // scalar, separately rounded (x_t - px)^2 as in the reference (a packed mul feeding the packed
-                    // add below would be contracted into FFMA2 by ptxas); the packed ops take scalars as broadcast operands
-                    const float dx = DVSG_ADD(xt, pc.x);
-                    const float2 dxx = f2dup(DVSG_MUL(dx, dx));
-                    const float2 cfx = f2dup(pc.y), cfy = f2dup(pc.z);
-                    const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
-#pragma unroll
-                    for (int j = 0; j < TR / 2; ++j) {
-                        const float2 d2 = __fadd2_rn(dxx, dy[j]);
-                        const float2 tt = __fadd2_rn(d2, eps);
-                        const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
-                        XP[j] = __ffma2_rn(cfx, r, XP[j]);
-                        YP[j] = __ffma2_rn(cfy, r, YP[j]);
-                    }
-                }
+            for (int q = 0; q < TR; ++q) {
+                const int row = min(row0 + q, oh - 1);
+                const size_t i = ((size_t)b * oh + row) * ow + T.col;
+                if (MODE == TMODE_GIVEN) { rx[q] = __ldg(p.x_in + i); ry[q] = __ldg(p.y_in + i); }
+                else { const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + i); rx[q] = f.x; ry[q] = f.y; }
             }
-            if (p.x_out && col_ok) {
+        }
+    };
+    // coordinates, last part: x / y outputs and the sampler's own coordinate convention
+    //   TPS: A4 pixel-space coordinate; others: clipped+1 coordinate in the zero-padded frame
+    auto coords_end = [&](const Tile& T, const float xt, float2 (&X)[TR / 2], float2 (&Y)[TR / 2], float (&rx)[TR], float (&ry)[TR]) {
+        if (MODE == TMODE_TPS) {
+            if (p.x_out && T.col_ok) {
 #pragma unroll
                 for (int j = 0; j < TR / 2; ++j) {
                     const int row = row0 + 2 * j;
-                    const size_t i = ((size_t)b * oh + row) * ow + col;
-                    if (row < oh) { p.x_out[i] = XP[j].x; p.y_out[i] = YP[j].x; }
-                    if (row + 1 < oh) { p.x_out[i + ow] = XP[j].y; p.y_out[i + ow] = YP[j].y; }
+                    const size_t i = ((size_t)b * oh + row) * ow + T.col;
+                    if (row < oh) { p.x_out[i] = X[j].x; p.y_out[i] = Y[j].x; }
+                    if (row + 1 < oh) { p.x_out[i + ow] = X[j].y; p.y_out[i + ow] = Y[j].y; }
                 }
             }
             // x_pix = ((x + 1) * W) / 2   (ThinPlateSpline.py:48-49), separately rounded
             const float2 wf = f2dup((float)W), hf = f2dup((float)H), half2 = f2dup(0.5f);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                XP[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(XP[j], one2), wf), half2);
-                YP[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(YP[j], one2), hf), half2);
+                X[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(X[j], one2), wf), half2);
+                Y[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(Y[j], one2), hf), half2);
             }
         } else {
-            float xs[TR], ys[TR];
             if (MODE == TMODE_GIVEN || MODE == TMODE_FLOW) {
 #pragma unroll
                 for (int q = 0; q < TR; ++q) {
-                    const int row = min(row0 + q, oh - 1);
-                    const size_t i = ((size_t)b * oh + row) * ow + col;
-                    if (MODE == TMODE_GIVEN) { xs[q] = __ldg(p.x_in + i); ys[q] = __ldg(p.y_in + i); }
-                    else { const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + i); xs[q] = f.x; ys[q] = f.y; }
-                }
-#pragma unroll
-                for (int q = 0; q < TR; ++q) {
-                    if (MODE == TMODE_GIVEN) { xs[q] = zp_pix_from_norm(xs[q], W); ys[q] = zp_pix_from_norm(ys[q], H); }
-                    else { xs[q] = DVSG_ADD((float)col, xs[q]); ys[q] = DVSG_ADD((float)min(row0 + q, oh - 1), ys[q]); }   // warp_with_optical_flow.py:107-120
+                    if (MODE == TMODE_GIVEN) { rx[q] = zp_pix_from_norm(rx[q], W); ry[q] = zp_pix_from_norm(ry[q], H); }
+                    else { rx[q] = DVSG_ADD((float)T.col, rx[q]); ry[q] = DVSG_ADD((float)min(row0 + q, oh - 1), ry[q]); }   // warp_with_optical_flow.py:107-120
                 }
             } else {
-                const float xt = lin_coord(col, p.step_x);
 #pragma unroll
                 for (int q = 0; q < TR; ++q) {
                     const float yt = s_yt[q];
@@ -288,23 +327,24 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
                         yn = zn != 0.0f ? DVSG_DIV(yn, zn) : 0.0f;
                     }
                     const int row = row0 + q;
-                    if (p.x_out && col_ok && row < oh) {
-                        const size_t i = ((size_t)b * oh + row) * ow + col;
+                    if (p.x_out && T.col_ok && row < oh) {
+                        const size_t i = ((size_t)b * oh + row) * ow + T.col;
                         p.x_out[i] = xn; p.y_out[i] = yn;
                     }
-                    xs[q] = zp_pix_from_norm(xn, W); ys[q] = zp_pix_from_norm(yn, H);
+                    rx[q] = zp_pix_from_norm(xn, W); ry[q] = zp_pix_from_norm(yn, H);
                 }
             }
             // clip to [-1, W] and shift into the zero-padded frame (spatial_transformer.py:517-521)
             const float wf = (float)W, hf = (float)H;
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                XP[j] = f2(DVSG_ADD(fminf(fmaxf(xs[2 * j], -1.0f), wf), 1.0f), DVSG_ADD(fminf(fmaxf(xs[2 * j + 1], -1.0f), wf), 1.0f));
-                YP[j] = f2(DVSG_ADD(fminf(fmaxf(ys[2 * j], -1.0f), hf), 1.0f), DVSG_ADD(fminf(fmaxf(ys[2 * j + 1], -1.0f), hf), 1.0f));
+                X[j] = f2(DVSG_ADD(fminf(fmaxf(rx[2 * j], -1.0f), wf), 1.0f), DVSG_ADD(fminf(fmaxf(rx[2 * j + 1], -1.0f), wf), 1.0f));
+                Y[j] = f2(DVSG_ADD(fminf(fmaxf(ry[2 * j], -1.0f), hf), 1.0f), DVSG_ADD(fminf(fmaxf(ry[2 * j + 1], -1.0f), hf), 1.0f));
             }
         }
-
-        // ================= F: footprint of the tile (warp-uniform after the REDUX) =================
+    };
+    // F + L: footprint of the tile (warp-uniform after the REDUX) and ONE TMA tensor copy of it into the staging buffer
+    auto footprint_load = [&](const float2 (&XP)[TR / 2], const float2 (&YP)[TR / 2], Tile& T) {
         const float xmn = min8n(XP), xmx = max8n(XP), ymn = min8n(YP), ymx = max8n(YP);
         // finite and small enough for the 2^23 arithmetic; NaN fails the comparison
         const bool sane = (fabsf(xmn) + fabsf(xmx)) + (fabsf(ymn) + fabsf(ymx)) < 4.0e6f;
@@ -313,16 +353,15 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
         x_lo = __reduce_min_sync(0xffffffffu, x_lo); x_hi = __reduce_max_sync(0xffffffffu, x_hi);
         y_lo = __reduce_min_sync(0xffffffffu, y_lo); y_hi = __reduce_max_sync(0xffffffffu, y_hi);
         const bool all_sane = x_lo > -(1 << 30);
-        bool interior;
         int fx_lo, fx_hi, fy_lo, fy_hi;    // source pixels to stage (inclusive; may reach outside the frame for the padded modes)
         if (MODE == TMODE_TPS) {
-            interior = x_lo >= 0 && x_hi <= W - 1 && y_lo >= 0 && y_hi <= H - 1;
+            T.interior = x_lo >= 0 && x_hi <= W - 1 && y_lo >= 0 && y_hi <= H - 1;
             fx_lo = min(max(x_lo, 0), W - 1); fx_hi = min(max(x_hi, 0), W - 1);
             fy_lo = min(max(y_lo, 0), H - 1); fy_hi = min(max(y_hi, 0), H - 1);
         } else {
             // padded-frame corners lie in [x_lo, x_hi]; real pixel = idx - 1.  Whatever falls outside the frame is
             // zero-filled by the TMA copy -- exactly the zero padding of the reference -- so every tile is "interior"
-            interior = true;
+            T.interior = true;
             fx_lo = x_lo - 1; fx_hi = x_hi - 1; fy_lo = y_lo - 1; fy_hi = y_hi - 1;
         }
         // the box starts at a 16-byte aligned float (TMA faults on unaligned box origins)
@@ -333,71 +372,66 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
         else if (fw <= p.bw[2] && nrows <= p.bh[2]) box = 2;
         if ((p.dbg & 1) && box == 1) box = -1;
         if ((p.dbg & 2) && box == 2) box = -1;
-        const int pitch = (box == 2 ? p.bw[2] : p.bw[0]) * 4;
+        T.pitch = (box == 2 ? p.bw[2] : p.bw[0]) * 4;
         const int box_rows = box == 0 ? p.bh[0] : (box == 1 ? p.bh[1] : p.bh[2]);
         // the packed gather forms byte offsets as exact fp32 integers below 2^22
-        const bool staged = box >= 0 && all_sane && (long long)(fy_hi + 3) * pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
+        T.staged = box >= 0 && all_sane && (long long)(fy_hi + 3) * T.pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
+        // sb = staging address of frame pixel (0,0); padded-frame modes index pixel idx-1: fold the -1 into it
+        T.sb = w_stage - (fy_lo * T.pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : T.pitch + 12);
+        if (T.staged && lane == 0) {
+            mbar_arrive_expect_tx(mbar, (unsigned)(T.pitch * box_rows));
+            tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
+        }
+    };
+#define DVSG_PAIR(J)                                                                                                            \
+    tile_pair<MODE, J>(cur.staged, cur.interior, XC[J], YC[J], cur.pitch, cur.sb, ot, wm1, hm1, W, H, srcb, mask_col, ow,       \
+                       cur.col_ok && row0 + 2 * J < oh, cur.col_ok && row0 + 2 * J + 1 < oh)
 
-        // ================= L: stage the footprint with one TMA tensor copy =================
-        if (staged) {
+    // ---- the software pipeline: the coordinates of tile t+1 are computed BEFORE tile t is gathered, so the TMA copy of
+    // a footprint has a whole coordinate phase to land before the warp waits for it
+    int t = t_begin + warp;
+    if (t < t_end) {
+        Tile cur, nxt;
+        float2 XC[TR / 2], YC[TR / 2], XN[TR / 2], YN[TR / 2];
+        float rx[TR], ry[TR], xt;
+        coords_begin(t, cur, xt, XC, YC, rx, ry);
+        coords_end(cur, xt, XC, YC, rx, ry);
+        footprint_load(XC, YC, cur);
+        while (true) {
+            const int tn = t + TNW;
+            const bool has_next = tn < t_end;
+            if (out_pending) {             // the previous tile's tensor store must have read the output tile
+                if (lane == 0) bulk_wait_read0();
+                out_pending = false;
+            }
+            if (has_next) coords_begin(tn, nxt, xt, XN, YN, rx, ry);
+            __syncwarp();
+            if (cur.staged) { mbar_wait(mbar, phase); phase ^= 1u; }
+            float* mask_col = want_mask ? p.mask_out + ((size_t)b * oh + row0) * ow + cur.col : nullptr;
+            DVSG_PAIR(0);
+            DVSG_PAIR(1);
+            DVSG_PAIR(2);
+            DVSG_PAIR(3);
+
+            // S: output tile -> global with one TMA tensor store (clipped at the frame edge)
+            fence_proxy_async_smem();      // this lane's generic-proxy writes -> visible to the async proxy
+            __syncwarp();
             if (lane == 0) {
-                mbar_arrive_expect_tx(mbar, (unsigned)(pitch * box_rows));
-                tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
+                tma_store_3d(&maps.out, cur.col0 * 3, row0, b, out_s);
+                bulk_commit();
             }
-        }
-        if (out_pending) {                 // the previous tile's tensor store must have read the output tile
-            if (lane == 0) bulk_wait_read0();
-            out_pending = false;
-        }
-        __syncwarp();
-        if (staged) { mbar_wait(mbar, phase); phase ^= 1u; }
+            out_pending = true;
+            if (!has_next) break;
 
-        // ================= G: gather + blend =================
-        const bool want_mask = MODE == TMODE_TPS && p.mask_out != nullptr;
-        if (staged) {
-            // sb = staging address of frame pixel (0,0); padded-frame modes index pixel idx-1: fold the -1 into it
-            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
-            float* ot = reinterpret_cast<float*>(w_out) + lane * 3;
-            const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-            float2 ms[TR / 2];
-            if (interior) {
-                gather_pair<MODE, false, 0>(XP[0], YP[0], pitch, sb, ot, ms[0], wm1, hm1);
-                gather_pair<MODE, false, 1>(XP[1], YP[1], pitch, sb, ot, ms[1], wm1, hm1);
-                gather_pair<MODE, false, 2>(XP[2], YP[2], pitch, sb, ot, ms[2], wm1, hm1);
-                gather_pair<MODE, false, 3>(XP[3], YP[3], pitch, sb, ot, ms[3], wm1, hm1);
-            } else if (MODE == TMODE_TPS) {
-                gather_pair<MODE, true, 0>(XP[0], YP[0], pitch, sb, ot, ms[0], wm1, hm1);
-                gather_pair<MODE, true, 1>(XP[1], YP[1], pitch, sb, ot, ms[1], wm1, hm1);
-                gather_pair<MODE, true, 2>(XP[2], YP[2], pitch, sb, ot, ms[2], wm1, hm1);
-                gather_pair<MODE, true, 3>(XP[3], YP[3], pitch, sb, ot, ms[3], wm1, hm1);
-            }
-            if (want_mask && col_ok) {
+            coords_end(nxt, xt, XN, YN, rx, ry);
+            footprint_load(XN, YN, nxt);   // the staging buffer is free: every lane passed the __syncwarp above
+            cur = nxt;
 #pragma unroll
-                for (int j = 0; j < TR / 2; ++j) {
-                    const int row = row0 + 2 * j;
-                    if (row < oh) p.mask_out[((size_t)b * oh + row) * ow + col] = ms[j].x;
-                    if (row + 1 < oh) p.mask_out[((size_t)b * oh + row + 1) * ow + col] = ms[j].y;
-                }
-            }
-        } else {
-            const uint32_t obase = out_s + (uint32_t)lane * 12u;
-#pragma unroll
-            for (int q = 0; q < TR; ++q) {     // unrolled: XP / YP must stay in registers (no dynamic indexing)
-                const float xp = (q & 1) ? XP[q >> 1].y : XP[q >> 1].x, yp = (q & 1) ? YP[q >> 1].y : YP[q >> 1].x;
-                float* mp = want_mask && col_ok && row0 + q < oh ? p.mask_out + ((size_t)b * oh + row0 + q) * ow + col : nullptr;
-                if (!(p.dbg & 4)) general_pixel<MODE>(xp, yp, W, H, srcb, obase + (uint32_t)(q * TC * 12), mp);
-            }
+            for (int j = 0; j < TR / 2; ++j) { XC[j] = XN[j]; YC[j] = YN[j]; }
+            t = tn;
         }
-
-        // ================= S: output tile -> global with one TMA tensor store (clipped at the frame edge) ===
-        fence_proxy_async_smem();          // this lane's generic-proxy writes -> visible to the async proxy
-        __syncwarp();
-        if (lane == 0) {
-            tma_store_3d(&maps.out, col0 * 3, row0, b, out_s);
-            bulk_commit();
-        }
-        out_pending = true;
     }
+#undef DVSG_PAIR
     if (out_pending && lane == 0) bulk_wait_read0();   // shared memory must outlive the store's reads
 }
 
@@ -435,7 +469,7 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     }
     const int rc = encode_frames(&maps.out, p.out, p.B, p.oh, p.ow, TC * 3, TR);
     if (rc) return rc;
-    const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)((p.pn + 3) & ~3) * sizeof(TpsRec) : 0);
+    const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)((p.pn + 7) & ~7) * sizeof(TpsRec) : 0);
     const dim3 grid((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B);
     if (g_tile_minb >= 6) {
         auto k = warp_fwd_tile_kernel<MODE, 6>;
