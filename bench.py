@@ -344,6 +344,15 @@ def run_ours(args, wl):
                 traffic = json.load(fh).get(args.workload)
         except Exception:
             pass
+        clocks = clk.summary()
+        if kind in ('tps', 'tps_train'):
+            # second roofline of the fused TPS kernel: one MUFU.LG2 per pixel and control point on the XU pipe
+            # (16 lanes per SM and clock); it binds for large meshes (cfg5), see DESIGN.md
+            mhz = (clocks or {}).get('sm_mhz') or 1965
+            n_logs = wl['mesh'] ** 2 * (2 if kind == 'tps_train' else 1)
+            xu_gpix = 148 * 16 * mhz * 1e6 / n_logs / 1e9
+            extra['xu_bound'] = {'unit': 'Gpix/s', 'peak': xu_gpix, 'achieved': pix_per_step / (kern_ms * 1e-3) / 1e9,
+                                 'frac': pix_per_step / (kern_ms * 1e-3) / 1e9 / xu_gpix, 'logs_per_px': n_logs, 'sm_mhz': mhz}
         line = {
             'metric': 'warped Mpix/s', 'value': value, 'unit': 'Mpix/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / max(args.steps, 1), 'higher_is_better': True,
@@ -355,7 +364,7 @@ def run_ours(args, wl):
             'roofline': {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_px': fwd_bpp, 'kernel_ms': kern_ms, **extra},
-            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk.summary(),
+            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
         }
         if not args.no_cpu and world == 1:
             threads = min(os.cpu_count() or 1, 16)
