@@ -65,7 +65,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// single MUFU.LG2 (t is never denormal on this path: t >= 1e-6)
+// single MUFU.LG2 (t is never denormal on this path: t >= 1e-30)
 __device__ __forceinline__ float lg2_approx(float t) {
     float r;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
@@ -74,3 +74,36 @@ __device__ __forceinline__ float lg2_approx(float t) {
 #endif  // __CUDACC__
 
 }  // namespace dvsg
+
+#if defined(__CUDACC__)
+#include "sampler_math.cuh"
+namespace dvsg {
+// ---- TPS radial term, shared by all four warp kernels (identical coordinates in every one of them) ---------
+// Radial term: the reference's r = d2 * log(d2 + 1e-6) (ThinPlateSpline.py:105) is evaluated as d2 * log(d2) + 1e-6:
+// d2 log(1 + 1e-6/d2) = 1e-6 - 1e-12/(2 d2) + ..., so the two differ by less than 1e-8 once d2 > 5e-5 (a pixel farther
+// than 0.007 normalised units from the control point) and by at most 1e-6 next to it.  The constant is not added per
+// term: sum_k c_k * 1e-6 is folded into the affine constant once per frame (it vanishes for coefficients that come out
+// of the TPS system, whose last three rows force sum_k c_k = 0).  That removes one packed add per (pixel pair, control
+// point).  d2 = 0 (a pixel exactly on a control point) would give 0 * -inf: the (y_t - p_y)^2 table entries are kept
+// >= TPS_TINY, so d2 >= 1e-30 and the term is -1e-28 ~ -0 as in the reference.
+constexpr float TPS_TINY = 1e-30f;
+constexpr float TPS_EPS = 1e-6f;
+// warp-collective: sum of pn coefficients in a fixed order (lane-strided partial sums, xor tree: same value on every lane)
+__device__ __forceinline__ float tps_coef_sum(const float* __restrict__ c, int pn, int lane) {
+    float s = 0.0f;
+    for (int k = lane; k < pn; k += 32) s = __fadd_rn(s, __ldg(c + k));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+    return s;
+}
+// affine constant of one output row of T with the folded epsilon term (called by one whole warp)
+__device__ __forceinline__ float tps_affine0(const float* __restrict__ Trow, int pn, int lane) {
+    return __fmaf_rn(TPS_EPS, tps_coef_sum(Trow + 3, pn, lane), __ldg(Trow));
+}
+// (y_t - p_y)^2 as stored in the tables
+__device__ __forceinline__ float tps_dy2(float yt, float py) {
+    const float dy = DVSG_SUB(yt, py);
+    return fmaxf(DVSG_MUL(dy, dy), TPS_TINY);
+}
+}  // namespace dvsg
+#endif  // __CUDACC__

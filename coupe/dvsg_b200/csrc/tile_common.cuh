@@ -42,6 +42,7 @@ struct TileParams {
     int bw[3], bh[3];     // staging boxes (floats x rows) of the three source tensor maps, clamped to the frame
     int n_tx, n_ty;       // tiles per strip / strips per frame
     int segs, seg_len;    // CTAs per strip, tiles per CTA
+    float one;            // 1.0f, opaque to ptxas: add2x() below
 };
 
 // staging boxes (floats wide x rows): pitch = 512 or 640 B keeps the row pitch a multiple of 128 B, so the
@@ -60,7 +61,7 @@ struct alignas(64) TileMaps {
 
 struct __align__(16) TpsRec {   // one control point, 48 B, read with three broadcast LDS.128
     float4 pc;    // (-px, cx ln2, cy ln2, 0)
-    float4 dya;   // (y_t(row0 + r) - py)^2, r = 0..3
+    float4 dya;   // max((y_t(row0 + r) - py)^2, TPS_TINY), r = 0..3
     float4 dyb;   // r = 4..7
 };
 
@@ -79,6 +80,9 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a
 // ptxas (CUDA 12.9) contracts mul.rn.f32x2 feeding add/fma.rn.f32x2 into one FFMA2 although both carry
 // .rn, which would fuse roundings the reference keeps apart: sums of products use scalar rounded adds.
 __device__ __forceinline__ float2 add2s(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+// the packed alternative: a + b as fma(a, one, b) with `one` = 1.0f loaded from the kernel parameters, which ptxas
+// cannot fold; fma(a, 1, b) rounds a + b once, i.e. it IS add.rn, and a product feeding it stays a separate FMUL2
+__device__ __forceinline__ float2 add2x(float2 a, float2 b, float2 one) { return __ffma2_rn(a, one, b); }
 // per-lane add rounded toward -infinity (FADD2.RM): x +rm 2^23 drops the fraction downwards = floor
 __device__ __forceinline__ float2 add2_rm(float2 a, float2 b) {
     float2 r;
@@ -95,6 +99,59 @@ __device__ __forceinline__ int t_floor_i32(float f) {
     const int v = __float2int_rd(f);
     return fabsf(f) < 2147483648.0f ? v : (int)0x80000000;
 }
+
+// ---- TPS tables shared by the forward and backward tile kernels (identical coordinates in both) -----------------------
+// Per-strip tables of a tile kernel: s_lin[0..5] = affine rows (constant, x, y) of x_s and y_s, records of the pn8
+// (padded) control points for the TR rows starting at row0.  Called by the whole CTA (>= 2 warps) before its barrier.
+__device__ __forceinline__ void tile_tps_tables(const float* __restrict__ Tb, const float* __restrict__ cb, int pn, int pn8,
+                                                int row0, int oh, float step_y, int tid, int nthreads, float* s_lin, TpsRec* wr) {
+    const int N = pn + 3, lane = tid & 31, warp = tid >> 5;
+    if (warp < 2) {
+        const float c0 = tps_affine0(Tb + warp * N, pn, lane);
+        if (lane == 0) s_lin[3 * warp] = c0;
+        else if (lane < 3) s_lin[3 * warp + lane] = __ldg(Tb + warp * N + lane);
+    }
+    for (int k = tid; k < pn8; k += nthreads) {
+        const bool real = k < pn;
+        const float px = real ? __ldg(cb + 2 * k) : 0.0f, py = real ? __ldg(cb + 2 * k + 1) : 0.0f;
+        const float cx = real ? __ldg(Tb + 3 + k) * TLN2 : 0.0f, cy = real ? __ldg(Tb + N + 3 + k) * TLN2 : 0.0f;
+        float d[TR];
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+            d[r] = real ? tps_dy2(lin_coord(min(row0 + r, oh - 1), step_y), py) : 1.0f;   // padding: d2 >= 1, weight 0 -> adds exactly 0
+        TpsRec rec;
+        rec.pc = make_float4(-px, cx, cy, 0.0f);
+        rec.dya = make_float4(d[0], d[1], d[2], d[3]); rec.dyb = make_float4(d[4], d[5], d[6], d[7]);
+        wr[k] = rec;
+    }
+}
+// TPS basis of all (padded) control points accumulated into X, Y (rows (2j, 2j+1) of the lane's column in pair j):
+// packed fp32x2, one MUFU.LG2 per (pixel, control point), ln 2 folded into the coefficients.  The scalar, separately
+// rounded (x_t - px)^2 enters the packed add as a broadcast operand (a packed mul feeding it would be contracted).
+__device__ __forceinline__ void tile_tps_basis(const unsigned char* __restrict__ recs, const int pn8, const float xt,
+                                               float2 (&X)[TR / 2], float2 (&Y)[TR / 2]) {
+    const unsigned char* rp = recs;
+    for (int k = 0; k < pn8; k += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
+            const float4 pc = *reinterpret_cast<const float4*>(rp);
+            const float4 da = *reinterpret_cast<const float4*>(rp + 16);
+            const float4 db = *reinterpret_cast<const float4*>(rp + 32);
+            const float dx = DVSG_ADD(xt, pc.x);
+            const float2 dxx = f2dup(DVSG_MUL(dx, dx));
+            const float2 cfx = f2dup(pc.y), cfy = f2dup(pc.z);
+            const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                const float2 d2 = __fadd2_rn(dxx, dy[j]);
+                const float2 r = __fmul2_rn(d2, f2(lg2_approx(d2.x), lg2_approx(d2.y)));
+                X[j] = __ffma2_rn(cfx, r, X[j]);
+                Y[j] = __ffma2_rn(cfy, r, Y[j]);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int x, int y, int z, uint32_t mbar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst_smem), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(mbar) : "memory");

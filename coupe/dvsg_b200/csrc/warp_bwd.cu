@@ -74,7 +74,13 @@ __global__ void __launch_bounds__(BNT, 3) warp_bwd_kernel(const BwdParams p) {
     float xs[BPR], ys[BPR];
     const float xt = lin_coord(col, p.step_x);
     if (MODE == BMODE_TPS) {
-        if (tid < 6) { s_lin[tid] = __ldg(Tb + (tid < 3 ? tid : N + tid - 3)); s_gaff[tid] = 0.0f; }
+        if (tid < 6) s_gaff[tid] = 0.0f;
+        if (tid < 64) {      // warps 0, 1: affine rows of x_s, y_s (constant with the folded epsilon term, x, y)
+            const int w = tid >> 5, l = tid & 31;
+            const float c0 = tps_affine0(Tb + w * N, p.pn, l);
+            if (l == 0) s_lin[3 * w] = c0;
+            else if (l < 3) s_lin[3 * w + l] = __ldg(Tb + w * N + l);
+        }
         for (int k0 = 0; k0 < p.pn; k0 += p.kc_cap) {
             const int kc = min(p.kc_cap, p.pn - k0);
             if (k0 > 0) __syncthreads();
@@ -83,8 +89,7 @@ __global__ void __launch_bounds__(BNT, 3) warp_bwd_kernel(const BwdParams p) {
                                       __ldg(Tb + N + 3 + k0 + k) * BLN2);
             for (int i = tid; i < kc * BTH; i += BNT) {
                 const int k = i / BTH, r = i % BTH;
-                const float dy = DVSG_SUB(lin_coord(row0 + r, p.step_y), __ldg(cb + 2 * (k0 + k) + 1));
-                s_dy2[i] = DVSG_MUL(dy, dy);
+                s_dy2[i] = tps_dy2(lin_coord(row0 + r, p.step_y), __ldg(cb + 2 * (k0 + k) + 1));
             }
             __syncthreads();
             if (k0 == 0) {
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(BNT, 3) warp_bwd_kernel(const BwdParams p) {
 #pragma unroll
                 for (int q = 0; q < BPR; ++q) {
                     const float d2 = DVSG_ADD(dx2, dv[q]);
-                    const float r = DVSG_MUL(d2, lg2_approx(DVSG_ADD(d2, 1e-6f)));
+                    const float r = DVSG_MUL(d2, lg2_approx(d2));
                     xs[q] = fmaf(pk.z, r, xs[q]);
                     ys[q] = fmaf(pk.w, r, ys[q]);
                 }
@@ -284,8 +289,7 @@ __global__ void __launch_bounds__(BNT, 3) warp_bwd_kernel(const BwdParams p) {
                     s_pt[k] = make_float4(__ldg(cb + 2 * (k0 + k)), __ldg(cb + 2 * (k0 + k) + 1), 0.f, 0.f);
                 for (int i = tid; i < kc * BTH; i += BNT) {
                     const int k = i / BTH, r = i % BTH;
-                    const float dy = DVSG_SUB(lin_coord(row0 + r, p.step_y), __ldg(cb + 2 * (k0 + k) + 1));
-                    s_dy2[i] = DVSG_MUL(dy, dy);
+                    s_dy2[i] = tps_dy2(lin_coord(row0 + r, p.step_y), __ldg(cb + 2 * (k0 + k) + 1));
                 }
             }
             for (int i = tid; i < 2 * kc; i += BNT) s_gt[i] = 0.0f;
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(BNT, 3) warp_bwd_kernel(const BwdParams p) {
 #pragma unroll
                 for (int q = 0; q < BPR; ++q) {
                     const float d2 = DVSG_ADD(dx2, dv[q]);
-                    const float r = DVSG_MUL(d2, lg2_approx(DVSG_ADD(d2, 1e-6f)));
+                    const float r = DVSG_MUL(d2, lg2_approx(d2));
                     ax = fmaf(gxs[q], r, ax);
                     ay = fmaf(gys[q], r, ay);
                 }

@@ -158,26 +158,8 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     if (tid < TR) s_yt[tid] = lin_coord(min(row0 + tid, oh - 1), p.step_y);
     if (MODE == TMODE_TPS) {
-        const int N = p.pn + 3;
-        const float* Tb = p.T + (size_t)b * 2 * N;
-        const float* cb = p.coord + (size_t)b * p.coord_stride;
-        if (tid < 6) s_lin[tid] = __ldg(Tb + (tid < 3 ? tid : N + tid - 3));
-        TpsRec* wr = reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (2 * TSTAGE_BYTES));
-        for (int k = tid; k < pn8; k += TNT) {
-            const bool real = k < p.pn;
-            const float px = real ? __ldg(cb + 2 * k) : 0.0f, py = real ? __ldg(cb + 2 * k + 1) : 0.0f;
-            const float cx = real ? __ldg(Tb + 3 + k) * TLN2 : 0.0f, cy = real ? __ldg(Tb + N + 3 + k) * TLN2 : 0.0f;
-            float d[TR];
-#pragma unroll
-            for (int r = 0; r < TR; ++r) {
-                const float dy = DVSG_SUB(lin_coord(min(row0 + r, oh - 1), p.step_y), py);
-                d[r] = real ? DVSG_MUL(dy, dy) : 1.0f;
-            }
-            TpsRec rec;
-            rec.pc = make_float4(-px, cx, cy, 0.0f);
-            rec.dya = make_float4(d[0], d[1], d[2], d[3]); rec.dyb = make_float4(d[4], d[5], d[6], d[7]);
-            wr[k] = rec;
-        }
+        tile_tps_tables(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, pn8, row0, oh, p.step_y, tid, TNT,
+                        s_lin, reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (2 * TSTAGE_BYTES)));
         if (want_gT) for (int i = lane; i < 2 * pn8 + 16; i += 32) w_gt[i] = 0.0f;
     }
     __syncthreads();
@@ -217,28 +199,7 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
                 XP[j] = __ffma2_rn(l2, ytp, f2dup(bx));
                 YP[j] = __ffma2_rn(l5, ytp, f2dup(by));
             }
-            const float2 eps = f2dup(1e-6f);
-            const unsigned char* rp = recs;
-            for (int k = 0; k < pn4; k += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
-                    const float4 pc = *reinterpret_cast<const float4*>(rp);
-                    const float4 da = *reinterpret_cast<const float4*>(rp + 16);
-                    const float4 db = *reinterpret_cast<const float4*>(rp + 32);
-                    const float dx = DVSG_ADD(xt, pc.x);
-                    const float2 dxx = f2dup(DVSG_MUL(dx, dx));
-                    const float2 cfx = f2dup(pc.y), cfy = f2dup(pc.z);
-                    const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
-#pragma unroll
-                    for (int j = 0; j < TR / 2; ++j) {
-                        const float2 d2 = __fadd2_rn(dxx, dy[j]);
-                        const float2 tt = __fadd2_rn(d2, eps);
-                        const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
-                        XP[j] = __ffma2_rn(cfx, r, XP[j]);
-                        YP[j] = __ffma2_rn(cfy, r, YP[j]);
-                    }
-                }
-            }
+            tile_tps_basis(recs, pn4, xt, XP, YP);
             const float2 wf = f2dup((float)W), hf = f2dup((float)H), half2 = f2dup(0.5f);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
@@ -446,7 +407,6 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
 
         // ================= P2: grad_T = sum over pixels of grad(x_s, y_s) * (1, x_t, y_t, r_1..r_pn) =================
         if (want_gT) {
-            const float2 eps = f2dup(1e-6f);
             const unsigned char* rp = recs;
             for (int k = 0; k < pn8; k += 8) {
                 float v[16];
@@ -462,8 +422,7 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
 #pragma unroll
                     for (int j = 0; j < TR / 2; ++j) {
                         const float2 d2 = __fadd2_rn(dxx, dy[j]);
-                        const float2 tt = __fadd2_rn(d2, eps);
-                        const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
+                        const float2 r = __fmul2_rn(d2, f2(lg2_approx(d2.x), lg2_approx(d2.y)));   // radial term as in tile_tps_basis
                         sx = __ffma2_rn(GX[j], r, sx);
                         sy = __ffma2_rn(GY[j], r, sy);
                     }

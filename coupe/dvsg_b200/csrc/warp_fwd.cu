@@ -52,14 +52,13 @@ struct FwdParams {
     int projective;
 };
 
-// Accumulate sum_k c_k * d2_k * ln(d2_k + 1e-6) for PR consecutive rows of one column in packed fp32x2
+// Accumulate sum_k c_k * d2_k * ln(d2_k) (the radial term as restated in dvsg_common.cuh) for PR consecutive rows of one column in packed fp32x2
 // (two rows per instruction).  pt[k] = (px, py, cx*ln2, cy*ln2); dy2[k*TH + r] = (y_t(row0+r) - py_k)^2.
 // Same operations in the same order as the tile kernel, so both produce identical coordinates.
 __device__ __forceinline__ void tps_accumulate(const float4* __restrict__ pt, const float* __restrict__ dy2, int kc,
                                                float xt, int rbase, float (&xs)[PR], float (&ys)[PR]) {
     float2 xa = make_float2(xs[0], xs[1]), xb = make_float2(xs[2], xs[3]);
     float2 ya = make_float2(ys[0], ys[1]), yb = make_float2(ys[2], ys[3]);
-    const float2 eps = make_float2(1e-6f, 1e-6f);
 #pragma unroll 4
     for (int k = 0; k < kc; ++k) {
         const float4 q = pt[k];
@@ -69,10 +68,8 @@ __device__ __forceinline__ void tps_accumulate(const float4* __restrict__ pt, co
         const float2 dxx = make_float2(dx2, dx2);
         const float2 d2a = __fadd2_rn(dxx, make_float2(d.x, d.y));
         const float2 d2b = __fadd2_rn(dxx, make_float2(d.z, d.w));
-        const float2 ta = __fadd2_rn(d2a, eps);
-        const float2 tb = __fadd2_rn(d2b, eps);
-        const float2 ra = __fmul2_rn(d2a, make_float2(lg2_approx(ta.x), lg2_approx(ta.y)));
-        const float2 rb = __fmul2_rn(d2b, make_float2(lg2_approx(tb.x), lg2_approx(tb.y)));
+        const float2 ra = __fmul2_rn(d2a, make_float2(lg2_approx(d2a.x), lg2_approx(d2a.y)));
+        const float2 rb = __fmul2_rn(d2b, make_float2(lg2_approx(d2b.x), lg2_approx(d2b.y)));
         const float2 cx = make_float2(q.z, q.z), cy = make_float2(q.w, q.w);
         xa = __ffma2_rn(cx, ra, xa);
         xb = __ffma2_rn(cx, rb, xb);
@@ -113,7 +110,12 @@ __global__ void __launch_bounds__(NT, 3) warp_fwd_kernel(const FwdParams p) {
         const int N = p.pn + 3;
         const float* Tb = p.T + (size_t)b * 2 * N;
         const float* cb = p.coord + (size_t)b * p.coord_stride;
-        if (tid < 6) s_lin[tid] = __ldg(Tb + (tid < 3 ? tid : N + tid - 3));
+        if (tid < 64) {      // warps 0, 1: affine rows of x_s, y_s (constant with the folded epsilon term, x, y)
+            const int w = tid >> 5, l = tid & 31;
+            const float c0 = tps_affine0(Tb + w * N, p.pn, l);
+            if (l == 0) s_lin[3 * w] = c0;
+            else if (l < 3) s_lin[3 * w + l] = __ldg(Tb + w * N + l);
+        }
         for (int k0 = 0; k0 < p.pn; k0 += p.kc_cap) {
             const int kc = min(p.kc_cap, p.pn - k0);
             if (k0 > 0) __syncthreads();
@@ -122,8 +124,7 @@ __global__ void __launch_bounds__(NT, 3) warp_fwd_kernel(const FwdParams p) {
                                       __ldg(Tb + 3 + k0 + k) * LN2, __ldg(Tb + N + 3 + k0 + k) * LN2);
             for (int i = tid; i < kc * TH; i += NT) {
                 const int k = i / TH, r = i % TH;
-                const float dy = DVSG_SUB(lin_coord(row0 + r, p.step_y), __ldg(cb + 2 * (k0 + k) + 1));
-                s_dy2[i] = DVSG_MUL(dy, dy);
+                s_dy2[i] = tps_dy2(lin_coord(row0 + r, p.step_y), __ldg(cb + 2 * (k0 + k) + 1));
             }
             __syncthreads();
             const float xt = lin_coord(col, p.step_x);

@@ -90,13 +90,13 @@ __device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, con
 // lane's column of the output tile.  All index quantities are exact fp32 integers below 2^22; floor() is
 // FADD2.RM against 2^23 and the byte offset y*pitch + x*12 rides on the same constant, so the XU pipe
 // (F2I / I2F) is not used at all.  Plain loads / stores (not volatile asm) and __restrict__ so that the
-// compiler may overlap the pairs.
+// compiler may overlap the pairs.  Sums of products are add2x (FFMA2 by an opaque 1.0): separately rounded.
 // CLAMP = false: no corner of the tile touches the frame border (corners a, a+12, a+pitch, a+pitch+12).
 // CLAMP = true : TPS sampler at the frame border, corners clamped first and weights taken FROM the clamped
 //                corners (ThinPlateSpline.py:57-60, 81-88).
-template <int MODE, bool CLAMP, int J>
+template <int MODE, bool CLAMP, bool MASK, int J>
 __device__ __forceinline__ void gather_pair(const float2 xp, const float2 yp, const int pitch, const unsigned char* __restrict__ sb,
-                                            float* __restrict__ ot, float2& msum, const float wm1, const float hm1) {
+                                            float* __restrict__ ot, float2& msum, const float wm1, const float hm1, const float2 one) {
     const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
     float2 x0f, y0f, x1f, y1f;
     if (!CLAMP) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void gather_pair(const float2 xp, const float2 yp, co
     const float2 ax1 = sub2(x1f, xp), ax0 = sub2(xp, x0f), ay1 = sub2(y1f, yp), ay0 = sub2(yp, y0f);
     // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
     const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
-    if (MODE == TMODE_TPS) msum = add2s(add2s(add2s(w00, w10), w01), w11);   // A4 add_n order (mask = warp of ones)
+    if (MASK) msum = add2x(add2x(add2x(w00, w10, one), w01, one), w11, one);   // A4 add_n order (mask = warp of ones)
     const float2 tx0 = __ffma2_rn(x0f, twelve, m23);
     const float2 o00 = __ffma2_rn(y0f, pitchf, tx0);
     const float* __restrict__ p00a = reinterpret_cast<const float*>(sb + (__float_as_int(o00.x) & 0x7fffff));
@@ -140,44 +140,45 @@ __device__ __forceinline__ void gather_pair(const float2 xp, const float2 yp, co
         const float2 i10 = f2(p10a[ch], p10b[ch]), i11 = f2(p11a[ch], p11b[ch]);
         const float2 t00 = __fmul2_rn(w00, i00), t01 = __fmul2_rn(w01, i01), t10 = __fmul2_rn(w10, i10), t11 = __fmul2_rn(w11, i11);
         float2 o;
-        if (MODE == TMODE_TPS) o = add2s(add2s(add2s(t00, t10), t01), t11);   // ThinPlateSpline.py:89
-        else o = add2s(add2s(add2s(t00, t01), t10), t11);                       // spatial_transformer.py:562
+        if (MODE == TMODE_TPS) o = add2x(add2x(add2x(t00, t10, one), t01, one), t11, one);   // ThinPlateSpline.py:89
+        else o = add2x(add2x(add2x(t00, t01, one), t10, one), t11, one);                       // spatial_transformer.py:562
         ot[(2 * J) * TC * 3 + ch] = o.x;
         ot[(2 * J + 1) * TC * 3 + ch] = o.y;
     }
 }
 
-// gather + blend of rows (2J, 2J+1) of the thread's column, whichever variant the tile takes (warp-uniform)
-template <int MODE, int J>
-__device__ __forceinline__ void tile_pair(const bool staged, const bool interior, const float2 xp, const float2 yp, const int pitch,
-                                          const unsigned char* __restrict__ sb, float* __restrict__ ot, const float wm1, const float hm1,
-                                          const int W, const int H, const float* __restrict__ srcb, float* mask_col, const int ow,
-                                          const bool ok_a, const bool ok_b) {
-    if (staged) {
-        float2 ms = f2dup(0.0f);
-        if (interior) gather_pair<MODE, false, J>(xp, yp, pitch, sb, ot, ms, wm1, hm1);
-        else if (MODE == TMODE_TPS) gather_pair<MODE, true, J>(xp, yp, pitch, sb, ot, ms, wm1, hm1);
-        if (MODE == TMODE_TPS && mask_col) {
-            if (ok_a) mask_col[(2 * J) * ow] = ms.x;
-            if (ok_b) mask_col[(2 * J + 1) * ow] = ms.y;
+// gather + blend of the thread's 8 pixels from the staged footprint (one variant per tile, warp-uniform)
+template <int MODE, bool CLAMP, bool MASK>
+__device__ __forceinline__ void gather_tile(const float2 (&XC)[TR / 2], const float2 (&YC)[TR / 2], const int pitch,
+                                            const unsigned char* __restrict__ sb, float* __restrict__ ot, const float wm1, const float hm1,
+                                            const float2 one, float* __restrict__ mask_col, const int ow, const int rows_ok) {
+    float2 ms[TR / 2];
+    gather_pair<MODE, CLAMP, MASK, 0>(XC[0], YC[0], pitch, sb, ot, ms[0], wm1, hm1, one);
+    gather_pair<MODE, CLAMP, MASK, 1>(XC[1], YC[1], pitch, sb, ot, ms[1], wm1, hm1, one);
+    gather_pair<MODE, CLAMP, MASK, 2>(XC[2], YC[2], pitch, sb, ot, ms[2], wm1, hm1, one);
+    gather_pair<MODE, CLAMP, MASK, 3>(XC[3], YC[3], pitch, sb, ot, ms[3], wm1, hm1, one);
+    if (MASK && mask_col) {      // mask_col == nullptr: column past the frame edge
+#pragma unroll
+        for (int j = 0; j < TR / 2; ++j) {
+            if (2 * j < rows_ok) mask_col[(2 * j) * ow] = ms[j].x;
+            if (2 * j + 1 < rows_ok) mask_col[(2 * j + 1) * ow] = ms[j].y;
         }
-    } else {
-        general_pixel<MODE>(xp.x, yp.x, W, H, srcb, ot + (2 * J) * TC * 3, (mask_col && ok_a) ? mask_col + (2 * J) * ow : nullptr);
-        general_pixel<MODE>(xp.y, yp.y, W, H, srcb, ot + (2 * J + 1) * TC * 3, (mask_col && ok_b) ? mask_col + (2 * J + 1) * ow : nullptr);
     }
 }
 
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TileParams p, const __grid_constant__ TileMaps maps) {
+template <int MODE, bool MASK>
+__global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams p, const __grid_constant__ TileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_mbar[TNW];
     __shared__ float s_lin[12];
     __shared__ __align__(16) float s_yt[TR];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler: tile bookkeeping lives in uniform registers
     const int H = p.H, W = p.W, oh = p.oh, ow = p.ow;
     const int seg = blockIdx.x, b = blockIdx.z;      // grid = (CTAs per strip, strips per frame, frames)
     const int row0 = blockIdx.y * TR;
+    const int rows_ok = min(TR, oh - row0);
     const int t_begin = seg * p.seg_len, t_end = min(t_begin + p.seg_len, p.n_tx);
 
     unsigned char* w_out = smem + (size_t)warp * (TOUT_BYTES + p.stage_bytes);
@@ -190,26 +191,8 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     if (tid < TR) s_yt[tid] = lin_coord(min(row0 + tid, oh - 1), p.step_y);
     if (MODE == TMODE_TPS) {
-        const int N = p.pn + 3;
-        const float* Tb = p.T + (size_t)b * 2 * N;
-        const float* cb = p.coord + (size_t)b * p.coord_stride;
-        if (tid < 6) s_lin[tid] = __ldg(Tb + (tid < 3 ? tid : N + tid - 3));
-        TpsRec* wr = reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes));
-        for (int k = tid; k < pn8; k += TNT) {
-            const bool real = k < p.pn;
-            const float px = real ? __ldg(cb + 2 * k) : 0.0f, py = real ? __ldg(cb + 2 * k + 1) : 0.0f;
-            const float cx = real ? __ldg(Tb + 3 + k) * TLN2 : 0.0f, cy = real ? __ldg(Tb + N + 3 + k) * TLN2 : 0.0f;
-            float d[TR];
-#pragma unroll
-            for (int r = 0; r < TR; ++r) {
-                const float dy = DVSG_SUB(lin_coord(min(row0 + r, oh - 1), p.step_y), py);
-                d[r] = real ? DVSG_MUL(dy, dy) : 1.0f;     // padding: d2 >= 1, weight 0 -> adds exactly 0
-            }
-            TpsRec rec;
-            rec.pc = make_float4(-px, cx, cy, 0.0f);
-            rec.dya = make_float4(d[0], d[1], d[2], d[3]); rec.dyb = make_float4(d[4], d[5], d[6], d[7]);
-            wr[k] = rec;
-        }
+        tile_tps_tables(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, pn8, row0, oh, p.step_y, tid, TNT,
+                        s_lin, reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes)));
     } else if (MODE == TMODE_HOMOG) {
         const int nt = p.projective ? 8 : 6;
         if (tid < 9) s_lin[tid] = tid < nt ? __ldg(p.theta + (size_t)b * nt + tid) : (tid == 8 ? 1.0f : 0.0f);
@@ -217,9 +200,8 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
     __syncthreads();
 
     const float* srcb = p.src + (size_t)b * H * W * 3;
-    const float2 one2 = f2dup(1.0f);
+    const float2 one2 = f2dup(1.0f), onex = f2dup(p.one);
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-    const bool want_mask = MODE == TMODE_TPS && p.mask_out != nullptr;
     float* const ot = reinterpret_cast<float*>(w_out) + lane * 3;      // this lane's column of the output tile
     unsigned phase = 0;
     bool out_pending = false;
@@ -232,34 +214,6 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
     };
 
     // ---- pieces of the per-tile work -----------------------------------------------------------------
-    // TPS basis of all (padded) control points, accumulated into X, Y (rows (2j, 2j+1) in lane pairs)
-    auto basis = [&](const float xt, float2 (&X)[TR / 2], float2 (&Y)[TR / 2]) {
-        const float2 eps = f2dup(1e-6f);
-        const unsigned char* rp = recs;
-        for (int k = 0; k < pn8; k += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
-                const float4 pc = *reinterpret_cast<const float4*>(rp);
-                const float4 da = *reinterpret_cast<const float4*>(rp + 16);
-                const float4 db = *reinterpret_cast<const float4*>(rp + 32);
-                // scalar, separately rounded (x_t - px)^2 as in the reference (a packed mul feeding the packed
-                // add below would be contracted into FFMA2 by ptxas); the packed ops take scalars as broadcast operands
-                const float dx = DVSG_ADD(xt, pc.x);
-                const float2 dxx = f2dup(DVSG_MUL(dx, dx));
-                const float2 cfx = f2dup(pc.y), cfy = f2dup(pc.z);
-                const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
-#pragma unroll
-                for (int j = 0; j < TR / 2; ++j) {
-                    const float2 d2 = __fadd2_rn(dxx, dy[j]);
-                    const float2 tt = __fadd2_rn(d2, eps);
-                    const float2 r = __fmul2_rn(d2, f2(lg2_approx(tt.x), lg2_approx(tt.y)));
-                    X[j] = __ffma2_rn(cfx, r, X[j]);
-                    Y[j] = __ffma2_rn(cfy, r, Y[j]);
-                }
-            }
-        }
-    };
-
     // coordinates, part 1.  TPS: affine part + basis.  GIVEN / FLOW: the raw loads only (consumed after the
     // current tile's gather, so their latency hides behind it).
     auto coords_begin = [&](const int tt, Tile& T, float& xt, float2 (&X)[TR / 2], float2 (&Y)[TR / 2], float (&rx)[TR], float (&ry)[TR]) {
@@ -276,7 +230,7 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
                 X[j] = __ffma2_rn(l2, ytp, f2dup(bx));
                 Y[j] = __ffma2_rn(l5, ytp, f2dup(by));
             }
-            basis(xt, X, Y);
+            tile_tps_basis(recs, pn8, xt, X, Y);
         } else if (MODE == TMODE_GIVEN || MODE == TMODE_FLOW) {
 #pragma unroll
             for (int q = 0; q < TR; ++q) {
@@ -294,10 +248,9 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
             if (p.x_out && T.col_ok) {
 #pragma unroll
                 for (int j = 0; j < TR / 2; ++j) {
-                    const int row = row0 + 2 * j;
-                    const size_t i = ((size_t)b * oh + row) * ow + T.col;
-                    if (row < oh) { p.x_out[i] = X[j].x; p.y_out[i] = Y[j].x; }
-                    if (row + 1 < oh) { p.x_out[i + ow] = X[j].y; p.y_out[i + ow] = Y[j].y; }
+                    const size_t i = ((size_t)b * oh + row0 + 2 * j) * ow + T.col;
+                    if (2 * j < rows_ok) { p.x_out[i] = X[j].x; p.y_out[i] = Y[j].x; }
+                    if (2 * j + 1 < rows_ok) { p.x_out[i + ow] = X[j].y; p.y_out[i + ow] = Y[j].y; }
                 }
             }
             // x_pix = ((x + 1) * W) / 2   (ThinPlateSpline.py:48-49), separately rounded
@@ -326,9 +279,8 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
                         xn = zn != 0.0f ? DVSG_DIV(xn, zn) : 0.0f;   // tf.div_no_nan, :446-447
                         yn = zn != 0.0f ? DVSG_DIV(yn, zn) : 0.0f;
                     }
-                    const int row = row0 + q;
-                    if (p.x_out && T.col_ok && row < oh) {
-                        const size_t i = ((size_t)b * oh + row) * ow + T.col;
+                    if (p.x_out && T.col_ok && q < rows_ok) {
+                        const size_t i = ((size_t)b * oh + row0 + q) * ow + T.col;
                         p.x_out[i] = xn; p.y_out[i] = yn;
                     }
                     rx[q] = zp_pix_from_norm(xn, W); ry[q] = zp_pix_from_norm(yn, H);
@@ -383,9 +335,6 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
             tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
         }
     };
-#define DVSG_PAIR(J)                                                                                                            \
-    tile_pair<MODE, J>(cur.staged, cur.interior, XC[J], YC[J], cur.pitch, cur.sb, ot, wm1, hm1, W, H, srcb, mask_col, ow,       \
-                       cur.col_ok && row0 + 2 * J < oh, cur.col_ok && row0 + 2 * J + 1 < oh)
 
     // ---- the software pipeline: the coordinates of tile t+1 are computed BEFORE tile t is gathered, so the TMA copy of
     // a footprint has a whole coordinate phase to land before the warp waits for it
@@ -400,18 +349,26 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
         while (true) {
             const int tn = t + TNW;
             const bool has_next = tn < t_end;
+            if (has_next) coords_begin(tn, nxt, xt, XN, YN, rx, ry);
             if (out_pending) {             // the previous tile's tensor store must have read the output tile
                 if (lane == 0) bulk_wait_read0();
                 out_pending = false;
             }
-            if (has_next) coords_begin(tn, nxt, xt, XN, YN, rx, ry);
             __syncwarp();
-            if (cur.staged) { mbar_wait(mbar, phase); phase ^= 1u; }
-            float* mask_col = want_mask ? p.mask_out + ((size_t)b * oh + row0) * ow + cur.col : nullptr;
-            DVSG_PAIR(0);
-            DVSG_PAIR(1);
-            DVSG_PAIR(2);
-            DVSG_PAIR(3);
+            float* mask_col = (MASK && cur.col_ok) ? p.mask_out + ((size_t)b * oh + row0) * ow + cur.col : nullptr;
+            if (cur.staged) {
+                mbar_wait(mbar, phase); phase ^= 1u;
+                if (MODE != TMODE_TPS || cur.interior)
+                    gather_tile<MODE, false, MASK>(XC, YC, cur.pitch, cur.sb, ot, wm1, hm1, onex, mask_col, ow, rows_ok);
+                else
+                    gather_tile<MODE, true, MASK>(XC, YC, cur.pitch, cur.sb, ot, wm1, hm1, onex, mask_col, ow, rows_ok);
+            } else {
+#pragma unroll
+                for (int q = 0; q < TR; ++q) {
+                    const float xq = (q & 1) ? XC[q >> 1].y : XC[q >> 1].x, yq = (q & 1) ? YC[q >> 1].y : YC[q >> 1].x;
+                    general_pixel<MODE>(xq, yq, W, H, srcb, ot + q * TC * 3, (MASK && mask_col && q < rows_ok) ? mask_col + q * ow : nullptr);
+                }
+            }
 
             // S: output tile -> global with one TMA tensor store (clipped at the frame edge)
             fence_proxy_async_smem();      // this lane's generic-proxy writes -> visible to the async proxy
@@ -431,7 +388,6 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
             t = tn;
         }
     }
-#undef DVSG_PAIR
     if (out_pending && lane == 0) bulk_wait_read0();   // shared memory must outlive the store's reads
 }
 
@@ -439,7 +395,6 @@ __global__ void __launch_bounds__(TNT, MINB) warp_fwd_tile_kernel(const TilePara
 static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 static int g_tile_target_ctas = 148 * 5 * 4;
 static int g_tile_dbg = 0;
-static int g_tile_minb = 5;                // resident CTAs per SM the kernel is compiled for (5 or 6)
 
 bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0) {
     return C == 3 && W % 4 == 0 && ow % 4 == 0 && ow >= TC && oh >= TR && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
@@ -451,6 +406,7 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
     p.stage_bytes = TSTAGE_BYTES;
     p.dbg = g_tile_dbg;
+    p.one = 1.0f;
     p.n_tx = (p.ow + TC - 1) / TC;
     p.n_ty = (p.oh + TR - 1) / TR;
     const long long strips = (long long)p.B * p.n_ty;
@@ -471,12 +427,17 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     if (rc) return rc;
     const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)((p.pn + 7) & ~7) * sizeof(TpsRec) : 0);
     const dim3 grid((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B);
-    if (g_tile_minb >= 6) {
-        auto k = warp_fwd_tile_kernel<MODE, 6>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, TNT, smem, st>>>(p, maps);
-    } else {
-        auto k = warp_fwd_tile_kernel<MODE, 5>;
+    bool launched = false;
+    if constexpr (MODE == TMODE_TPS) {
+        if (p.mask_out) {
+            auto k = warp_fwd_tile_kernel<MODE, true>;
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k<<<grid, TNT, smem, st>>>(p, maps);
+            launched = true;
+        }
+    }
+    if (!launched) {
+        auto k = warp_fwd_tile_kernel<MODE, false>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, TNT, smem, st>>>(p, maps);
     }
@@ -520,7 +481,7 @@ int tile_homog(const float* im, const float* theta, int projective, float* out, 
 void tile_set_tuning(int stage_bytes, int target_ctas, int minb) {
     if (stage_bytes >= 0 && stage_bytes < 16) g_tile_dbg = stage_bytes;      // debug mask (the staging buffer is sized by the largest TMA box)
     if (target_ctas > 0) g_tile_target_ctas = target_ctas;
-    if (minb > 0) g_tile_minb = minb;
+    (void)minb;
 }
 
 }  // namespace dvsg

@@ -60,11 +60,8 @@ def main():
     if only in ('all', 'tps'):
         for amp in (0.2, 0.04, 0.0):
             U, coord, T = tps_case(B, H, W, 4, amp)
-            for minb in (5, 6):
-                lib.dvsg_set_tile_tuning(-1, -1, minb)
-                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
-                rec('tps720 4x4 amp=%.2f tile (compiled for %d CTAs/SM)' % (amp, minb), ms, px, 24)
-            lib.dvsg_set_tile_tuning(-1, -1, 5)
+            ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
+            rec('tps720 4x4 amp=%.2f tile' % amp, ms, px, 24)
             if amp == 0.2:
                 for tc in (148 * 5 * 4, 148 * 5 * 24):
                     lib.dvsg_set_tile_tuning(-1, tc, -1)
