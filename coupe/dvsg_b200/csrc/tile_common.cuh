@@ -131,7 +131,8 @@ __device__ __forceinline__ void tile_tps_tables(const float* __restrict__ Tb, co
 __device__ __forceinline__ void tile_tps_basis(const unsigned char* __restrict__ recs, const int pn8, const float xt,
                                                float2 (&X)[TR / 2], float2 (&Y)[TR / 2]) {
     const unsigned char* rp = recs;
-    for (int k = 0; k < pn8; k += 4) {
+    const unsigned char* const rend = recs + (size_t)pn8 * sizeof(TpsRec);
+    do {      // pn8 >= 4: no guard in front of the loop
 #pragma unroll
         for (int u = 0; u < 4; ++u, rp += sizeof(TpsRec)) {
             const float4 pc = *reinterpret_cast<const float4*>(rp);
@@ -144,6 +145,77 @@ __device__ __forceinline__ void tile_tps_basis(const unsigned char* __restrict__
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
                 const float2 d2 = __fadd2_rn(dxx, dy[j]);
+                const float2 r = __fmul2_rn(d2, f2(lg2_approx(d2.x), lg2_approx(d2.y)));
+                X[j] = __ffma2_rn(cfx, r, X[j]);
+                Y[j] = __ffma2_rn(cfy, r, Y[j]);
+            }
+        }
+    } while (rp != rend);
+}
+
+// ---- separable meshes (control point k = (gx[k % G], gy[k / G]), the regular mesh of every reference call site) --------
+// Same arithmetic in the same order as tile_tps_basis -- identical coordinates -- but the tables shrink from 48 B per
+// control point to 8 B (cx ln2, cy ln2) + 32 B per mesh ROW ((y_t - gy)^2 of the 8 tile rows) + 4 B per mesh column
+// (-gx): 34 instead of 96 shared-memory wavefronts per tile at G = 4 (a broadcast LDS.128 costs two wavefronts), and
+// (x_t - gx)^2 is formed once per mesh column instead of once per control point.
+template <int G>
+struct SepLayout {
+    static constexpr int DY = 0;                                   // float [G][TR]
+    static constexpr int CF = G * TR * 4;                          // float2 [G*G]
+    static constexpr int NPX = (CF + G * G * 8 + 15) & ~15;        // float [G]
+    static constexpr int BYTES = NPX + ((G * 4 + 15) & ~15);
+};
+// Tables of one strip; returns true (CTA-uniform) when the frame's mesh is separable and the compact tables were built,
+// false after building the generic records instead.  Contains one CTA barrier; the caller still needs its own.
+template <int G>
+__device__ __forceinline__ bool tile_tps_tables_sep(const float* __restrict__ Tb, const float* __restrict__ cb, int pn8, int row0, int oh,
+                                                    float step_y, int tid, int nthreads, float* s_lin, unsigned char* recs) {
+    constexpr int PN = G * G;
+    bool ok = true;
+    for (int k = tid; k < PN; k += nthreads)
+        ok = ok && __ldg(cb + 2 * k) == __ldg(cb + 2 * (k % G)) && __ldg(cb + 2 * k + 1) == __ldg(cb + 2 * (k / G * G) + 1);
+    if (!__syncthreads_and(ok)) {
+        tile_tps_tables(Tb, cb, PN, pn8, row0, oh, step_y, tid, nthreads, s_lin, reinterpret_cast<TpsRec*>(recs));
+        return false;
+    }
+    const int N = PN + 3, lane = tid & 31, warp = tid >> 5;
+    if (warp < 2) {
+        const float c0 = tps_affine0(Tb + warp * N, PN, lane);
+        if (lane == 0) s_lin[3 * warp] = c0;
+        else if (lane < 3) s_lin[3 * warp + lane] = __ldg(Tb + warp * N + lane);
+    }
+    float* dyt = reinterpret_cast<float*>(recs + SepLayout<G>::DY);
+    float2* cf = reinterpret_cast<float2*>(recs + SepLayout<G>::CF);
+    float* npx = reinterpret_cast<float*>(recs + SepLayout<G>::NPX);
+    for (int i = tid; i < G * TR; i += nthreads)
+        dyt[i] = tps_dy2(lin_coord(min(row0 + i % TR, oh - 1), step_y), __ldg(cb + 2 * (i / TR * G) + 1));
+    for (int k = tid; k < PN; k += nthreads) cf[k] = make_float2(__ldg(Tb + 3 + k) * TLN2, __ldg(Tb + N + 3 + k) * TLN2);
+    if (tid < G) npx[tid] = -__ldg(cb + 2 * tid);
+    return true;
+}
+template <int G>
+__device__ __forceinline__ void tile_tps_basis_sep(const unsigned char* __restrict__ recs, const float xt, float2 (&X)[TR / 2], float2 (&Y)[TR / 2]) {
+    const float* __restrict__ npx = reinterpret_cast<const float*>(recs + SepLayout<G>::NPX);
+    float dxx[G];
+#pragma unroll
+    for (int gx = 0; gx < G; ++gx) {
+        const float dx = DVSG_ADD(xt, npx[gx]);
+        dxx[gx] = DVSG_MUL(dx, dx);
+    }
+    const unsigned char* dp = recs + SepLayout<G>::DY;
+    const unsigned char* cp = recs + SepLayout<G>::CF;
+#pragma unroll 1
+    for (int gy = 0; gy < G; ++gy, dp += TR * 4, cp += G * 8) {
+        const float4 da = *reinterpret_cast<const float4*>(dp);
+        const float4 db = *reinterpret_cast<const float4*>(dp + 16);
+        const float2 dy[TR / 2] = {f2(da.x, da.y), f2(da.z, da.w), f2(db.x, db.y), f2(db.z, db.w)};
+#pragma unroll
+        for (int gx = 0; gx < G; ++gx) {
+            const float2 c = *reinterpret_cast<const float2*>(cp + gx * 8);
+            const float2 cfx = f2dup(c.x), cfy = f2dup(c.y), dx2 = f2dup(dxx[gx]);
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                const float2 d2 = __fadd2_rn(dx2, dy[j]);
                 const float2 r = __fmul2_rn(d2, f2(lg2_approx(d2.x), lg2_approx(d2.y)));
                 X[j] = __ffma2_rn(cfx, r, X[j]);
                 Y[j] = __ffma2_rn(cfy, r, Y[j]);

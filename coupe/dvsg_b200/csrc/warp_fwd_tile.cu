@@ -30,6 +30,8 @@
 //             global memory: footprints larger than the biggest box, non-finite coordinates
 // Nothing but the frames themselves touches HBM: the [B, pn+3, h*w] basis and the sampling
 // grid of the reference never exist (x, y are written only when the caller asks).
+#include <stdlib.h>
+
 #include "tile_common.cuh"
 
 namespace dvsg {
@@ -114,25 +116,27 @@ __device__ __forceinline__ void gather_pair(const float2 xp, const float2 yp, co
     // 00 = (x0,y0), 01 = (x1,y0), 10 = (x0,y1), 11 = (x1,y1)
     const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
     if (MASK) msum = add2x(add2x(add2x(w00, w10, one), w01, one), w11, one);   // A4 add_n order (mask = warp of ones)
+    // byte offsets as exact fp32 integers riding on 2^23: the float's bit pattern is 0x4B000000 + offset, and sb already has
+    // 0x4B000000 subtracted, so pattern + sb is the corner's address (one LDS [R + UR + imm] per channel, no integer ops)
     const float2 tx0 = __ffma2_rn(x0f, twelve, m23);
     const float2 o00 = __ffma2_rn(y0f, pitchf, tx0);
-    const float* __restrict__ p00a = reinterpret_cast<const float*>(sb + (__float_as_int(o00.x) & 0x7fffff));
-    const float* __restrict__ p00b = reinterpret_cast<const float*>(sb + (__float_as_int(o00.y) & 0x7fffff));
+    const float* __restrict__ p00a = reinterpret_cast<const float*>(sb + __float_as_uint(o00.x));
+    const float* __restrict__ p00b = reinterpret_cast<const float*>(sb + __float_as_uint(o00.y));
     const float *__restrict__ p01a, *__restrict__ p01b, *__restrict__ p10a, *__restrict__ p10b, *__restrict__ p11a, *__restrict__ p11b;
     if (!CLAMP) {
         p01a = p00a + 3; p01b = p00b + 3;
-        p10a = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p00a) + pitch);
-        p10b = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p00b) + pitch);
+        p10a = reinterpret_cast<const float*>(sb + pitch + __float_as_uint(o00.x));
+        p10b = reinterpret_cast<const float*>(sb + pitch + __float_as_uint(o00.y));
         p11a = p10a + 3; p11b = p10b + 3;
     } else {
         const float2 tx1 = __ffma2_rn(x1f, twelve, m23);
         const float2 o01 = __ffma2_rn(y0f, pitchf, tx1), o10 = __ffma2_rn(y1f, pitchf, tx0), o11 = __ffma2_rn(y1f, pitchf, tx1);
-        p01a = reinterpret_cast<const float*>(sb + (__float_as_int(o01.x) & 0x7fffff));
-        p01b = reinterpret_cast<const float*>(sb + (__float_as_int(o01.y) & 0x7fffff));
-        p10a = reinterpret_cast<const float*>(sb + (__float_as_int(o10.x) & 0x7fffff));
-        p10b = reinterpret_cast<const float*>(sb + (__float_as_int(o10.y) & 0x7fffff));
-        p11a = reinterpret_cast<const float*>(sb + (__float_as_int(o11.x) & 0x7fffff));
-        p11b = reinterpret_cast<const float*>(sb + (__float_as_int(o11.y) & 0x7fffff));
+        p01a = reinterpret_cast<const float*>(sb + __float_as_uint(o01.x));
+        p01b = reinterpret_cast<const float*>(sb + __float_as_uint(o01.y));
+        p10a = reinterpret_cast<const float*>(sb + __float_as_uint(o10.x));
+        p10b = reinterpret_cast<const float*>(sb + __float_as_uint(o10.y));
+        p11a = reinterpret_cast<const float*>(sb + __float_as_uint(o11.x));
+        p11b = reinterpret_cast<const float*>(sb + __float_as_uint(o11.y));
     }
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -166,7 +170,9 @@ __device__ __forceinline__ void gather_tile(const float2 (&XC)[TR / 2], const fl
     }
 }
 
-template <int MODE, bool MASK>
+// G > 0: kernel specialised for G x G meshes; the compact separable-mesh tables are used when the frame's mesh is
+// separable (checked in the prologue), the generic records otherwise.
+template <int MODE, bool MASK, int G>
 __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams p, const __grid_constant__ TileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_mbar[TNW];
@@ -190,9 +196,13 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
     // ---- prologue: mbarriers, per-strip tables (the only CTA barrier of the kernel) -----------------
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     if (tid < TR) s_yt[tid] = lin_coord(min(row0 + tid, oh - 1), p.step_y);
+    bool sep = false;
     if (MODE == TMODE_TPS) {
-        tile_tps_tables(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, pn8, row0, oh, p.step_y, tid, TNT,
-                        s_lin, reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes)));
+        unsigned char* tab = smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes);
+        const float* Tb = p.T + (size_t)b * 2 * (p.pn + 3);
+        const float* cb = p.coord + (size_t)b * p.coord_stride;
+        if (G > 0) sep = tile_tps_tables_sep<(G > 0 ? G : 1)>(Tb, cb, pn8, row0, oh, p.step_y, tid, TNT, s_lin, tab);
+        else tile_tps_tables(Tb, cb, p.pn, pn8, row0, oh, p.step_y, tid, TNT, s_lin, reinterpret_cast<TpsRec*>(tab));
     } else if (MODE == TMODE_HOMOG) {
         const int nt = p.projective ? 8 : 6;
         if (tid < 9) s_lin[tid] = tid < nt ? __ldg(p.theta + (size_t)b * nt + tid) : (tid == 8 ? 1.0f : 0.0f);
@@ -230,7 +240,8 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
                 X[j] = __ffma2_rn(l2, ytp, f2dup(bx));
                 Y[j] = __ffma2_rn(l5, ytp, f2dup(by));
             }
-            tile_tps_basis(recs, pn8, xt, X, Y);
+            if (G > 0 && sep) tile_tps_basis_sep<(G > 0 ? G : 1)>(recs, xt, X, Y);
+            else tile_tps_basis(recs, pn8, xt, X, Y);
         } else if (MODE == TMODE_GIVEN || MODE == TMODE_FLOW) {
 #pragma unroll
             for (int q = 0; q < TR; ++q) {
@@ -319,17 +330,16 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
         // the box starts at a 16-byte aligned float (TMA faults on unaligned box origins)
         const int fx0 = (fx_lo * 3) & ~3;
         const int fw = (fx_hi + 1) * 3 - fx0, nrows = fy_hi - fy_lo + 1;
-        int box = -1;
-        if (fw <= p.bw[0]) box = nrows <= p.bh[0] ? 0 : (nrows <= p.bh[1] ? 1 : -1);
-        else if (fw <= p.bw[2] && nrows <= p.bh[2]) box = 2;
-        if ((p.dbg & 1) && box == 1) box = -1;
-        if ((p.dbg & 2) && box == 2) box = -1;
-        T.pitch = (box == 2 ? p.bw[2] : p.bw[0]) * 4;
-        const int box_rows = box == 0 ? p.bh[0] : (box == 1 ? p.bh[1] : p.bh[2]);
-        // the packed gather forms byte offsets as exact fp32 integers below 2^22
-        T.staged = box >= 0 && all_sane && (long long)(fy_hi + 3) * T.pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
-        // sb = staging address of frame pixel (0,0); padded-frame modes index pixel idx-1: fold the -1 into it
-        T.sb = w_stage - (fy_lo * T.pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : T.pitch + 12);
+        // box 0: 128 x 10, box 1: 128 x 13, box 2: 160 x 10 (floats x rows; a box disabled by the host has height 0)
+        const bool wide = fw > p.bw[0];
+        const int box = wide ? 2 : (nrows <= p.bh[0] ? 0 : 1);
+        const int box_rows = wide ? p.bh[2] : (nrows <= p.bh[0] ? p.bh[0] : p.bh[1]);
+        T.pitch = (wide ? p.bw[2] : p.bw[0]) * 4;
+        // p.bh[] are 0 for frames whose byte offsets would not fit the packed gather's exact fp32 integers (< 2^22)
+        T.staged = all_sane && fw <= p.bw[2] && nrows <= box_rows;
+        // sb = staging address of frame pixel (0,0) minus the bit pattern of 2^23 (see gather_pair); padded-frame modes
+        // index pixel idx-1: fold the -1 into it
+        T.sb = w_stage - (fy_lo * T.pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : T.pitch + 12) - 0x4B000000ll;
         if (T.staged && lane == 0) {
             mbar_arrive_expect_tx(mbar, (unsigned)(T.pitch * box_rows));
             tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
@@ -395,6 +405,23 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
 static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 static int g_tile_target_ctas = 148 * 5 * 4;
 static int g_tile_dbg = 0;
+// staging boxes of the forward kernel (floats x rows): box 0 = bw0 x bh0, box 1 = bw0 x bh1, box 2 = bw2 x bh2.
+// 128 x 10 (5 KB) covers 60 % of the tiles of a +-0.1 TPS warp at 720p; 128 x 15 and 160 x 12 (7.5 KB, the most that
+// still leaves 5 CTAs per SM) cover all but ~0.05 % -- a tile that fits no box takes the per-pixel path, which costs
+// about six staged tiles, so the tall boxes are worth their extra TMA bytes (measured: 63.1 % -> 67.5 % of HBM).
+static int g_bw0 = 128, g_bh0 = 10, g_bh1 = 15, g_bw2 = 160, g_bh2 = 12;
+static void tile_env_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char* e = getenv("DVSG_TILE_BOXES")) {       // experiments only: "bw0,bh0,bh1,bw2,bh2"
+        int v[5];
+        if (sscanf(e, "%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4) == 5 && v[0] % 32 == 0 && v[3] % 4 == 0) {
+            g_bw0 = v[0]; g_bh0 = v[1]; g_bh1 = v[2]; g_bw2 = v[3]; g_bh2 = v[4];
+        }
+    }
+}
+static int tile_stage_bytes() { return 4 * max(g_bw0 * max(g_bh0, g_bh1), g_bw2 * g_bh2); }
 
 bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0) {
     return C == 3 && W % 4 == 0 && ow % 4 == 0 && ow >= TC && oh >= TR && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
@@ -404,7 +431,8 @@ bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh,
 template <int MODE>
 static int launch_tile(TileParams p, cudaStream_t st) {
     if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
-    p.stage_bytes = TSTAGE_BYTES;
+    tile_env_once();
+    p.stage_bytes = tile_stage_bytes();
     p.dbg = g_tile_dbg;
     p.one = 1.0f;
     p.n_tx = (p.ow + TC - 1) / TC;
@@ -417,29 +445,31 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
     TileMaps maps;
+    // the packed gather forms byte offsets y*pitch + x*12 as exact fp32 integers below 2^22 (corners reach one pixel
+    // past the frame in the padded modes); larger frames take the per-pixel path
+    const bool offsets_fit = (long long)(p.H + 3) * (max(g_bw0, g_bw2) * 4) + (long long)(p.W + 3) * 12 < (1LL << 22);
     for (int i = 0; i < NBOX; ++i) {
-        p.bw[i] = min(box_w(i), 3 * p.W);      // a box may not exceed the tensor (tiny frames)
-        p.bh[i] = min(box_h(i), p.H);
+        p.bw[i] = min(i == 2 ? g_bw2 : g_bw0, 3 * p.W);      // a box may not exceed the tensor (tiny frames)
+        p.bh[i] = min(i == 0 ? g_bh0 : (i == 1 ? g_bh1 : g_bh2), p.H);
         const int rc = encode_frames(&maps.src[i], p.src, p.B, p.H, p.W, p.bw[i], p.bh[i]);
         if (rc) return rc;
+        if (!offsets_fit || (i > 0 && (p.dbg & i))) p.bh[i] = 0;     // box disabled (debug mask: bit 0 = box 1, bit 1 = box 2)
     }
     const int rc = encode_frames(&maps.out, p.out, p.B, p.oh, p.ow, TC * 3, TR);
     if (rc) return rc;
     const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)((p.pn + 7) & ~7) * sizeof(TpsRec) : 0);
     const dim3 grid((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B);
-    bool launched = false;
-    if constexpr (MODE == TMODE_TPS) {
-        if (p.mask_out) {
-            auto k = warp_fwd_tile_kernel<MODE, true>;
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k<<<grid, TNT, smem, st>>>(p, maps);
-            launched = true;
-        }
-    }
-    if (!launched) {
-        auto k = warp_fwd_tile_kernel<MODE, false>;
+    auto go = [&](auto k) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, TNT, smem, st>>>(p, maps);
+    };
+    if constexpr (MODE == TMODE_TPS) {
+        const bool m = p.mask_out != nullptr;
+        if (p.pn == 16) { if (m) go(warp_fwd_tile_kernel<MODE, true, 4>); else go(warp_fwd_tile_kernel<MODE, false, 4>); }
+        else if (p.pn == 25) { if (m) go(warp_fwd_tile_kernel<MODE, true, 5>); else go(warp_fwd_tile_kernel<MODE, false, 5>); }
+        else { if (m) go(warp_fwd_tile_kernel<MODE, true, 0>); else go(warp_fwd_tile_kernel<MODE, false, 0>); }
+    } else {
+        go(warp_fwd_tile_kernel<MODE, false, 0>);
     }
     count_launch();
     return check_launch("warp_fwd_tile_kernel");

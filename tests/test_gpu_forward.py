@@ -144,6 +144,37 @@ def test_tps_forward_vs_oracle_seeded(shape, flags):
     np.testing.assert_array_equal(out, O.tps_interpolate(u, x, y, h, w).reshape(out.shape))
 
 
+@pytest.mark.parametrize('m', [4, 5, 6])
+def test_tps_irregular_and_mixed_meshes(m):
+    """Per-frame meshes: frame 0 keeps the regular (separable) mesh, frame 1 an irregular one, frame 2 a separable but
+    non-uniform one.  The tile kernel's compact separable-mesh tables and its generic records, and the direct kernel,
+    perform the same arithmetic: identical bits; values against the oracle within the stated tolerances."""
+    from coupe.dvsg_b200 import ops
+    b, h, w = 3, 96, 160
+    rng = np.random.default_rng(7 + m)
+    u = smooth_image(rng, b, h, w, 3)
+    coord = tiled_mesh(m, m, b)
+    coord[1] += rng.uniform(-0.05, 0.05, coord[1].shape).astype(np.float32)
+    reg = np.linspace(-1, 1, m)
+    gx = (reg + rng.uniform(-0.05, 0.05, m)).astype(np.float32)
+    gy = (reg + rng.uniform(-0.05, 0.05, m)).astype(np.float32)
+    coord[2] = np.stack(np.meshgrid(gx, gy), -1).reshape(m * m, 2)
+    vec = rng.uniform(-0.08, 0.08, coord.shape).astype(np.float32)
+    U, C_, S = cu(u), cu(coord), cu(vec)
+    T = ops.tps_solve(C_, C_ + S)
+    a = ops.tps_warp_fwd(U, C_, T, (h, w), want_grid=True, want_mask=True)
+    d = ops.tps_warp_fwd(U, C_, T, (h, w), want_grid=True, want_mask=True, flags=FORCE_DIRECT)
+    for p_, q_ in zip(a, d):
+        assert torch.equal(p_, q_)
+    for i in range(b):      # a frame's result does not depend on which table variant its batch neighbours take
+        one = ops.tps_warp_fwd(U[i:i + 1].contiguous(), C_[i:i + 1].contiguous(), T[i:i + 1].contiguous(), (h, w), want_grid=True)
+        assert torch.equal(one[0][0], a[0][i]) and torch.equal(one[1], a[1][i * h * w:(i + 1) * h * w])
+    r_out, r_x, r_y = O.thin_plate_spline(u, coord, vec, (h, w))
+    x, y = a[1].cpu().numpy(), a[2].cpu().numpy()
+    assert max(np.abs(x - r_x).max(), np.abs(y - r_y).max()) <= 2e-5
+    np.testing.assert_array_equal(a[0].cpu().numpy(), O.tps_interpolate(u, x, y, h, w).reshape(b, h, w, 3))
+
+
 def test_staged_and_direct_kernels_agree_bitwise_at_720p():
     """Full-size property: the shared-memory-staged kernel and the direct-gather kernel perform
     the same arithmetic, so their outputs are identical bit for bit (white-noise frames)."""
