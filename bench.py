@@ -301,6 +301,7 @@ def run_ours(args, wl):
 
     # ---- e2e: host buffers through the C-ABI host pipeline (TPS workloads with small meshes) ----
     e2e = None
+    e2e_u8 = None
     if kind == 'tps' and wl['mesh'] ** 2 + 3 <= 32 and not args.no_e2e:
         Be = min(B, args.e2e_frames)
         pipe = ops.HostPipeline(H, W, 3, wl['mesh'] ** 2, frames_per_chunk=max(1, min(args.e2e_chunk, Be)), n_slots=args.e2e_slots, device=local)
@@ -323,6 +324,24 @@ def run_ours(args, wl):
                'h2d_bytes_per_step': int(U_h.numel() * 4 + vec_h.numel() * 4 + mesh_h.numel() * 4),
                'd2h_bytes_per_step': int(out_h.numel() * 4), 'frames_per_step': Be,
                'api': 'dvsg_host_tps_warp (coupe.dvsg_b200.ops.HostPipeline.thin_plate_spline), pinned host buffers'}
+        # same call with uint8 frames on the host side (N4: ingest u/255 and egress uint8(x*255) on the device)
+        U8_h = (U_h * 255.0).to(torch.uint8).pin_memory()
+        out8_h = torch.empty_like(U8_h).pin_memory()
+        for _ in range(2):
+            pipe.thin_plate_spline_u8(U8_h, mesh_h, vec_h, out8_h)
+        barrier()
+        ts = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            pipe.thin_plate_spline_u8(U8_h, mesh_h, vec_h, out8_h)
+        te8 = time.perf_counter() - ts
+        if world > 1:
+            t = torch.tensor([te8], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te8 = float(t.item())
+        e2e_u8 = {'value': world * Be * H * W * args.e2e_steps / te8 / 1e6, 'unit': 'Mpix/s',
+                  'h2d_bytes_per_step': int(U8_h.numel() + vec_h.numel() * 4 + mesh_h.numel() * 4),
+                  'd2h_bytes_per_step': int(out8_h.numel()), 'frames_per_step': Be,
+                  'api': 'dvsg_host_tps_warp_u8 (HostPipeline.thin_plate_spline_u8): uint8 BGR frames in and out, eval.py:76-81,112-113 on the device'}
         pipe.close()
 
     if rank == 0:
@@ -366,6 +385,8 @@ def run_ours(args, wl):
                          'algorithmic_bytes_per_px': fwd_bpp, 'kernel_ms': kern_ms, **extra},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
         }
+        if e2e_u8 is not None:
+            line['e2e_u8'] = e2e_u8
         if not args.no_cpu and world == 1:
             threads = min(os.cpu_count() or 1, 16)
             threads, frames = cpu_sample_plan(wl, threads)

@@ -34,6 +34,9 @@ PROTOTYPES = {
     'dvsg_host_pipeline_create': (c_int, [ctypes.POINTER(c_void_p)] + [c_int] * 7),
     'dvsg_host_pipeline_destroy': (None, [_P]),
     'dvsg_host_tps_warp': (c_int, [_P, _P, _P, _P, _P, c_int]),
+    'dvsg_frames_u8_to_f32': (c_int, [_P, _P, c_longlong, c_int, _P]),
+    'dvsg_frames_f32_to_u8': (c_int, [_P, _P, c_longlong, c_int, _P]),
+    'dvsg_host_tps_warp_u8': (c_int, [_P, _P, _P, _P, _P, c_int, c_int]),
 }
 # tuning knobs used by bench / profiling experiments (exported, but not in the public header)
 TUNING_PROTOTYPES = {

@@ -49,6 +49,7 @@ struct dvsg_host_pipeline {
     float* d_coord;                 // [pn, 2] shared mesh
     std::vector<cudaStream_t> streams;
     std::vector<float*> d_in, d_out, d_vec, d_T;
+    std::vector<unsigned char*> d_in8, d_out8;     // uint8 staging of the frames (allocated by the first u8 call)
 };
 
 #define DVSG_CUDA(call)                                                   \
@@ -97,6 +98,8 @@ extern "C" void dvsg_host_pipeline_destroy(dvsg_host_pipeline* p) {
     for (auto q : p->d_out) cudaFree(q);
     for (auto q : p->d_vec) cudaFree(q);
     for (auto q : p->d_T) cudaFree(q);
+    for (auto q : p->d_in8) cudaFree(q);
+    for (auto q : p->d_out8) cudaFree(q);
     cudaFree(p->d_coord);
     delete p;
 }
@@ -135,6 +138,55 @@ extern "C" int dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, co
                                p->C, p->H, p->W, pn, 0, st);
         if (rc) return rc;
         DVSG_CUDA(cudaMemcpyAsync(out_host + (size_t)f0 * fe, p->d_out[s], fe * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    for (auto st : p->streams) DVSG_CUDA(cudaStreamSynchronize(st));
+    return DVSG_OK;
+}
+
+// Same pipeline with uint8 frames on the host side: the ingest u/255 (+ optional BGR->RGB) and the
+// egress uint8(x*255) (+ RGB->BGR) of eval.py:79-80,112-113 run on the device, so a frame crosses PCIe as 3 bytes per
+// pixel each way instead of 12.  The warp itself is the unchanged fp32 path.
+extern "C" int dvsg_host_tps_warp_u8(dvsg_host_pipeline* p, const unsigned char* U_host, const float* coord_host,
+                                     const float* vector_host, unsigned char* out_host, int B, int swap_rb) {
+    DVSG_REQUIRE(p && B >= 0, "host_tps_warp_u8: bad argument");
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(U_host && coord_host && vector_host && out_host, "host_tps_warp_u8: null pointer");
+    DVSG_REQUIRE(p->C == 3, "host_tps_warp_u8: uint8 frames are 3-channel (the pipeline was created with C = %d)", p->C);
+    DVSG_CUDA(cudaSetDevice(p->device));
+    const size_t fe = p->frame_elems;
+    const int pn = p->pn;
+    while ((int)p->d_in8.size() < p->n_slots) {
+        unsigned char *a = nullptr, *b = nullptr;
+        DVSG_CUDA(cudaMalloc(&a, fe * p->fpc));
+        p->d_in8.push_back(a);
+        DVSG_CUDA(cudaMalloc(&b, fe * p->fpc));
+        p->d_out8.push_back(b);
+    }
+    DVSG_CUDA(cudaMemcpyAsync(p->d_coord, coord_host, (size_t)pn * 2 * sizeof(float), cudaMemcpyHostToDevice, p->streams[0]));
+    DVSG_CUDA(cudaStreamSynchronize(p->streams[0]));
+    int chunk = 0;
+    for (int f0 = 0; f0 < B; f0 += p->fpc, ++chunk) {
+        const int s = chunk % p->n_slots;
+        const int nf = B - f0 < p->fpc ? B - f0 : p->fpc;
+        cudaStream_t st = p->streams[s];
+        DVSG_CUDA(cudaMemcpyAsync(p->d_in8[s], U_host + (size_t)f0 * fe, fe * nf, cudaMemcpyHostToDevice, st));
+        DVSG_CUDA(cudaMemcpyAsync(p->d_vec[s], vector_host + (size_t)f0 * pn * 2, (size_t)nf * pn * 2 * sizeof(float),
+                                  cudaMemcpyHostToDevice, st));
+        int rc = dvsg_frames_u8_to_f32(p->d_in8[s], p->d_in[s], (long long)nf * p->H * p->W, swap_rb, st);
+        if (rc) return rc;
+        const int n = nf * pn * 2;
+        add_mesh_kernel<<<(n + 255) / 256, 256, 0, st>>>(p->d_coord, p->d_vec[s], n, pn * 2);
+        count_launch();
+        rc = check_launch("add_mesh_kernel");
+        if (rc) return rc;
+        rc = dvsg_tps_solve(p->d_coord, 0, p->d_vec[s], p->d_T[s], nf, pn, nullptr, 0, st);
+        if (rc) return rc;
+        rc = dvsg_tps_warp_fwd(p->d_in[s], p->d_coord, 0, p->d_T[s], p->d_out[s], nullptr, nullptr, nullptr, nf, p->H, p->W,
+                               p->C, p->H, p->W, pn, 0, st);
+        if (rc) return rc;
+        rc = dvsg_frames_f32_to_u8(p->d_out[s], p->d_out8[s], (long long)nf * p->H * p->W, swap_rb, st);
+        if (rc) return rc;
+        DVSG_CUDA(cudaMemcpyAsync(out_host + (size_t)f0 * fe, p->d_out8[s], fe * nf, cudaMemcpyDeviceToHost, st));
     }
     for (auto st : p->streams) DVSG_CUDA(cudaStreamSynchronize(st));
     return DVSG_OK;

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
         // the box starts at a 16-byte aligned float (TMA faults on unaligned box origins)
         const int fx0 = (fx_lo * 3) & ~3;
         const int fw = (fx_hi + 1) * 3 - fx0, nrows = fy_hi - fy_lo + 1;
-        // box 0: 128 x 10, box 1: 128 x 13, box 2: 160 x 10 (floats x rows; a box disabled by the host has height 0)
+        // box 0 / 1: bw[0] wide, bh[0] / bh[1] rows; box 2: bw[2] x bh[2] (floats x rows; a box disabled by the host has height 0)
         const bool wide = fw > p.bw[0];
         const int box = wide ? 2 : (nrows <= p.bh[0] ? 0 : 1);
         const int box_rows = wide ? p.bh[2] : (nrows <= p.bh[0] ? p.bh[0] : p.bh[1]);
@@ -406,22 +406,24 @@ static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f;
 static int g_tile_target_ctas = 148 * 5 * 4;
 static int g_tile_dbg = 0;
 // staging boxes of the forward kernel (floats x rows): box 0 = bw0 x bh0, box 1 = bw0 x bh1, box 2 = bw2 x bh2.
-// 128 x 10 (5 KB) covers 60 % of the tiles of a +-0.1 TPS warp at 720p; 128 x 15 and 160 x 12 (7.5 KB, the most that
-// still leaves 5 CTAs per SM) cover all but ~0.05 % -- a tile that fits no box takes the per-pixel path, which costs
-// about six staged tiles, so the tall boxes are worth their extra TMA bytes (measured: 63.1 % -> 67.5 % of HBM).
-static int g_bw0 = 128, g_bh0 = 10, g_bh1 = 15, g_bw2 = 160, g_bh2 = 12;
+// TPS / homography (smooth maps): 128 x 10 (5 KB) covers 60 % of the tiles of a +-0.1 TPS warp at 720p; 128 x 15 and
+// 160 x 12 (7.5 KB, the most that still leaves 5 CTAs per SM) cover all but ~0.05 % -- a tile that fits no box takes
+// the per-pixel path, which costs about six staged tiles, so the tall boxes are worth their extra TMA bytes
+// (measured: 63.1 % -> 67.5 % of HBM).  Given-grid and flow samplers take arbitrary fields: their boxes stay at
+// 128 x 13 / 160 x 10, because the per-pixel path of a rough field lives on the L1 cache that a larger shared-memory
+// carve-out takes away (white-noise +-8 px flow: 0.57 ms with the small boxes, 1.17 ms with the large ones).
+struct BoxSet { int bw0, bh0, bh1, bw2, bh2; };
+static BoxSet g_box_smooth = {128, 10, 15, 160, 12}, g_box_field = {BOX_W0, BOX_H0, BOX_H1, BOX_W2, BOX_H2};
 static void tile_env_once() {
     static bool done = false;
     if (done) return;
     done = true;
     if (const char* e = getenv("DVSG_TILE_BOXES")) {       // experiments only: "bw0,bh0,bh1,bw2,bh2"
         int v[5];
-        if (sscanf(e, "%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4) == 5 && v[0] % 32 == 0 && v[3] % 4 == 0) {
-            g_bw0 = v[0]; g_bh0 = v[1]; g_bh1 = v[2]; g_bw2 = v[3]; g_bh2 = v[4];
-        }
+        if (sscanf(e, "%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4) == 5 && v[0] % 32 == 0 && v[3] % 4 == 0)
+            g_box_smooth = g_box_field = BoxSet{v[0], v[1], v[2], v[3], v[4]};
     }
 }
-static int tile_stage_bytes() { return 4 * max(g_bw0 * max(g_bh0, g_bh1), g_bw2 * g_bh2); }
 
 bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0) {
     return C == 3 && W % 4 == 0 && ow % 4 == 0 && ow >= TC && oh >= TR && aligned16(src) && aligned16(out) && W < (1 << 20) && H < (1 << 20) &&
@@ -432,7 +434,8 @@ template <int MODE>
 static int launch_tile(TileParams p, cudaStream_t st) {
     if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
     tile_env_once();
-    p.stage_bytes = tile_stage_bytes();
+    const BoxSet bx = (MODE == TMODE_TPS || MODE == TMODE_HOMOG) ? g_box_smooth : g_box_field;
+    p.stage_bytes = 4 * max(bx.bw0 * max(bx.bh0, bx.bh1), bx.bw2 * bx.bh2);
     p.dbg = g_tile_dbg;
     p.one = 1.0f;
     p.n_tx = (p.ow + TC - 1) / TC;
@@ -447,10 +450,10 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     TileMaps maps;
     // the packed gather forms byte offsets y*pitch + x*12 as exact fp32 integers below 2^22 (corners reach one pixel
     // past the frame in the padded modes); larger frames take the per-pixel path
-    const bool offsets_fit = (long long)(p.H + 3) * (max(g_bw0, g_bw2) * 4) + (long long)(p.W + 3) * 12 < (1LL << 22);
+    const bool offsets_fit = (long long)(p.H + 3) * (max(bx.bw0, bx.bw2) * 4) + (long long)(p.W + 3) * 12 < (1LL << 22);
     for (int i = 0; i < NBOX; ++i) {
-        p.bw[i] = min(i == 2 ? g_bw2 : g_bw0, 3 * p.W);      // a box may not exceed the tensor (tiny frames)
-        p.bh[i] = min(i == 0 ? g_bh0 : (i == 1 ? g_bh1 : g_bh2), p.H);
+        p.bw[i] = min(i == 2 ? bx.bw2 : bx.bw0, 3 * p.W);      // a box may not exceed the tensor (tiny frames)
+        p.bh[i] = min(i == 0 ? bx.bh0 : (i == 1 ? bx.bh1 : bx.bh2), p.H);
         const int rc = encode_frames(&maps.src[i], p.src, p.B, p.H, p.W, p.bw[i], p.bh[i]);
         if (rc) return rc;
         if (!offsets_fit || (i > 0 && (p.dbg & i))) p.bh[i] = 0;     // box disabled (debug mask: bit 0 = box 1, bit 1 = box 2)

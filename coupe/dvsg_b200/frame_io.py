@@ -1,0 +1,43 @@
+"""Frame ingest / egress on the device.
+
+The reference's inference loop converts every frame on the CPU (eval.py:76-81: BGR uint8 -> RGB, / 255.) and converts
+the stabilised frame back (eval.py:112-113: np.uint8(x * 255.), RGB -> BGR).  These are the same two conversions as
+CUDA kernels behind the C ABI (dvsg_frames_u8_to_f32 / dvsg_frames_f32_to_u8), so frames can cross PCIe as uint8.
+The resize of eval.py:80 is the identity for videos that already have the working size and is not implemented.
+"""
+import torch
+
+from . import _lib
+from ._tensors import stream_ptr
+
+
+def _check_u8(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError('%s: expected a CUDA torch tensor (no CPU fallback on this path)' % name)
+    if t.shape[-1] != 3:
+        raise ValueError('%s: frames are [..., 3], got %r' % (name, tuple(t.shape)))
+    return t.contiguous()
+
+
+def frames_u8_to_f32(frames_u8, swap_rb=True):
+    """uint8 [..., H, W, 3] (BGR when swap_rb) -> fp32 RGB in [0, 1] = u / 255  (eval.py:79-80)."""
+    f = _check_u8(frames_u8, 'frames_u8')
+    if f.dtype != torch.uint8:
+        raise ValueError('frames_u8: dtype must be uint8, got %s' % f.dtype)
+    out = torch.empty(f.shape, dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        rc = _lib.load().dvsg_frames_u8_to_f32(f.data_ptr(), out.data_ptr(), f.numel() // 3, 1 if swap_rb else 0, stream_ptr(f.device))
+    _lib.check(rc, 'dvsg_frames_u8_to_f32')
+    return out
+
+
+def frames_f32_to_u8(frames_f32, swap_rb=True):
+    """fp32 [..., H, W, 3] RGB -> uint8 (BGR when swap_rb) = uint8(x * 255.)  (eval.py:112-113)."""
+    f = _check_u8(frames_f32, 'frames_f32')
+    if f.dtype != torch.float32:
+        raise ValueError('frames_f32: dtype must be float32, got %s' % f.dtype)
+    out = torch.empty(f.shape, dtype=torch.uint8, device=f.device)
+    with torch.cuda.device(f.device):
+        rc = _lib.load().dvsg_frames_f32_to_u8(f.data_ptr(), out.data_ptr(), f.numel() // 3, 1 if swap_rb else 0, stream_ptr(f.device))
+    _lib.check(rc, 'dvsg_frames_f32_to_u8')
+    return out

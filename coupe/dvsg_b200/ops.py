@@ -335,6 +335,28 @@ class HostPipeline(object):
         _lib.check(rc, 'dvsg_host_tps_warp')
         return out_host
 
+    def thin_plate_spline_u8(self, U_host, coord_host, vector_host, out_host=None, swap_rb=True):
+        """Same call with uint8 frames on the host side: U_host [B,H,W,3] uint8 (BGR when swap_rb,
+        as cv2 delivers it) -> ingest u/255 on the device -> fp32 ThinPlateSpline -> egress uint8(x*255) -> out_host
+        uint8.  3 bytes per pixel cross PCIe each way instead of 12."""
+        lib = _lib.load()
+        if U_host.is_cuda or U_host.dtype != torch.uint8 or not U_host.is_contiguous():
+            raise ValueError('U must be a contiguous uint8 CPU tensor')
+        for name, t in (('coord', coord_host), ('vector', vector_host)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError('%s must be a contiguous fp32 CPU tensor' % name)
+        B = U_host.shape[0]
+        if tuple(U_host.shape[1:]) != self.shape or tuple(coord_host.shape) != (self.pn, 2) or tuple(vector_host.shape) != (B, self.pn, 2):
+            raise ValueError('shape mismatch with the pipeline configuration')
+        if out_host is None:
+            out_host = torch.empty_like(U_host, pin_memory=U_host.is_pinned())
+        elif out_host.is_cuda or out_host.dtype != torch.uint8 or not out_host.is_contiguous() or out_host.shape != U_host.shape:
+            raise ValueError('out must be a contiguous uint8 CPU tensor shaped like U')
+        rc = lib.dvsg_host_tps_warp_u8(self._h, U_host.data_ptr(), coord_host.data_ptr(), vector_host.data_ptr(), out_host.data_ptr(),
+                                       B, 1 if swap_rb else 0)
+        _lib.check(rc, 'dvsg_host_tps_warp_u8')
+        return out_host
+
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
             _lib.load().dvsg_host_pipeline_destroy(self._h)

@@ -147,3 +147,30 @@ def test_flow_warp_backward_matches_fp64_finite_differences():
     g_im, g_flow = O.tf_warp_bwd(im, flow, h, w, g_out, dtype=np.float64)
     assert np.abs(_fd(loss, im, 1e-6) - g_im).max() < 1e-6
     assert np.abs(_fd(loss, flow, 1e-7) - g_flow).max() < 1e-5
+
+
+# ---- N4: frame ingest / egress -------------------------------------------------------------------
+def test_frame_io_oracle_matches_cv2_and_numpy_casts():
+    """eval.py:76-81,112-113 are plain cv2 / NumPy calls: the oracle's restatement is compared with those very calls
+    (cv2.cvtColor for the channel order, np.uint8() for the cast), and the device formula for u/255 -- q = u*c,
+    r = fma(-255, q, u), q + r*c -- is checked for all 256 inputs in exact arithmetic."""
+    import cv2
+    rng = np.random.default_rng(0)
+    f8 = rng.integers(0, 256, (2, 9, 11, 3), dtype=np.uint8)
+    for i in range(2):
+        ref = (cv2.cvtColor(f8[i], cv2.COLOR_BGR2RGB) / 255.).astype(np.float32)
+        np.testing.assert_array_equal(O.frames_u8_to_f32(f8[i], True), ref)
+    x = rng.uniform(0, 1, (9, 11, 3)).astype(np.float32)
+    ref8 = cv2.cvtColor(np.uint8(x * 255.), cv2.COLOR_RGB2BGR)
+    np.testing.assert_array_equal(O.frames_f32_to_u8(x, True), ref8)
+    np.testing.assert_array_equal(O.frames_f32_to_u8(O.frames_u8_to_f32(f8, True), True), f8)   # round trip is the identity
+    from fractions import Fraction
+
+    def rn(fr):     # exact rational -> nearest float32
+        return np.float32(float(fr)) if fr == 0 else np.float32(np.float64(fr.numerator) / np.float64(fr.denominator))
+    c = np.float32(1.0 / 255.0)
+    for u in range(256):
+        q = np.float32(np.float32(u) * c)
+        r = rn(Fraction(u) - 255 * Fraction(float(q)))
+        q2 = rn(Fraction(float(q)) + Fraction(float(r)) * Fraction(float(c)))
+        assert q2 == np.float32(u / 255.), u
