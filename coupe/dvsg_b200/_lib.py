@@ -37,6 +37,11 @@ PROTOTYPES = {
     'dvsg_frames_u8_to_f32': (c_int, [_P, _P, c_longlong, c_int, _P]),
     'dvsg_frames_f32_to_u8': (c_int, [_P, _P, c_longlong, c_int, _P]),
     'dvsg_host_tps_warp_u8': (c_int, [_P, _P, _P, _P, _P, c_int, c_int]),
+    'dvsg_tps_eval_points': (c_int, [_P, c_longlong, _P, _P, _P, _P] + [c_int] * 5 + [_P]),
+    'dvsg_tps_eval_points_bwd': (c_int, [_P, c_longlong, _P, _P, _P, _P] + [c_int] * 5 + [_P]),
+    'dvsg_masked_mse_workspace_bytes': (c_size_t, [c_int, c_longlong]),
+    'dvsg_masked_mse_fwd': (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, c_size_t, c_int, c_longlong, c_int, _P]),
+    'dvsg_masked_mse_bwd': (c_int, [_P, _P, _P, c_int, _P, _P, ctypes.c_float, _P, _P, _P, c_int, c_longlong, c_int, _P]),
 }
 # tuning knobs used by bench / profiling experiments (exported, but not in the public header)
 TUNING_PROTOTYPES = {

@@ -155,6 +155,30 @@ int  dvsg_host_tps_warp_u8(dvsg_host_pipeline* p, const unsigned char* U_host,
                            const float* coord_host, const float* vector_host,
                            unsigned char* out_host, int B, int swap_rb);
 
+
+/* ---- N3: consumers of the warp outputs in the training graph -------------------------------------
+ * dvsg_tps_eval_points evaluates the spline of dvsg_tps_warp_fwd at the flat pixel indices
+ * idx [B,P] (idx = col + row*ow; idx == oh*ow gives -1) instead of gathering the dense grid as
+ * get_surf_loss does (trainer.py:363-386, tf.batch_gather at :379-380): x_out, y_out [B,P] equal
+ * x[b*oh*ow + idx] of the dense kernel bit for bit.  _bwd OVERWRITES grad_T [B,2,pn+3].
+ * dvsg_masked_mse_* replace Trainer.masked_MSE (trainer.py:232-243): per frame
+ * sq = sum((pred*mask - gt*mask)^2), msum = sum(mask); loss = mean_b div_no_nan(sq, msum).
+ * mask_channels is C or 1; the workspace holds the stage-1 partial sums (deterministic order).    */
+int dvsg_tps_eval_points(const float* coord, long long coord_batch_stride, const float* T,
+                         const int* idx, float* x_out, float* y_out, int B, int oh, int ow,
+                         int pn, int P, void* stream);
+int dvsg_tps_eval_points_bwd(const float* coord, long long coord_batch_stride, const int* idx,
+                             const float* grad_x, const float* grad_y, float* grad_T, int B,
+                             int oh, int ow, int pn, int P, void* stream);
+size_t dvsg_masked_mse_workspace_bytes(int B, long long n_per_frame);
+int dvsg_masked_mse_fwd(const float* pred, const float* gt, const float* mask, int mask_channels,
+                        float* sq_out, float* msum_out, float* loss_out, void* workspace,
+                        size_t workspace_bytes, int B, long long n_pixels, int C, void* stream);
+int dvsg_masked_mse_bwd(const float* pred, const float* gt, const float* mask, int mask_channels,
+                        const float* sq, const float* msum, float grad_loss, float* grad_pred,
+                        float* grad_gt, float* grad_mask, int B, long long n_pixels, int C,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,3 +174,25 @@ def test_frame_io_oracle_matches_cv2_and_numpy_casts():
         r = rn(Fraction(u) - 255 * Fraction(float(q)))
         q2 = rn(Fraction(float(q)) + Fraction(float(r)) * Fraction(float(c)))
         assert q2 == np.float32(u / 255.), u
+
+
+# ---- N3: masked MSE and surf loss ------------------------------------------------------------------
+def test_masked_mse_and_surf_loss_known_answers():
+    pred = np.full((2, 4, 4, 3), 0.75, np.float32)
+    gt = np.full((2, 4, 4, 3), 0.25, np.float32)
+    mask = np.zeros((2, 4, 4, 3), np.float32)
+    mask[0, :2] = 1.0                                    # 24 active elements in frame 0, none in frame 1
+    loss, sq, ms = O.masked_mse(pred, gt, mask)
+    assert sq[0] == 24 * 0.25 and ms[0] == 24 and sq[1] == 0 and ms[1] == 0
+    assert loss == (0.25 + 0.0) / 2                      # div_no_nan: the empty frame contributes 0
+    # identity spline: the grid holds the normalised pixel coordinates, so features that did not move give zero loss
+    h, w, b = 6, 8, 1
+    xs = np.tile(O.tf_linspace(-1, 1, w)[None], (h, 1)).reshape(-1)
+    ys = np.tile(O.tf_linspace(-1, 1, h)[:, None], (1, w)).reshape(-1)
+    surf = np.zeros((1, 2, 3, 2), np.int32)
+    surf[0, 0] = surf[0, 1] = [[1, 2], [7, 5], [0, 0]]
+    loss, idx = O.surf_loss(surf, xs, ys, np.array([3.0]), b, w, h)
+    assert list(idx[0]) == [1 + 2 * w, 7 + 5 * w, 0] and loss < 1e-12
+    surf[0, 0, 0] = [3, 2]                               # unstable feature two pixels to the right
+    loss, _ = O.surf_loss(surf, xs, ys, np.array([3.0]), b, w, h)
+    assert abs(loss - (2 * 2.0 / (w - 1)) ** 2 / 3.0) < 1e-6
