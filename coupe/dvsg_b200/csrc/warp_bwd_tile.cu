@@ -133,6 +133,120 @@ __device__ __forceinline__ void rmw_round(float* __restrict__ q, float c0, float
     __syncwarp();
 }
 
+// ---- one pixel pair (rows 2j, 2j+1 of the lane's column) of a staged tile, fast variant ---------------------------
+// Inlined four times per tile: out-of-line calls were measured and lose (caller-saved registers spill around every
+// call: 172 us instead of 157 us at the training shape), although the unrolled kernel is 110 KB of SASS.
+// Returns (d out/d x_pix of the two pixels, d out/d y_pix of the two pixels); scatters w_k * grad_out into the private
+// accumulation buffer (= staging buffer + TSTAGE_BYTES, same layout) with read-modify-write rounds.
+__device__ __forceinline__ float4 bwd_pair_fast(const float2 xp, const float2 yp, const float2 x0f, const float2 y0f, const float ga0, const float ga1,
+                                             const float ga2, const float gb0, const float gb1, const float gb2, const unsigned char* __restrict__ sb,
+                                             const int pitch, const bool scatter) {
+    const int lane = threadIdx.x & 31;
+    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
+    const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
+    const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
+    const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
+    const float2 o00 = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
+    const int ka = __float_as_int(o00.x) & 0x7fffff, kb = __float_as_int(o00.y) & 0x7fffff;
+    const float* __restrict__ pa = reinterpret_cast<const float*>(sb + ka);
+    const float* __restrict__ pb = reinterpret_cast<const float*>(sb + kb);
+    const float* __restrict__ qa = reinterpret_cast<const float*>(sb + ka + pitch);
+    const float* __restrict__ qb = reinterpret_cast<const float*>(sb + kb + pitch);
+    const float2 g[3] = {f2(ga0, gb0), f2(ga1, gb1), f2(ga2, gb2)};
+    float2 dx = f2dup(0.0f), dy = f2dup(0.0f);
+    float2 c00[3], c01[3], c10[3], c11[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float2 i00 = f2(pa[ch], pb[ch]), i01 = f2(pa[3 + ch], pb[3 + ch]);
+        const float2 i10 = f2(qa[ch], qb[ch]), i11 = f2(qa[3 + ch], qb[3 + ch]);
+        const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
+        const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
+        dx = __ffma2_rn(g[ch], ux, dx);
+        dy = __ffma2_rn(g[ch], uy, dy);
+        c00[ch] = __fmul2_rn(w00, g[ch]); c01[ch] = __fmul2_rn(w01, g[ch]);
+        c10[ch] = __fmul2_rn(w10, g[ch]); c11[ch] = __fmul2_rn(w11, g[ch]);
+    }
+    if (scatter) {
+        float* __restrict__ aa = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pa) + TSTAGE_BYTES));
+        float* __restrict__ ab = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pb) + TSTAGE_BYTES));
+        float* __restrict__ ca = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(qa) + TSTAGE_BYTES));
+        float* __restrict__ cb2 = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(qb) + TSTAGE_BYTES));
+        {   // row a: the four corner classes share one duplicate pattern (x1 = x0+1, y1 = y0+1)
+            const int nk = __shfl_down_sync(0xffffffffu, ka, 1), pk = __shfl_up_sync(0xffffffffu, ka, 1);
+            const bool head = lane == 0 || pk != ka, dupn = lane != 31 && nk == ka;
+            rmw_round(aa, c00[0].x, c00[1].x, c00[2].x, head, dupn);
+            rmw_round(aa + 3, c01[0].x, c01[1].x, c01[2].x, head, dupn);
+            rmw_round(ca, c10[0].x, c10[1].x, c10[2].x, head, dupn);
+            rmw_round(ca + 3, c11[0].x, c11[1].x, c11[2].x, head, dupn);
+        }
+        {   // row b
+            const int nk = __shfl_down_sync(0xffffffffu, kb, 1), pk = __shfl_up_sync(0xffffffffu, kb, 1);
+            const bool head = lane == 0 || pk != kb, dupn = lane != 31 && nk == kb;
+            rmw_round(ab, c00[0].y, c00[1].y, c00[2].y, head, dupn);
+            rmw_round(ab + 3, c01[0].y, c01[1].y, c01[2].y, head, dupn);
+            rmw_round(cb2, c10[0].y, c10[1].y, c10[2].y, head, dupn);
+            rmw_round(cb2 + 3, c11[0].y, c11[1].y, c11[2].y, head, dupn);
+        }
+    }
+    return make_float4(dx.x, dx.y, dy.x, dy.y);
+}
+
+// Clamped variant (TPS border tiles and folding maps): corners clamped first, weights FROM the clamped corners
+// (ThinPlateSpline.py:57-60, 81-88; the integer clamps pass no gradient).  The source pixels still come from the staged
+// footprint; the scatter goes straight to global memory as red.global.add.f32 (fire-and-forget, combined per sector
+// in L2): float atomics on shared memory are CAS loops and cost more than the whole per-pixel path.
+__device__ __forceinline__ float4 bwd_pair_clamped(const float2 xp, const float2 yp, const float ga0, const float ga1, const float ga2, const float gb0,
+                                                const float gb1, const float gb2, const unsigned char* __restrict__ sb, const int pitch, const int W,
+                                                const int H, float* __restrict__ gsrcb, const bool ok_a, const bool ok_b) {
+    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const float2 fx = floor2_any(xp), fy = floor2_any(yp);
+    const float2 hx = __fadd2_rn(fx, one2), hy = __fadd2_rn(fy, one2);
+    const float2 x0f = f2(fminf(fmaxf(fx.x, 0.0f), wm1), fminf(fmaxf(fx.y, 0.0f), wm1));
+    const float2 x1f = f2(fminf(fmaxf(hx.x, 0.0f), wm1), fminf(fmaxf(hx.y, 0.0f), wm1));
+    const float2 y0f = f2(fminf(fmaxf(fy.x, 0.0f), hm1), fminf(fmaxf(fy.y, 0.0f), hm1));
+    const float2 y1f = f2(fminf(fmaxf(hy.x, 0.0f), hm1), fminf(fmaxf(hy.y, 0.0f), hm1));
+    const float2 ax1 = sub2(x1f, xp), ax0 = sub2(xp, x0f), ay1 = sub2(y1f, yp), ay0 = sub2(yp, y0f);
+    const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
+    const float2 tx0 = __ffma2_rn(x0f, twelve, m23), tx1 = __ffma2_rn(x1f, twelve, m23);
+    const float2 o00 = __ffma2_rn(y0f, pitchf, tx0), o01 = __ffma2_rn(y0f, pitchf, tx1);
+    const float2 o10 = __ffma2_rn(y1f, pitchf, tx0), o11 = __ffma2_rn(y1f, pitchf, tx1);
+    const float* p00[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o00.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o00.y) & 0x7fffff))};
+    const float* p01[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o01.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o01.y) & 0x7fffff))};
+    const float* p10[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o10.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o10.y) & 0x7fffff))};
+    const float* p11[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o11.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o11.y) & 0x7fffff))};
+    // exact fp32 integers below 2^22 -> int through the 2^23 bit pattern (no F2I on the XU pipe)
+    const int xa[2] = {__float_as_int(x0f.x + MAGIC23) & 0x7fffff, __float_as_int(x0f.y + MAGIC23) & 0x7fffff};
+    const int xb[2] = {__float_as_int(x1f.x + MAGIC23) & 0x7fffff, __float_as_int(x1f.y + MAGIC23) & 0x7fffff};
+    const int ya[2] = {__float_as_int(y0f.x + MAGIC23) & 0x7fffff, __float_as_int(y0f.y + MAGIC23) & 0x7fffff};
+    const int yb[2] = {__float_as_int(y1f.x + MAGIC23) & 0x7fffff, __float_as_int(y1f.y + MAGIC23) & 0x7fffff};
+    const bool ok[2] = {ok_a, ok_b};
+    const float gq[2][3] = {{ga0, ga1, ga2}, {gb0, gb1, gb2}};
+    float2 dx = f2dup(0.0f), dy = f2dup(0.0f);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float2 g = f2(gq[0][ch], gq[1][ch]);
+        const float2 i00 = f2(p00[0][ch], p00[1][ch]), i01 = f2(p01[0][ch], p01[1][ch]);
+        const float2 i10 = f2(p10[0][ch], p10[1][ch]), i11 = f2(p11[0][ch], p11[1][ch]);
+        const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
+        const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
+        dx = __ffma2_rn(g, ux, dx);
+        dy = __ffma2_rn(g, uy, dy);
+        if (gsrcb) {
+            const float2 c00 = __fmul2_rn(w00, g), c01 = __fmul2_rn(w01, g), c10 = __fmul2_rn(w10, g), c11 = __fmul2_rn(w11, g);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!ok[h]) continue;      // duplicated edge pixels carry a zero gradient anyway
+                atomicAdd(gsrcb + ((size_t)ya[h] * W + xa[h]) * 3 + ch, h ? c00.y : c00.x);
+                atomicAdd(gsrcb + ((size_t)yb[h] * W + xa[h]) * 3 + ch, h ? c10.y : c10.x);
+                atomicAdd(gsrcb + ((size_t)ya[h] * W + xb[h]) * 3 + ch, h ? c01.y : c01.x);
+                atomicAdd(gsrcb + ((size_t)yb[h] * W + xb[h]) * 3 + ch, h ? c11.y : c11.x);
+            }
+        }
+    }
+    return make_float4(dx.x, dx.y, dy.x, dy.y);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTileParams p, const __grid_constant__ BwdTileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -243,7 +357,9 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         int fx_lo, fx_hi, fy_lo, fy_hi;
         if (MODE == TMODE_TPS) {
             interior = x_lo >= 0 && x_hi <= W - 1 && y_lo >= 0 && y_hi <= H - 1;
-            fx_lo = x_lo; fx_hi = x_hi; fy_lo = y_lo; fy_hi = y_hi;
+            // border tiles: the A4 sampler clamps its corners into the frame (ThinPlateSpline.py:57-60), so does the footprint
+            fx_lo = min(max(x_lo, 0), W - 1); fx_hi = min(max(x_hi, 0), W - 1);
+            fy_lo = min(max(y_lo, 0), H - 1); fy_hi = min(max(y_hi, 0), H - 1);
         } else {
             fx_lo = x_lo - 1; fx_hi = x_hi - 1; fy_lo = y_lo - 1; fy_hi = y_hi - 1;
             // frame-border tiles (footprint reaching into the zero padding) take the per-pixel path: the TMA
@@ -257,11 +373,14 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         else if (fw <= p.bw[2] && nrows <= p.bh[2]) box = 2;
         const int pitch = (box == 2 ? p.bw[2] : p.bw[0]) * 4;
         const int box_rows = box == 0 ? p.bh[0] : (box == 1 ? p.bh[1] : p.bh[2]);
-        bool staged = box >= 0 && all_sane && interior && (long long)(fy_hi + 3) * pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
-        // the read-modify-write rounds need source columns that do not decrease along a row and never repeat
-        // more than twice (x scale >= 0.5, no fold): otherwise this tile takes the per-pixel path
+        bool staged = box >= 0 && all_sane && (MODE == TMODE_TPS || interior) &&
+                      (long long)(fy_hi + 3) * pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
+        // Two staged variants.  fast: no corner touches the frame border and the source columns of every row do not
+        // decrease and never repeat more than twice (x scale >= 0.5, no fold) -- the read-modify-write rounds below.
+        // Otherwise (TPS only): clamped corners and shared-memory atomics into the same accumulation buffer.
+        bool fast = staged && interior;
         float2 X0F[TR / 2], Y0F[TR / 2];
-        if (staged) {
+        if (fast) {
             bool mono = true;
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
@@ -270,8 +389,9 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
                 const float b1 = __shfl_down_sync(0xffffffffu, X0F[j].y, 1), b2 = __shfl_down_sync(0xffffffffu, X0F[j].y, 2);
                 mono = mono && (lane == 31 || (a1 >= X0F[j].x && b1 >= X0F[j].y)) && (lane >= 30 || (a2 > X0F[j].x && b2 > X0F[j].y));
             }
-            staged = __all_sync(0xffffffffu, mono);
+            fast = __all_sync(0xffffffffu, mono);
         }
+        if (MODE != TMODE_TPS) staged = fast;      // the padded samplers have no clamped variant: per-pixel path
 
         // ================= L: stage the source footprint, clear the accumulation buffer =================
         if (red_pending) {                 // the previous tile's reduce-add must have read the accumulation buffer
@@ -284,7 +404,7 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
                 mbar_arrive_expect_tx(mbar, (unsigned)(pitch * box_rows));
                 tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
             }
-            if (gsrcb) {
+            if (gsrcb && fast) {
                 float4* z = reinterpret_cast<float4*>(w_acc);
                 const int n16 = pitch * box_rows / 16;
                 for (int i = lane; i < n16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -295,59 +415,21 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
 
         // ================= G: d out / d coordinates, scatter of grad_im =================
         float2 GX[TR / 2], GY[TR / 2];     // gradient w.r.t. the sampler's pixel-space coordinate, then chained
-        if (staged) {
+        if (fast) {
             const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
-            const float2 m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                const float2 xp = XP[j], yp = YP[j], x0f = X0F[j], y0f = Y0F[j];
-                const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
-                const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
-                const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
-                const float2 o00 = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
-                const int ka = __float_as_int(o00.x) & 0x7fffff, kb = __float_as_int(o00.y) & 0x7fffff;
-                const float* __restrict__ pa = reinterpret_cast<const float*>(sb + ka);
-                const float* __restrict__ pb = reinterpret_cast<const float*>(sb + kb);
-                const float* __restrict__ qa = reinterpret_cast<const float*>(sb + ka + pitch);
-                const float* __restrict__ qb = reinterpret_cast<const float*>(sb + kb + pitch);
-                float2 g[3], dx = f2dup(0.0f), dy = f2dup(0.0f);
-                float2 c00[3], c01[3], c10[3], c11[3];
+                const float4 d = bwd_pair_fast(XP[j], YP[j], X0F[j], Y0F[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0],
+                                               gq[2 * j + 1][1], gq[2 * j + 1][2], sb, pitch, gsrcb != nullptr);
+                GX[j] = f2(d.x, d.y); GY[j] = f2(d.z, d.w);
+            }
+        } else if (MODE == TMODE_TPS && staged) {
+            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4);
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    g[ch] = f2(gq[2 * j][ch], gq[2 * j + 1][ch]);
-                    const float2 i00 = f2(pa[ch], pb[ch]), i01 = f2(pa[3 + ch], pb[3 + ch]);
-                    const float2 i10 = f2(qa[ch], qb[ch]), i11 = f2(qa[3 + ch], qb[3 + ch]);
-                    const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
-                    const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
-                    dx = __ffma2_rn(g[ch], ux, dx);
-                    dy = __ffma2_rn(g[ch], uy, dy);
-                    c00[ch] = __fmul2_rn(w00, g[ch]); c01[ch] = __fmul2_rn(w01, g[ch]);
-                    c10[ch] = __fmul2_rn(w10, g[ch]); c11[ch] = __fmul2_rn(w11, g[ch]);
-                }
-                GX[j] = dx; GY[j] = dy;
-                if (gsrcb) {
-                    // accumulation buffer = staging buffer + TSTAGE_BYTES, same layout
-                    float* __restrict__ aa = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pa) + TSTAGE_BYTES));
-                    float* __restrict__ ab = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pb) + TSTAGE_BYTES));
-                    float* __restrict__ ca = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(qa) + TSTAGE_BYTES));
-                    float* __restrict__ cb2 = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(qb) + TSTAGE_BYTES));
-                    {   // row a: the four corner classes share one duplicate pattern (x1 = x0+1, y1 = y0+1)
-                        const int nk = __shfl_down_sync(0xffffffffu, ka, 1), pk = __shfl_up_sync(0xffffffffu, ka, 1);
-                        const bool head = lane == 0 || pk != ka, dupn = lane != 31 && nk == ka;
-                        rmw_round(aa, c00[0].x, c00[1].x, c00[2].x, head, dupn);
-                        rmw_round(aa + 3, c01[0].x, c01[1].x, c01[2].x, head, dupn);
-                        rmw_round(ca, c10[0].x, c10[1].x, c10[2].x, head, dupn);
-                        rmw_round(ca + 3, c11[0].x, c11[1].x, c11[2].x, head, dupn);
-                    }
-                    {   // row b
-                        const int nk = __shfl_down_sync(0xffffffffu, kb, 1), pk = __shfl_up_sync(0xffffffffu, kb, 1);
-                        const bool head = lane == 0 || pk != kb, dupn = lane != 31 && nk == kb;
-                        rmw_round(ab, c00[0].y, c00[1].y, c00[2].y, head, dupn);
-                        rmw_round(ab + 3, c01[0].y, c01[1].y, c01[2].y, head, dupn);
-                        rmw_round(cb2, c10[0].y, c10[1].y, c10[2].y, head, dupn);
-                        rmw_round(cb2 + 3, c11[0].y, c11[1].y, c11[2].y, head, dupn);
-                    }
-                }
+            for (int j = 0; j < TR / 2; ++j) {
+                const float4 d = bwd_pair_clamped(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1],
+                                                  gq[2 * j + 1][2], sb, pitch, W, H, gsrcb, col_ok && row0 + 2 * j < oh, col_ok && row0 + 2 * j + 1 < oh);
+                GX[j] = f2(d.x, d.y); GY[j] = f2(d.z, d.w);
             }
         } else {
 #pragma unroll
@@ -395,7 +477,7 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         }
 
         // ================= S: accumulation buffer -> grad_im with one TMA tensor reduce-add =================
-        if (staged && gsrcb) {
+        if (fast && gsrcb) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
