@@ -333,14 +333,17 @@ static size_t big_workspace_bytes(int B, int pn, long long stride) {
     return nsys * N * 2 * N * sizeof(double) + 256;   // + status word, kept 256-B apart
 }
 
+// prepared: 0 = invert into the workspace, then apply; 1 = the workspace already holds the inverse(s) of this mesh
+// (dvsg_tps_prepare), apply only; 2 = invert only
 template <bool TRANSPOSED>
 static int solve_impl(const float* coord, long long stride, const float* rhs, float* out, int B, int pn, void* ws,
-                      size_t ws_bytes, cudaStream_t st, const char* what) {
+                      size_t ws_bytes, cudaStream_t st, const char* what, int prepared = 0) {
     DVSG_REQUIRE(B >= 0 && pn >= 3, "%s: need B >= 0 and at least 3 control points (got B=%d pn=%d)", what, B, pn);
     if (B == 0) return DVSG_OK;
-    DVSG_REQUIRE(coord && rhs && out, "%s: null pointer", what);
+    DVSG_REQUIRE(coord && (prepared == 2 || (rhs && out)), "%s: null pointer", what);
     DVSG_REQUIRE(stride == 0 || stride >= 2LL * pn, "%s: coord stride %lld < 2*pn", what, stride);
     const int N = pn + 3;
+    if (N <= SMALL_N && prepared == 2) return DVSG_OK;      // small systems are factorised inside the solve kernels
     if (N <= SMALL_N && stride == 0) {
         tps_solve_shared_kernel<TRANSPOSED><<<(B + SH_FRAMES - 1) / SH_FRAMES, SH_THREADS, 0, st>>>(coord, rhs, out, B, pn);
         count_launch();
@@ -360,10 +363,12 @@ static int solve_impl(const float* coord, long long stride, const float* rhs, fl
     DVSG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7u) == 0, "%s: workspace must be 8-byte aligned", what);
     const int nsys = stride == 0 ? 1 : B;
     double* work = reinterpret_cast<double*>(ws);
-    tps_inverse_kernel<<<nsys, INV_THREADS, (size_t)3 * N * sizeof(double), st>>>(coord, stride, pn, work, nullptr);
-    count_launch();
-    int rc = check_launch("tps_inverse_kernel");
-    if (rc) return rc;
+    if (prepared != 1) {
+        tps_inverse_kernel<<<nsys, INV_THREADS, (size_t)3 * N * sizeof(double), st>>>(coord, stride, pn, work, nullptr);
+        count_launch();
+        const int rc = check_launch("tps_inverse_kernel");
+        if (rc || prepared == 2) return rc;
+    }
     const long long n_out = (long long)B * (TRANSPOSED ? pn : N);
     tps_apply_kernel<TRANSPOSED><<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(work, stride == 0, rhs, out, B, pn);
     count_launch();
@@ -382,6 +387,25 @@ extern "C" size_t dvsg_tps_solve_workspace_bytes(int B, int pn, long long coord_
 extern "C" int dvsg_tps_solve(const float* coord, long long coord_batch_stride, const float* target, float* T, int B, int pn,
                               void* workspace, size_t workspace_bytes, void* stream) {
     return solve_impl<false>(coord, coord_batch_stride, target, T, B, pn, workspace, workspace_bytes, (cudaStream_t)stream, "tps_solve");
+}
+
+// The mesh of a clip is a constant (model.py:62-68): dvsg_tps_prepare inverts its system(s) into the
+// workspace once, dvsg_tps_solve_prepared / _bwd_prepared then only apply W^-1 (a [B,N] x [N,N] product) per call.
+// For pn + 3 <= 32 the prepare step is a no-op and the prepared calls are the plain solves.
+extern "C" int dvsg_tps_prepare(const float* coord, long long coord_batch_stride, int B, int pn, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    return solve_impl<false>(coord, coord_batch_stride, nullptr, nullptr, B, pn, workspace, workspace_bytes, (cudaStream_t)stream, "tps_prepare", 2);
+}
+
+extern "C" int dvsg_tps_solve_prepared(const float* coord, long long coord_batch_stride, const float* target, float* T, int B, int pn,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    return solve_impl<false>(coord, coord_batch_stride, target, T, B, pn, workspace, workspace_bytes, (cudaStream_t)stream, "tps_solve_prepared", 1);
+}
+
+extern "C" int dvsg_tps_solve_bwd_prepared(const float* coord, long long coord_batch_stride, const float* grad_T, float* grad_target, int B,
+                                           int pn, void* workspace, size_t workspace_bytes, void* stream) {
+    return solve_impl<true>(coord, coord_batch_stride, grad_T, grad_target, B, pn, workspace, workspace_bytes, (cudaStream_t)stream,
+                            "tps_solve_bwd_prepared", 1);
 }
 
 extern "C" int dvsg_tps_solve_bwd(const float* coord, long long coord_batch_stride, const float* grad_T, float* grad_target,

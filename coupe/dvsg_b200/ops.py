@@ -6,6 +6,8 @@ warp_with_optical_flow.py) only rename these to the reference's signatures.
 """
 import ctypes
 
+import collections
+
 import torch
 
 from . import _lib
@@ -53,6 +55,32 @@ def _mesh_args(coord, B, pn_expected=None):
     return coord.contiguous(), pn * 2, pn
 
 
+# Inverse of the system of a constant shared mesh with more than 29 control points (cfg5: 16x16), kept per mesh so that
+# a clip inverts it once.  The entry holds the mesh storage alive, so its address cannot be recycled,
+# and is keyed on the tensor version, so an in-place update of the mesh invalidates it.
+_prepared = collections.OrderedDict()
+
+
+def _prepared_workspace(lib, cbuf, cstride, B, pn, nbytes):
+    """Workspace holding W^-1 for this mesh, or None when the system is small / per-frame (plain solve)."""
+    if nbytes == 0 or cstride != 0:
+        return None
+    st = cbuf.untyped_storage()
+    key = (cbuf.device.index, st.data_ptr(), cbuf.storage_offset(), cbuf._version, pn)
+    hit = _prepared.get(key)
+    if hit is None:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=cbuf.device)
+        with torch.cuda.device(cbuf.device):
+            rc = lib.dvsg_tps_prepare(ptr(cbuf), 0, B, pn, ptr(ws), nbytes, stream_ptr(cbuf.device))
+        _lib.check(rc, 'dvsg_tps_prepare')
+        _prepared[key] = hit = (ws, st)
+        while len(_prepared) > 4:
+            _prepared.popitem(last=False)
+    else:
+        _prepared.move_to_end(key)
+    return hit[0]
+
+
 # ---- K1 ------------------------------------------------------------------------------------
 def tps_solve(coord, target):
     """_solve_system (ThinPlateSpline.py:143-166) -> T [B, 2, pn+3]."""
@@ -67,9 +95,13 @@ def tps_solve(coord, target):
         raise ValueError('TPS needs at least 3 control points, got %d' % pn)
     T = torch.empty((B, 2, pn + 3), dtype=torch.float32, device=target.device)
     nbytes = lib.dvsg_tps_solve_workspace_bytes(B, pn, cstride)
-    ws = _workspace(target.device, nbytes)
+    pws = _prepared_workspace(lib, cbuf, cstride, B, pn, nbytes) if B > 0 else None
     with torch.cuda.device(target.device):
-        rc = lib.dvsg_tps_solve(ptr(cbuf), cstride, ptr(target), ptr(T), B, pn, ptr(ws), nbytes, stream_ptr(target.device))
+        if pws is not None:
+            rc = lib.dvsg_tps_solve_prepared(ptr(cbuf), cstride, ptr(target), ptr(T), B, pn, ptr(pws), nbytes, stream_ptr(target.device))
+        else:
+            ws = _workspace(target.device, nbytes)
+            rc = lib.dvsg_tps_solve(ptr(cbuf), cstride, ptr(target), ptr(T), B, pn, ptr(ws), nbytes, stream_ptr(target.device))
     _lib.check(rc, 'dvsg_tps_solve')
     return T
 
@@ -81,9 +113,13 @@ def tps_solve_bwd(coord, grad_T):
     cbuf, cstride, pn = _mesh_args(coord, B, N - 3)
     g = torch.empty((B, pn, 2), dtype=torch.float32, device=grad_T.device)
     nbytes = lib.dvsg_tps_solve_workspace_bytes(B, pn, cstride)
-    ws = _workspace(grad_T.device, nbytes)
+    pws = _prepared_workspace(lib, cbuf, cstride, B, pn, nbytes) if B > 0 else None
     with torch.cuda.device(grad_T.device):
-        rc = lib.dvsg_tps_solve_bwd(ptr(cbuf), cstride, ptr(grad_T), ptr(g), B, pn, ptr(ws), nbytes, stream_ptr(grad_T.device))
+        if pws is not None:
+            rc = lib.dvsg_tps_solve_bwd_prepared(ptr(cbuf), cstride, ptr(grad_T), ptr(g), B, pn, ptr(pws), nbytes, stream_ptr(grad_T.device))
+        else:
+            ws = _workspace(grad_T.device, nbytes)
+            rc = lib.dvsg_tps_solve_bwd(ptr(cbuf), cstride, ptr(grad_T), ptr(g), B, pn, ptr(ws), nbytes, stream_ptr(grad_T.device))
     _lib.check(rc, 'dvsg_tps_solve_bwd')
     return g
 

@@ -66,6 +66,18 @@ int dvsg_tps_solve_bwd(const float* coord, long long coord_batch_stride, const f
                        float* grad_target, int B, int pn, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Constant meshes (every reference call site, model.py:62-68): invert the system(s) into the
+ * workspace once with dvsg_tps_prepare, then apply only.  The workspace must stay untouched
+ * between the calls; for pn+3 <= 32 prepare is a no-op and these are the plain solves.       */
+int dvsg_tps_prepare(const float* coord, long long coord_batch_stride, int B, int pn,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int dvsg_tps_solve_prepared(const float* coord, long long coord_batch_stride, const float* target,
+                            float* T, int B, int pn, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int dvsg_tps_solve_bwd_prepared(const float* coord, long long coord_batch_stride,
+                                const float* grad_T, float* grad_target, int B, int pn,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K2+K3: fused TPS grid generation + bilinear gather ------------------------------
  * Replaces _meshgrid (ThinPlateSpline.py:92-111), tf.matmul(T, grid) (:129) and
  * _interpolate (:30-90) -- the [B, pn+3, h*w] basis is never materialised.

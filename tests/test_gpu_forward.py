@@ -103,6 +103,37 @@ def test_tps_solve_coefficients(n, tol32, tol64):
     assert np.abs(Ts - T).max() <= 1e-6
 
 
+def test_prepared_solve_of_a_constant_mesh_matches_the_plain_solve():
+    """Shared meshes above 29 control points: the inverse is computed once per mesh (dvsg_tps_prepare) and reused;
+    the coefficients equal the plain solve bit for bit, and an in-place change of the mesh invalidates the cache."""
+    from coupe.dvsg_b200 import _lib, ops
+    lib = _lib.load()
+    m, b = 7, 5
+    rng = np.random.default_rng(2)
+    mesh = cu(tiled_mesh(m, m, 1)[0])
+    target = mesh.unsqueeze(0) + cu(rng.uniform(-0.05, 0.05, (b, m * m, 2)).astype(np.float32))
+
+    def plain(mesh_t):
+        T = torch.empty((b, 2, m * m + 3), dtype=torch.float32, device=DEV)
+        nbytes = lib.dvsg_tps_solve_workspace_bytes(b, m * m, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+        rc = lib.dvsg_tps_solve(mesh_t.data_ptr(), 0, target.data_ptr(), T.data_ptr(), b, m * m, ws.data_ptr(), nbytes,
+                                torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        return T
+
+    first = ops.tps_solve(mesh.unsqueeze(0).expand(b, -1, -1), target)
+    n0 = _lib.launch_count()
+    second = ops.tps_solve(mesh.unsqueeze(0).expand(b, -1, -1), target)
+    assert _lib.launch_count() - n0 == 1                      # apply only: the inverse was reused
+    assert torch.equal(first, plain(mesh)) and torch.equal(second, first)
+    g = torch.rand_like(first)
+    assert ops.tps_solve_bwd(mesh.unsqueeze(0).expand(b, -1, -1), g).shape == (b, m * m, 2)
+    mesh.mul_(0.9)                                            # in-place update -> new tensor version -> fresh inverse
+    third = ops.tps_solve(mesh.unsqueeze(0).expand(b, -1, -1), target)
+    assert torch.equal(third, plain(mesh)) and not torch.equal(third, first)
+
+
 def test_tps_identity_and_affine_known_answers():
     from coupe.dvsg_b200 import ops
     coord = tiled_mesh(4, 4, 1)
