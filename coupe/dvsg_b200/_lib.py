@@ -23,6 +23,7 @@ PROTOTYPES = {
     'dvsg_tps_solve_workspace_bytes': (c_size_t, [c_int, c_int, c_longlong]),
     'dvsg_tps_solve': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     'dvsg_tps_solve_bwd': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
+    'dvsg_tps_prepare_workspace_bytes': (c_size_t, [c_int, c_int, c_longlong]),
     'dvsg_tps_prepare': (c_int, [_P, c_longlong, c_int, c_int, _P, c_size_t, _P]),
     'dvsg_tps_solve_prepared': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     'dvsg_tps_solve_bwd_prepared': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),

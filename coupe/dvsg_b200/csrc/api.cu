@@ -47,6 +47,8 @@ struct dvsg_host_pipeline {
     int device, H, W, C, pn, fpc, n_slots;
     size_t frame_elems;
     float* d_coord;                 // [pn, 2] shared mesh
+    void* d_winv;                   // inverse of the mesh's TPS system (dvsg_tps_prepare), refreshed by every call
+    size_t winv_bytes;
     std::vector<cudaStream_t> streams;
     std::vector<float*> d_in, d_out, d_vec, d_T;
     std::vector<unsigned char*> d_in8, d_out8;     // uint8 staging of the frames (allocated by the first u8 call)
@@ -65,14 +67,16 @@ extern "C" int dvsg_host_pipeline_create(dvsg_host_pipeline** out, int device, i
                                          int frames_per_chunk, int n_slots) {
     DVSG_REQUIRE(out && H > 0 && W > 0 && C > 0 && pn >= 3 && frames_per_chunk > 0 && n_slots > 0 && n_slots <= 16,
                  "host_pipeline_create: bad argument");
-    DVSG_REQUIRE(pn + 3 <= 32, "host_pipeline_create: meshes above 29 control points are not supported by the host pipeline");
     DVSG_CUDA(cudaSetDevice(device));
     dvsg_host_pipeline* p = new dvsg_host_pipeline();
     p->device = device; p->H = H; p->W = W; p->C = C; p->pn = pn; p->fpc = frames_per_chunk; p->n_slots = n_slots;
     p->frame_elems = (size_t)H * W * C;
     p->d_coord = nullptr;
+    p->d_winv = nullptr;
+    p->winv_bytes = dvsg_tps_prepare_workspace_bytes(1, pn, 0);
     *out = p;
     DVSG_CUDA(cudaMalloc(&p->d_coord, (size_t)pn * 2 * sizeof(float)));
+    DVSG_CUDA(cudaMalloc(&p->d_winv, p->winv_bytes));
     for (int s = 0; s < n_slots; ++s) {
         cudaStream_t st;
         float *a = nullptr, *b = nullptr, *v = nullptr, *t = nullptr;
@@ -101,6 +105,7 @@ extern "C" void dvsg_host_pipeline_destroy(dvsg_host_pipeline* p) {
     for (auto q : p->d_in8) cudaFree(q);
     for (auto q : p->d_out8) cudaFree(q);
     cudaFree(p->d_coord);
+    cudaFree(p->d_winv);
     delete p;
 }
 
@@ -118,6 +123,10 @@ extern "C" int dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, co
     const size_t fe = p->frame_elems;
     const int pn = p->pn;
     DVSG_CUDA(cudaMemcpyAsync(p->d_coord, coord_host, (size_t)pn * 2 * sizeof(float), cudaMemcpyHostToDevice, p->streams[0]));
+    {   // one inversion of the mesh's system per call; every chunk then only applies it
+        const int rc0 = dvsg_tps_prepare(p->d_coord, 0, 1, pn, p->d_winv, p->winv_bytes, p->streams[0]);
+        if (rc0) return rc0;
+    }
     DVSG_CUDA(cudaStreamSynchronize(p->streams[0]));
     int chunk = 0;
     for (int f0 = 0; f0 < B; f0 += p->fpc, ++chunk) {
@@ -132,7 +141,7 @@ extern "C" int dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, co
         count_launch();
         int rc = check_launch("add_mesh_kernel");
         if (rc) return rc;
-        rc = dvsg_tps_solve(p->d_coord, 0, p->d_vec[s], p->d_T[s], nf, pn, nullptr, 0, st);
+        rc = dvsg_tps_solve_prepared(p->d_coord, 0, p->d_vec[s], p->d_T[s], nf, pn, p->d_winv, p->winv_bytes, st);
         if (rc) return rc;
         rc = dvsg_tps_warp_fwd(p->d_in[s], p->d_coord, 0, p->d_T[s], p->d_out[s], nullptr, nullptr, nullptr, nf, p->H, p->W,
                                p->C, p->H, p->W, pn, 0, st);
@@ -163,6 +172,10 @@ extern "C" int dvsg_host_tps_warp_u8(dvsg_host_pipeline* p, const unsigned char*
         p->d_out8.push_back(b);
     }
     DVSG_CUDA(cudaMemcpyAsync(p->d_coord, coord_host, (size_t)pn * 2 * sizeof(float), cudaMemcpyHostToDevice, p->streams[0]));
+    {   // one inversion of the mesh's system per call; every chunk then only applies it
+        const int rc0 = dvsg_tps_prepare(p->d_coord, 0, 1, pn, p->d_winv, p->winv_bytes, p->streams[0]);
+        if (rc0) return rc0;
+    }
     DVSG_CUDA(cudaStreamSynchronize(p->streams[0]));
     int chunk = 0;
     for (int f0 = 0; f0 < B; f0 += p->fpc, ++chunk) {
@@ -179,7 +192,7 @@ extern "C" int dvsg_host_tps_warp_u8(dvsg_host_pipeline* p, const unsigned char*
         count_launch();
         rc = check_launch("add_mesh_kernel");
         if (rc) return rc;
-        rc = dvsg_tps_solve(p->d_coord, 0, p->d_vec[s], p->d_T[s], nf, pn, nullptr, 0, st);
+        rc = dvsg_tps_solve_prepared(p->d_coord, 0, p->d_vec[s], p->d_T[s], nf, pn, p->d_winv, p->winv_bytes, st);
         if (rc) return rc;
         rc = dvsg_tps_warp_fwd(p->d_in[s], p->d_coord, 0, p->d_T[s], p->d_out[s], nullptr, nullptr, nullptr, nf, p->H, p->W,
                                p->C, p->H, p->W, pn, 0, st);

@@ -343,13 +343,12 @@ static int solve_impl(const float* coord, long long stride, const float* rhs, fl
     DVSG_REQUIRE(coord && (prepared == 2 || (rhs && out)), "%s: null pointer", what);
     DVSG_REQUIRE(stride == 0 || stride >= 2LL * pn, "%s: coord stride %lld < 2*pn", what, stride);
     const int N = pn + 3;
-    if (N <= SMALL_N && prepared == 2) return DVSG_OK;      // small systems are factorised inside the solve kernels
-    if (N <= SMALL_N && stride == 0) {
+    if (N <= SMALL_N && prepared == 0 && stride == 0) {
         tps_solve_shared_kernel<TRANSPOSED><<<(B + SH_FRAMES - 1) / SH_FRAMES, SH_THREADS, 0, st>>>(coord, rhs, out, B, pn);
         count_launch();
         return check_launch("tps_solve_shared_kernel");
     }
-    if (N <= SMALL_N) {
+    if (N <= SMALL_N && prepared == 0) {
         tps_solve_warp_kernel<TRANSPOSED><<<(B + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, st>>>(coord, stride, rhs, out, B, pn);
         count_launch();
         return check_launch("tps_solve_warp_kernel");
@@ -391,7 +390,13 @@ extern "C" int dvsg_tps_solve(const float* coord, long long coord_batch_stride, 
 
 // The mesh of a clip is a constant (model.py:62-68): dvsg_tps_prepare inverts its system(s) into the
 // workspace once, dvsg_tps_solve_prepared / _bwd_prepared then only apply W^-1 (a [B,N] x [N,N] product) per call.
-// For pn + 3 <= 32 the prepare step is a no-op and the prepared calls are the plain solves.
+// Works for every mesh size: with a 4x4 mesh the per-call work drops from a 23 us factorisation kernel to a ~3 us
+// [B,16] x [16,19] product (size the workspace with dvsg_tps_prepare_workspace_bytes).
+extern "C" size_t dvsg_tps_prepare_workspace_bytes(int B, int pn, long long coord_batch_stride) {
+    if (B <= 0 || pn < 3) return 0;
+    return big_workspace_bytes(B, pn, coord_batch_stride);
+}
+
 extern "C" int dvsg_tps_prepare(const float* coord, long long coord_batch_stride, int B, int pn, void* workspace, size_t workspace_bytes,
                                 void* stream) {
     return solve_impl<false>(coord, coord_batch_stride, nullptr, nullptr, B, pn, workspace, workspace_bytes, (cudaStream_t)stream, "tps_prepare", 2);

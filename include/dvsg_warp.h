@@ -67,8 +67,10 @@ int dvsg_tps_solve_bwd(const float* coord, long long coord_batch_stride, const f
                        size_t workspace_bytes, void* stream);
 
 /* Constant meshes (every reference call site, model.py:62-68): invert the system(s) into the
- * workspace once with dvsg_tps_prepare, then apply only.  The workspace must stay untouched
- * between the calls; for pn+3 <= 32 prepare is a no-op and these are the plain solves.       */
+ * workspace once with dvsg_tps_prepare (fp64 Gauss-Jordan, any mesh size), then only apply
+ * W^-1 per call (fp64 accumulation, rounded once).  The workspace
+ * (dvsg_tps_prepare_workspace_bytes) must stay untouched between the calls.                  */
+size_t dvsg_tps_prepare_workspace_bytes(int B, int pn, long long coord_batch_stride);
 int dvsg_tps_prepare(const float* coord, long long coord_batch_stride, int B, int pn,
                      void* workspace, size_t workspace_bytes, void* stream);
 int dvsg_tps_solve_prepared(const float* coord, long long coord_batch_stride, const float* target,

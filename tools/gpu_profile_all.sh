@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round evidence: plain runs first, then launch lists and one ncu --set full capture per dominant kernel.
 mkdir -p gpurun_out
-for WL in cfg2 cfg4 cfg3; do
+for WL in cfg2 hd1080 cfg4 cfg3; do
   CMD="python bench.py --workload $WL --steps 3 --warmup 3 --no-cpu --no-e2e"
   $CMD > gpurun_out/plain_$WL.log 2>&1 || { echo "plain $WL failed"; tail -3 gpurun_out/plain_$WL.log; continue; }
   ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$WL.csv $CMD > /dev/null 2>&1
