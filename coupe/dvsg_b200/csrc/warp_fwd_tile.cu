@@ -344,6 +344,22 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             mbar_arrive_expect_tx(mbar, (unsigned)(T.pitch * box_rows));
             tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
         }
+        if ((MODE == TMODE_TPS || MODE == TMODE_HOMOG) && !T.staged && all_sane && !(p.dbg & 4)) {
+            // per-pixel tile of a smooth map (rare; rough given-grid / flow fields would only double their L2 requests): its gathers are issued a whole coordinate phase from now -- pull the two source rows of
+            // every pixel into L2 meanwhile (the x1 corner shares the line of x0 in all but 1 of 10 cases)
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float xq = h ? XP[j].y : XP[j].x, yq = h ? YP[j].y : YP[j].x;
+                    const int off = MODE == TMODE_TPS ? 0 : 1;
+                    const int xi = min(max(floor_small(xq) - off, 0), W - 1), yi = min(max(floor_small(yq) - off, 0), H - 1);
+                    const float* a0 = srcb + ((size_t)yi * W + xi) * 3;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a0));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + (yi + 1 < H ? 3 * W : 0)));
+                }
+            }
+        }
     };
 
     // ---- the software pipeline: the coordinates of tile t+1 are computed BEFORE tile t is gathered, so the TMA copy of

@@ -58,10 +58,15 @@ def main():
     B, H, W = 64, 720, 1280
     px = B * H * W
     if only in ('all', 'tps'):
-        for amp in (0.2, 0.04, 0.0):
+        for amp in (0.2, 0.04, 0.0, 0.4, 0.6):
             U, coord, T = tps_case(B, H, W, 4, amp)
             ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
             rec('tps720 4x4 amp=%.2f tile' % amp, ms, px, 24)
+            if amp >= 0.4:
+                lib.dvsg_set_tile_tuning(4, -1, -1)
+                ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
+                rec('tps720 4x4 amp=%.2f tile, no L2 prefetch of per-pixel tiles' % amp, ms, px, 24)
+                lib.dvsg_set_tile_tuning(0, -1, -1)
             if amp == 0.2:
                 for tc in (148 * 5 * 4, 148 * 5 * 24):
                     lib.dvsg_set_tile_tuning(-1, tc, -1)
