@@ -9,7 +9,8 @@ import os
 from ctypes import c_char_p, c_int, c_longlong, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libdvsg_warp.so')
+# DVSG_LIB: A/B experiments with an alternative build of the same sources (tools/); never a different implementation
+LIB_PATH = os.environ.get('DVSG_LIB') or os.path.join(HERE, 'libdvsg_warp.so')
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 FLAG_FORCE_DIRECT = 1
