@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
     const int seg = blockIdx.x, b = blockIdx.z;
     const int row0 = blockIdx.y * TR;
     const int t_begin = seg * p.seg_len, t_end = min(t_begin + p.seg_len, p.n_tx);
+    const int rows_ok = min(TR, oh - row0);
     const int pn4 = (p.pn + 3) & ~3, pn8 = (p.pn + 7) & ~7;
     const bool want_gT = MODE == TMODE_TPS && p.grad_T != nullptr;
 
@@ -292,13 +293,17 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
 
         // grad_out of the thread's 8 pixels: issued first, the global-memory latency hides behind the basis
         float gq[TR][3];
+        const size_t opix0 = ((size_t)b * oh + row0) * ow + col;      // flat index of the lane's pixel in row 0 of the tile
+        {
+            const float* gp = p.grad_out + opix0 * 3;
+            const int rstride = ow * 3;
 #pragma unroll
-        for (int q = 0; q < TR; ++q) {
-            const int row = row0 + q;
-            const bool ok = col_ok && row < oh;
-            const float* gp = p.grad_out + (((size_t)b * oh + min(row, oh - 1)) * ow + col) * 3;
+            for (int q = 0; q < TR; ++q) {
+                const bool ok = col_ok && q < rows_ok;
+                const float* gr = gp + min(q, rows_ok - 1) * rstride;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) gq[q][ch] = ok ? __ldg(gp + ch) : 0.0f;
+                for (int ch = 0; ch < 3; ++ch) gq[q][ch] = ok ? __ldg(gr + ch) : 0.0f;
+            }
         }
 
         // ================= A: coordinates (identical arithmetic to the forward kernel) =================
@@ -448,9 +453,9 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         for (int j = 0; j < TR / 2; ++j) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int q = 2 * j + h, row = row0 + q;
-                const bool ok = col_ok && row < oh;
-                const size_t opix = ((size_t)b * oh + min(row, oh - 1)) * ow + col;
+                const int q = 2 * j + h;
+                const bool ok = col_ok && q < rows_ok;
+                const size_t opix = opix0 + (size_t)(min(q, rows_ok - 1) * ow);
                 float gx = h ? GX[j].y : GX[j].x, gy = h ? GY[j].y : GY[j].x;
                 if (MODE == TMODE_TPS) {
                     gx = gx * (float)W * 0.5f;                     // x_pix = (x+1)*W/2
