@@ -238,6 +238,60 @@ __global__ void __launch_bounds__(NT, 3) warp_fwd_kernel(const FwdParams p) {
     }
 }
 
+// ---- wide pixels (C even, C != 3): one thread per PAIR OF CHANNELS of one output pixel ----------------------------
+// bilinear_interp's only live call sites carry C = 18 (model.py:156-167): a pixel is 72 contiguous bytes, so letting the
+// lanes run over (pixel, channel pair) makes every corner gather and the output store coalesced 8-byte accesses
+// (the per-column mapping of warp_fwd_kernel reads 4-byte words 72 bytes apart: 25 % of the HBM roofline at C = 18;
+// this mapping: 34.5 % for given grids, 27 % for the projective grid, whose two IEEE divisions every thread of a pixel
+// repeats -- instruction-bound, a per-pixel coordinate pass through shared memory is the next step).  Same operations
+// in the same order as the other kernels: identical bits.
+// grid = (ceil(ow * C/2 / 256), oh, B).
+template <int MODE>
+__global__ void __launch_bounds__(256) warp_fwd_wide_kernel(const FwdParams p) {
+    const int H = p.H, W = p.W, C = p.C, oh = p.oh, ow = p.ow, cv = C >> 1;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= ow * cv) return;
+    const int col = i / cv, c2 = i - col * cv, row = blockIdx.y, b = blockIdx.z;
+    const size_t pix = ((size_t)b * oh + row) * ow + col;
+    float xs, ys;      // pixel-space coordinate before the clip
+    if (MODE == MODE_GIVEN) {
+        xs = zp_pix_from_norm(__ldg(p.x_in + pix), W);
+        ys = zp_pix_from_norm(__ldg(p.y_in + pix), H);
+    } else if (MODE == MODE_FLOW) {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + pix);
+        xs = DVSG_ADD((float)col, f.x);   // warp_with_optical_flow.py:107-120
+        ys = DVSG_ADD((float)row, f.y);
+    } else {
+        const int nt = p.projective ? 8 : 6;
+        const float* th = p.theta + (size_t)b * nt;
+        const float xt = lin_coord(col, p.step_x), yt = lin_coord(row, p.step_y);
+        // rows of theta @ [x_t; y_t; 1], accumulated k = 0,1,2 (spatial_transformer.py:437)
+        float xn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 0), xt), DVSG_MUL(__ldg(th + 1), yt)), __ldg(th + 2));
+        float yn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 3), xt), DVSG_MUL(__ldg(th + 4), yt)), __ldg(th + 5));
+        if (p.projective) {
+            const float zn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 6), xt), DVSG_MUL(__ldg(th + 7), yt)), 1.0f);
+            xn = zn != 0.0f ? DVSG_DIV(xn, zn) : 0.0f;   // tf.div_no_nan, :446-447
+            yn = zn != 0.0f ? DVSG_DIV(yn, zn) : 0.0f;
+        }
+        if (p.x_out && c2 == 0) { p.x_out[pix] = xn; p.y_out[pix] = yn; }
+        xs = zp_pix_from_norm(xn, W);
+        ys = zp_pix_from_norm(yn, H);
+    }
+    const Corners c = zp_corners(xs, ys, W, H);
+    const bool vx0 = zp_valid(c.x0, W), vx1 = zp_valid(c.x1, W), vy0 = zp_valid(c.y0, H), vy1 = zp_valid(c.y1, H);
+    // keep addresses legal for the (unused) loads of invalid corners
+    const int x0 = min(max(c.x0, 1) - 1, W - 1), x1 = max(min(c.x1, W) - 1, 0);
+    const int y0 = min(max(c.y0, 1) - 1, H - 1), y1 = max(min(c.y1, H) - 1, 0);
+    const float2* srcb = reinterpret_cast<const float2*>(p.src + (size_t)b * H * W * C) + c2;
+    const float2 z = make_float2(0.0f, 0.0f);
+    const float2 i00 = (vx0 && vy0) ? __ldg(srcb + ((size_t)y0 * W + x0) * cv) : z;
+    const float2 i01 = (vx1 && vy0) ? __ldg(srcb + ((size_t)y0 * W + x1) * cv) : z;
+    const float2 i10 = (vx0 && vy1) ? __ldg(srcb + ((size_t)y1 * W + x0) * cv) : z;
+    const float2 i11 = (vx1 && vy1) ? __ldg(srcb + ((size_t)y1 * W + x1) * cv) : z;
+    reinterpret_cast<float2*>(p.out)[pix * cv + c2] =
+        make_float2(zp_blend(c, i00.x, i01.x, i10.x, i11.x), zp_blend(c, i00.y, i01.y, i10.y, i11.y));
+}
+
 // ---- spatial_transformer._meshgrid (spatial_transformer.py:460-482) --------------------------
 __global__ void st_meshgrid_kernel(float* __restrict__ grid, int oh, int ow, float step_x, float step_y) {
     const int n = oh * ow;
@@ -278,6 +332,21 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
     return check_launch("warp_fwd_kernel");
 }
 
+static bool wide_path_ok(int flags, const void* src, const void* out, int C, int oh, int ow) {
+    return !(flags & DVSG_FLAG_FORCE_DIRECT) && C >= 4 && C % 2 == 0 && (reinterpret_cast<uintptr_t>(src) & 7u) == 0 &&
+           (reinterpret_cast<uintptr_t>(out) & 7u) == 0 && oh <= 65535 && (long long)ow * (C / 2) < (1LL << 30);
+}
+
+template <int MODE>
+static int launch_fwd_wide(FwdParams p, cudaStream_t st) {
+    if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
+    DVSG_REQUIRE(p.B <= 65535, "batch %d exceeds the grid z limit 65535: split the call", p.B);
+    const dim3 grid((unsigned)((p.ow * (p.C / 2) + 255) / 256), (unsigned)p.oh, (unsigned)p.B);
+    warp_fwd_wide_kernel<MODE><<<grid, 256, 0, st>>>(p);
+    count_launch();
+    return check_launch("warp_fwd_wide_kernel");
+}
+
 }  // namespace dvsg
 
 using namespace dvsg;
@@ -315,6 +384,7 @@ extern "C" int dvsg_bilinear_fwd(const float* im, const float* x, const float* y
     FwdParams p = {};
     p.src = im; p.out = out; p.x_in = x; p.y_in = y;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow;
+    if (wide_path_ok(flags, im, out, C, oh, ow)) return launch_fwd_wide<MODE_GIVEN>(p, (cudaStream_t)stream);
     return launch_fwd<MODE_GIVEN>(p, (cudaStream_t)stream);
 }
 
@@ -329,6 +399,7 @@ extern "C" int dvsg_flow_warp_fwd(const float* im, const float* flow, float* out
     FwdParams p = {};
     p.src = im; p.out = out; p.flow = flow;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = H; p.ow = W;
+    if (wide_path_ok(flags, im, out, C, H, W)) return launch_fwd_wide<MODE_FLOW>(p, (cudaStream_t)stream);
     return launch_fwd<MODE_FLOW>(p, (cudaStream_t)stream);
 }
 
@@ -344,6 +415,7 @@ extern "C" int dvsg_homography_warp_fwd(const float* im, const float* theta, int
     p.src = im; p.out = out; p.x_out = x_out; p.y_out = y_out; p.theta = theta; p.projective = projective;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow;
     p.step_x = lin_step(ow); p.step_y = lin_step(oh);
+    if (wide_path_ok(0, im, out, C, oh, ow)) return launch_fwd_wide<MODE_HOMOG>(p, (cudaStream_t)stream);
     return launch_fwd<MODE_HOMOG>(p, (cudaStream_t)stream);
 }
 

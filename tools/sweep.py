@@ -116,5 +116,35 @@ def main():
         rec('torch copy 398MB', ms, pxf, 24)
 
 
+
+
+
+def c18():
+    """the only live call sites of bilinear_interp: C = 18 (model.py:156-167), generic direct kernel"""
+    B, H, W, C = 32, 288, 512, 18
+    im = torch.rand((B, H, W, C), device=dev)
+    px = B * H * W
+    theta = torch.tensor([1.02, 0.01, 0.0, -0.01, 0.98, 0.01, 1e-3, -1e-3], device=dev).repeat(B, 1)
+    ms = timeit(lambda: ops.homography_warp(im, theta, (H, W), True))
+    rec('projective C=18 288x512 B=32 (wide-pixel kernel)', ms, px, 8 * C)
+    lat = (torch.rand((B, 2, 9, 16), device=dev) - 0.5) * 0.05
+    g = torch.nn.functional.interpolate(lat, size=(H, W), mode='bilinear', align_corners=True)
+    lin_x = torch.linspace(-1, 1, W, device=dev).view(1, 1, W).expand(B, H, W)
+    lin_y = torch.linspace(-1, 1, H, device=dev).view(1, H, 1).expand(B, H, W)
+    x = (lin_x + g[:, 0]).reshape(-1).contiguous()
+    y = (lin_y + g[:, 1]).reshape(-1).contiguous()
+    ms = timeit(lambda: ops.bilinear_interp(im, x, y, (H, W)))
+    rec('bilinear_interp C=18 288x512 B=32 smooth grid (wide-pixel kernel)', ms, px, 8 * C + 8)
+    B2 = 8
+    im2 = torch.rand((B2, 1080, 1920, C), device=dev)
+    theta2 = theta[:B2].contiguous()
+    ms = timeit(lambda: ops.homography_warp(im2, theta2, (1080, 1920), True), n=10)
+    rec('projective C=18 1080p B=8 (wide-pixel kernel, 2.4 GB per call)', ms, B2 * 1080 * 1920, 8 * C)
+
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'c18':
+        c18()
+    else:
+        main()
