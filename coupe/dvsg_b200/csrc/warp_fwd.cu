@@ -238,58 +238,89 @@ __global__ void __launch_bounds__(NT, 3) warp_fwd_kernel(const FwdParams p) {
     }
 }
 
-// ---- wide pixels (C even, C != 3): one thread per PAIR OF CHANNELS of one output pixel ----------------------------
-// bilinear_interp's only live call sites carry C = 18 (model.py:156-167): a pixel is 72 contiguous bytes, so letting the
-// lanes run over (pixel, channel pair) makes every corner gather and the output store coalesced 8-byte accesses
-// (the per-column mapping of warp_fwd_kernel reads 4-byte words 72 bytes apart: 25 % of the HBM roofline at C = 18;
-// this mapping: 34.5 % for given grids, 27 % for the projective grid, whose two IEEE divisions every thread of a pixel
-// repeats -- instruction-bound, a per-pixel coordinate pass through shared memory is the next step).  Same operations
-// in the same order as the other kernels: identical bits.
-// grid = (ceil(ow * C/2 / 256), oh, B).
+// ---- wide pixels (C even, C != 3): lanes over (pixel, channel pair) --------------------------------------------------
+// bilinear_interp's only live call sites carry C = 18 (model.py:156-167): a pixel is 72 contiguous bytes.  The
+// per-column mapping of warp_fwd_kernel reads 4-byte words 72 bytes apart (25 % of the HBM roofline at C = 18), and a
+// thread per (pixel, channel pair) that recomputes the pixel's coordinates is instruction-bound (243 instructions per
+// 8 output bytes with the projective grid's two IEEE divisions: 29 %).  So the CTA works in two phases on a tile of
+// WIDE_PX x WIDE_ROWS output pixels: (1) one thread per pixel computes the sampling coordinate, the four corner offsets
+// (-1 = outside the frame, i.e. the zero padding) and the four weights once -- same operations in the same order as
+// the other kernels -- into a 32-byte shared-memory record; (2) all threads run over (pixel, channel pair): two
+// LDS.128, four coalesced LDG.64, the blend in the reference's add_n order, one coalesced STG.64.  Identical bits.
+constexpr int WIDE_PX = 64, WIDE_ROWS = 4, WIDE_NT = 256;
+struct __align__(16) WideRec { int o00, o01, o10, o11; float w00, w01, w10, w11; };
+
 template <int MODE>
-__global__ void __launch_bounds__(256) warp_fwd_wide_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(WIDE_NT) warp_fwd_wide_kernel(const FwdParams p) {
+    __shared__ WideRec s_rec[WIDE_ROWS * WIDE_PX];
     const int H = p.H, W = p.W, C = p.C, oh = p.oh, ow = p.ow, cv = C >> 1;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= ow * cv) return;
-    const int col = i / cv, c2 = i - col * cv, row = blockIdx.y, b = blockIdx.z;
-    const size_t pix = ((size_t)b * oh + row) * ow + col;
-    float xs, ys;      // pixel-space coordinate before the clip
-    if (MODE == MODE_GIVEN) {
-        xs = zp_pix_from_norm(__ldg(p.x_in + pix), W);
-        ys = zp_pix_from_norm(__ldg(p.y_in + pix), H);
-    } else if (MODE == MODE_FLOW) {
-        const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + pix);
-        xs = DVSG_ADD((float)col, f.x);   // warp_with_optical_flow.py:107-120
-        ys = DVSG_ADD((float)row, f.y);
-    } else {
-        const int nt = p.projective ? 8 : 6;
-        const float* th = p.theta + (size_t)b * nt;
-        const float xt = lin_coord(col, p.step_x), yt = lin_coord(row, p.step_y);
-        // rows of theta @ [x_t; y_t; 1], accumulated k = 0,1,2 (spatial_transformer.py:437)
-        float xn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 0), xt), DVSG_MUL(__ldg(th + 1), yt)), __ldg(th + 2));
-        float yn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 3), xt), DVSG_MUL(__ldg(th + 4), yt)), __ldg(th + 5));
-        if (p.projective) {
-            const float zn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 6), xt), DVSG_MUL(__ldg(th + 7), yt)), 1.0f);
-            xn = zn != 0.0f ? DVSG_DIV(xn, zn) : 0.0f;   // tf.div_no_nan, :446-447
-            yn = zn != 0.0f ? DVSG_DIV(yn, zn) : 0.0f;
+    const int tid = threadIdx.x, col0 = blockIdx.x * WIDE_PX, row0 = blockIdx.y * WIDE_ROWS, b = blockIdx.z;
+    // ---- phase 1: one record per pixel ---------------------------------------------------------------
+    {
+        const int r = tid / WIDE_PX, col = col0 + tid % WIDE_PX, row = row0 + r;     // WIDE_NT == WIDE_ROWS * WIDE_PX
+        WideRec rec = {-1, -1, -1, -1, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (col < ow && row < oh) {
+            const size_t pix = ((size_t)b * oh + row) * ow + col;
+            float xq, yq;      // pixel-space coordinate before the clip
+            if (MODE == MODE_GIVEN) {
+                xq = zp_pix_from_norm(__ldg(p.x_in + pix), W);
+                yq = zp_pix_from_norm(__ldg(p.y_in + pix), H);
+            } else if (MODE == MODE_FLOW) {
+                const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + pix);
+                xq = DVSG_ADD((float)col, f.x);   // warp_with_optical_flow.py:107-120
+                yq = DVSG_ADD((float)row, f.y);
+            } else {
+                const int nt = p.projective ? 8 : 6;
+                const float* th = p.theta + (size_t)b * nt;
+                const float xt = lin_coord(col, p.step_x), yt = lin_coord(row, p.step_y);
+                // rows of theta @ [x_t; y_t; 1], accumulated k = 0,1,2 (spatial_transformer.py:437)
+                float xn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 0), xt), DVSG_MUL(__ldg(th + 1), yt)), __ldg(th + 2));
+                float yn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 3), xt), DVSG_MUL(__ldg(th + 4), yt)), __ldg(th + 5));
+                if (p.projective) {
+                    const float zn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 6), xt), DVSG_MUL(__ldg(th + 7), yt)), 1.0f);
+                    xn = zn != 0.0f ? DVSG_DIV(xn, zn) : 0.0f;   // tf.div_no_nan, :446-447
+                    yn = zn != 0.0f ? DVSG_DIV(yn, zn) : 0.0f;
+                }
+                if (p.x_out) { p.x_out[pix] = xn; p.y_out[pix] = yn; }
+                xq = zp_pix_from_norm(xn, W);
+                yq = zp_pix_from_norm(yn, H);
+            }
+            const Corners c = zp_corners(xq, yq, W, H);
+            const bool vx0 = zp_valid(c.x0, W), vx1 = zp_valid(c.x1, W), vy0 = zp_valid(c.y0, H), vy1 = zp_valid(c.y1, H);
+            // element offsets (in pixels) of the corners inside the frame; padded index - 1 = frame index
+            rec.o00 = (vx0 && vy0) ? (c.y0 - 1) * W + (c.x0 - 1) : -1;
+            rec.o01 = (vx1 && vy0) ? (c.y0 - 1) * W + (c.x1 - 1) : -1;
+            rec.o10 = (vx0 && vy1) ? (c.y1 - 1) * W + (c.x0 - 1) : -1;
+            rec.o11 = (vx1 && vy1) ? (c.y1 - 1) * W + (c.x1 - 1) : -1;
+            rec.w00 = DVSG_MUL(c.ax1, c.ay1); rec.w01 = DVSG_MUL(c.ax0, c.ay1);       // as zp_blend forms them
+            rec.w10 = DVSG_MUL(c.ax1, c.ay0); rec.w11 = DVSG_MUL(c.ax0, c.ay0);
         }
-        if (p.x_out && c2 == 0) { p.x_out[pix] = xn; p.y_out[pix] = yn; }
-        xs = zp_pix_from_norm(xn, W);
-        ys = zp_pix_from_norm(yn, H);
+        s_rec[tid] = rec;
     }
-    const Corners c = zp_corners(xs, ys, W, H);
-    const bool vx0 = zp_valid(c.x0, W), vx1 = zp_valid(c.x1, W), vy0 = zp_valid(c.y0, H), vy1 = zp_valid(c.y1, H);
-    // keep addresses legal for the (unused) loads of invalid corners
-    const int x0 = min(max(c.x0, 1) - 1, W - 1), x1 = max(min(c.x1, W) - 1, 0);
-    const int y0 = min(max(c.y0, 1) - 1, H - 1), y1 = max(min(c.y1, H) - 1, 0);
-    const float2* srcb = reinterpret_cast<const float2*>(p.src + (size_t)b * H * W * C) + c2;
+    __syncthreads();
+    // ---- phase 2: (pixel, channel pair) -----------------------------------------------------------------
+    const float2* srcb = reinterpret_cast<const float2*>(p.src + (size_t)b * H * W * C);
+    const int npx = min(WIDE_PX, ow - col0), per_row = npx * cv;
     const float2 z = make_float2(0.0f, 0.0f);
-    const float2 i00 = (vx0 && vy0) ? __ldg(srcb + ((size_t)y0 * W + x0) * cv) : z;
-    const float2 i01 = (vx1 && vy0) ? __ldg(srcb + ((size_t)y0 * W + x1) * cv) : z;
-    const float2 i10 = (vx0 && vy1) ? __ldg(srcb + ((size_t)y1 * W + x0) * cv) : z;
-    const float2 i11 = (vx1 && vy1) ? __ldg(srcb + ((size_t)y1 * W + x1) * cv) : z;
-    reinterpret_cast<float2*>(p.out)[pix * cv + c2] =
-        make_float2(zp_blend(c, i00.x, i01.x, i10.x, i11.x), zp_blend(c, i00.y, i01.y, i10.y, i11.y));
+    const int px_first = tid / cv, c2_first = tid - px_first * cv, dpx = WIDE_NT / cv, dc2 = WIDE_NT - dpx * cv;   // e -> (px, c2) without a division per element
+    for (int r = 0; r < WIDE_ROWS && row0 + r < oh; ++r) {
+        float2* orow = reinterpret_cast<float2*>(p.out) + (((size_t)b * oh + row0 + r) * ow + col0) * cv;
+        int px = px_first, c2 = c2_first;
+#pragma unroll 3
+        for (int e = tid; e < per_row; e += WIDE_NT, px += dpx, c2 += dc2) {
+            if (c2 >= cv) { c2 -= cv; ++px; }
+            const WideRec rec = s_rec[r * WIDE_PX + px];
+            const float2 i00 = rec.o00 >= 0 ? __ldg(srcb + (size_t)rec.o00 * cv + c2) : z;
+            const float2 i01 = rec.o01 >= 0 ? __ldg(srcb + (size_t)rec.o01 * cv + c2) : z;
+            const float2 i10 = rec.o10 >= 0 ? __ldg(srcb + (size_t)rec.o10 * cv + c2) : z;
+            const float2 i11 = rec.o11 >= 0 ? __ldg(srcb + (size_t)rec.o11 * cv + c2) : z;
+            // add_n([w00*I00, w01*I01, w10*I10, w11*I11]) left to right (spatial_transformer.py:557-562)
+            float2 o;
+            o.x = DVSG_ADD(DVSG_ADD(DVSG_ADD(DVSG_MUL(rec.w00, i00.x), DVSG_MUL(rec.w01, i01.x)), DVSG_MUL(rec.w10, i10.x)), DVSG_MUL(rec.w11, i11.x));
+            o.y = DVSG_ADD(DVSG_ADD(DVSG_ADD(DVSG_MUL(rec.w00, i00.y), DVSG_MUL(rec.w01, i01.y)), DVSG_MUL(rec.w10, i10.y)), DVSG_MUL(rec.w11, i11.y));
+            orow[e] = o;
+        }
+    }
 }
 
 // ---- spatial_transformer._meshgrid (spatial_transformer.py:460-482) --------------------------
@@ -334,15 +365,15 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
 
 static bool wide_path_ok(int flags, const void* src, const void* out, int C, int oh, int ow) {
     return !(flags & DVSG_FLAG_FORCE_DIRECT) && C >= 4 && C % 2 == 0 && (reinterpret_cast<uintptr_t>(src) & 7u) == 0 &&
-           (reinterpret_cast<uintptr_t>(out) & 7u) == 0 && oh <= 65535 && (long long)ow * (C / 2) < (1LL << 30);
+           (reinterpret_cast<uintptr_t>(out) & 7u) == 0 && (oh + WIDE_ROWS - 1) / WIDE_ROWS <= 65535;
 }
 
 template <int MODE>
 static int launch_fwd_wide(FwdParams p, cudaStream_t st) {
     if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
     DVSG_REQUIRE(p.B <= 65535, "batch %d exceeds the grid z limit 65535: split the call", p.B);
-    const dim3 grid((unsigned)((p.ow * (p.C / 2) + 255) / 256), (unsigned)p.oh, (unsigned)p.B);
-    warp_fwd_wide_kernel<MODE><<<grid, 256, 0, st>>>(p);
+    const dim3 grid((unsigned)((p.ow + WIDE_PX - 1) / WIDE_PX), (unsigned)((p.oh + WIDE_ROWS - 1) / WIDE_ROWS), (unsigned)p.B);
+    warp_fwd_wide_kernel<MODE><<<grid, WIDE_NT, 0, st>>>(p);
     count_launch();
     return check_launch("warp_fwd_wide_kernel");
 }
