@@ -165,6 +165,12 @@ def run_reference(args, wl):
         return
     threads = os.cpu_count() or 1
     threads, frames = cpu_sample_plan(wl, min(threads, 64))
+    # bounded run: size the per-step sample so that warmup + steps finish in about DVSG_REF_BUDGET_S seconds whatever
+    # --steps / --warmup the caller chose (one calibration step of one frame per thread measures the host first)
+    budget = float(os.environ.get('DVSG_REF_BUDGET_S', '150'))
+    t_cal, _ = cpu_run(wl, threads, threads, seed=1)
+    per_thread = int(budget / max((args.steps + args.warmup) * t_cal, 1e-9))
+    frames = threads * max(1, min(frames // threads, per_thread))
     for _ in range(args.warmup):
         cpu_run(wl, frames, threads, seed=1)
     total_t, total_px = 0.0, 0
