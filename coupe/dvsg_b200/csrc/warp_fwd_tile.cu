@@ -345,8 +345,9 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
         }
         if ((MODE == TMODE_TPS || MODE == TMODE_HOMOG) && !T.staged && all_sane && !(p.dbg & 4)) {
-            // per-pixel tile of a smooth map (rare; rough given-grid / flow fields would only double their L2 requests): its gathers are issued a whole coordinate phase from now -- pull the two source rows of
-            // every pixel into L2 meanwhile (the x1 corner shares the line of x0 in all but 1 of 10 cases)
+            // per-pixel tile of a smooth map (rare; rough given-grid / flow fields would only double their L2 requests):
+            // its gathers are issued a whole coordinate phase from now -- pull the two source rows of every pixel into
+            // L2 meanwhile (the x1 corner shares the line of x0 in all but 1 of 10 cases)
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
 #pragma unroll
