@@ -41,6 +41,7 @@ PROTOTYPES = {
     'dvsg_host_tps_warp': (c_int, [_P, _P, _P, _P, _P, c_int]),
     'dvsg_frames_u8_to_f32': (c_int, [_P, _P, c_longlong, c_int, _P]),
     'dvsg_frames_f32_to_u8': (c_int, [_P, _P, c_longlong, c_int, _P]),
+    'dvsg_frames_u8_resize_to_f32': (c_int, [_P, _P] + [c_int] * 6 + [_P]),
     'dvsg_host_tps_warp_u8': (c_int, [_P, _P, _P, _P, _P, c_int, c_int]),
     'dvsg_tps_eval_points': (c_int, [_P, c_longlong, _P, _P, _P, _P] + [c_int] * 5 + [_P]),
     'dvsg_tps_eval_points_bwd': (c_int, [_P, c_longlong, _P, _P, _P, _P] + [c_int] * 5 + [_P]),

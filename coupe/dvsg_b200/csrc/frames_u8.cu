@@ -86,6 +86,44 @@ __global__ void f32_to_u8_elem_kernel(const float* __restrict__ src, unsigned ch
         dst[i] = (unsigned char)unit_to_u8(__ldg(src + swapped(i, swap_rb)));
 }
 
+// ---- ingest with the resize of eval.py:80: cv2.resize(frame / 255., (out_w, out_h)), INTER_LINEAR on float64 ---------
+// OpenCV's linear resize of a CV_64F image (third-party, version not pinned by the reference; restated from its
+// observable behaviour -- impulse responses and 9 size pairs compared in tests/test_oracle_kat.py against cv2 4.13):
+// pixel centres aligned, fx = (dx + 0.5) * scale - 0.5 with scale = 1 / (dst / src) in double, sx = floor(fx),
+// fx -= sx; sx < 0 -> (0, fx = 0), sx >= src - 1 -> (src - 1, fx = 0); rows likewise but clamped without touching the
+// weight; horizontal pass first, all in double, cast to fp32 by the feed.  The same formulas in double here.
+__global__ void __launch_bounds__(256) u8_resize_to_f32_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int Hs, int Ws,
+                                                               int h, int w, double scale_x, double scale_y, int swap_rb) {
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, b = blockIdx.z;
+    if (dx >= w) return;
+    double fx = __dadd_rn(__dmul_rn((double)dx + 0.5, scale_x), -0.5);
+    int sx = (int)floor(fx);
+    fx = __dadd_rn(fx, -(double)sx);
+    if (sx < 0) { sx = 0; fx = 0.0; }
+    if (sx >= Ws - 1) { sx = Ws - 1; fx = 0.0; }
+    const int sx1 = min(sx + 1, Ws - 1);
+    double fy = __dadd_rn(__dmul_rn((double)dy + 0.5, scale_y), -0.5);
+    const int sy = (int)floor(fy);
+    fy = __dadd_rn(fy, -(double)sy);
+    const int sy0 = min(max(sy, 0), Hs - 1), sy1 = min(max(sy + 1, 0), Hs - 1);
+    const double a0 = __dadd_rn(1.0, -fx), a1 = fx, b0 = __dadd_rn(1.0, -fy), b1 = fy;
+    const unsigned char* f = src + (size_t)b * Hs * Ws * 3;
+    const unsigned char* p00 = f + ((size_t)sy0 * Ws + sx) * 3;
+    const unsigned char* p01 = f + ((size_t)sy0 * Ws + sx1) * 3;
+    const unsigned char* p10 = f + ((size_t)sy1 * Ws + sx) * 3;
+    const unsigned char* p11 = f + ((size_t)sy1 * Ws + sx1) * 3;
+    float* o = dst + (((size_t)b * h + dy) * w + dx) * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const int cs = swap_rb ? 2 - ch : ch;      // cvtColor(BGR2RGB) comes first (eval.py:79)
+        const double s00 = __ddiv_rn((double)__ldg(p00 + cs), 255.0), s01 = __ddiv_rn((double)__ldg(p01 + cs), 255.0);
+        const double s10 = __ddiv_rn((double)__ldg(p10 + cs), 255.0), s11 = __ddiv_rn((double)__ldg(p11 + cs), 255.0);
+        const double r0 = __dadd_rn(__dmul_rn(s00, a0), __dmul_rn(s01, a1));
+        const double r1 = __dadd_rn(__dmul_rn(s10, a0), __dmul_rn(s11, a1));
+        o[ch] = (float)__dadd_rn(__dmul_rn(r0, b0), __dmul_rn(r1, b1));
+    }
+}
+
 static int grid_for(long long n) {
     const long long blocks = (n + 255) / 256;
     return (int)(blocks < 148 * 16 ? (blocks > 0 ? blocks : 1) : 148 * 16);     // grid-stride: 8 CTAs of 256 threads per SM, two rounds
@@ -115,4 +153,18 @@ extern "C" int dvsg_frames_f32_to_u8(const float* src, unsigned char* dst, long 
     else f32_to_u8_elem_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(src, dst, n, swap_rb);
     count_launch();
     return check_launch("f32_to_u8_kernel");
+}
+
+extern "C" int dvsg_frames_u8_resize_to_f32(const unsigned char* src, float* dst, int B, int Hs, int Ws, int h, int w, int swap_rb,
+                                            void* stream) {
+    DVSG_REQUIRE(B >= 0 && Hs >= 2 && Ws >= 2 && h > 0 && w > 0, "frames_u8_resize_to_f32: bad shape (source frames need at least 2 x 2 pixels)");
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(src && dst, "frames_u8_resize_to_f32: null pointer");
+    DVSG_REQUIRE(B <= 65535 && h <= 65535, "frames_u8_resize_to_f32: batch %d / height %d exceed the grid limits", B, h);
+    // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale (both double)
+    const double scale_x = 1.0 / ((double)w / (double)Ws), scale_y = 1.0 / ((double)h / (double)Hs);
+    u8_resize_to_f32_kernel<<<dim3((unsigned)((w + 255) / 256), (unsigned)h, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        src, dst, Hs, Ws, h, w, scale_x, scale_y, swap_rb);
+    count_launch();
+    return check_launch("u8_resize_to_f32_kernel");
 }

@@ -3,7 +3,7 @@
 The reference's inference loop converts every frame on the CPU (eval.py:76-81: BGR uint8 -> RGB, / 255.) and converts
 the stabilised frame back (eval.py:112-113: np.uint8(x * 255.), RGB -> BGR).  These are the same two conversions as
 CUDA kernels behind the C ABI (dvsg_frames_u8_to_f32 / dvsg_frames_f32_to_u8), so frames can cross PCIe as uint8.
-The resize of eval.py:80 is the identity for videos that already have the working size and is not implemented.
+read_frames() also performs the resize of eval.py:80 (cv2.resize of the float64 frame, INTER_LINEAR) on the device.
 """
 import torch
 
@@ -40,4 +40,19 @@ def frames_f32_to_u8(frames_f32, swap_rb=True):
     with torch.cuda.device(f.device):
         rc = _lib.load().dvsg_frames_f32_to_u8(f.data_ptr(), out.data_ptr(), f.numel() // 3, 1 if swap_rb else 0, stream_ptr(f.device))
     _lib.check(rc, 'dvsg_frames_f32_to_u8')
+    return out
+
+
+def read_frames(frames_u8, out_size, swap_rb=True):
+    """read_frame (eval.py:76-81) for a batch: uint8 [B, Hs, Ws, 3] (BGR when swap_rb) -> fp32 RGB [B, h, w, 3] =
+    cv2.resize(cv2.cvtColor(frame, BGR2RGB) / 255., (w, h)), cast to fp32 as the feed does.  out_size = (h, w)."""
+    f = _check_u8(frames_u8, 'frames_u8')
+    if f.dtype != torch.uint8 or f.dim() != 4:
+        raise ValueError('frames_u8: expected a uint8 [B, H, W, 3] tensor, got %s %r' % (f.dtype, tuple(f.shape)))
+    h, w = int(out_size[0]), int(out_size[1])
+    B, Hs, Ws = f.shape[0], f.shape[1], f.shape[2]
+    out = torch.empty((B, h, w, 3), dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        rc = _lib.load().dvsg_frames_u8_resize_to_f32(f.data_ptr(), out.data_ptr(), B, Hs, Ws, h, w, 1 if swap_rb else 0, stream_ptr(f.device))
+    _lib.check(rc, 'dvsg_frames_u8_resize_to_f32')
     return out

@@ -153,8 +153,8 @@ int  dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, const float*
 
 /* ---- N4: frame ingest / egress (the steps on either side of the warp in eval.py) -------------
  * dvsg_frames_u8_to_f32 replaces read_frame's `cv2.cvtColor(frame, BGR2RGB); frame / 255.`
- * (eval.py:79-80; the resize of :80 is the identity when the video already has the working size
- * and is not implemented): src [n_pixels,3] uint8 -> dst [n_pixels,3] fp32 = u/255 exactly as
+ * (eval.py:79-80; the resize of :80 is the identity when the video already has the working size,
+ * see dvsg_frames_u8_resize_to_f32 otherwise): src [n_pixels,3] uint8 -> dst [n_pixels,3] fp32 = u/255 exactly as
  * numpy's fp64 division followed by the fp32 feed gives it; swap_rb != 0 reverses the channels.
  * dvsg_frames_f32_to_u8 replaces `np.uint8(frame * 255.)` + `cv2.cvtColor(.., RGB2BGR)`
  * (eval.py:112-113): truncation of the exact product, low byte of the int32 cast outside
@@ -163,6 +163,11 @@ int dvsg_frames_u8_to_f32(const unsigned char* src, float* dst, long long n_pixe
                           void* stream);
 int dvsg_frames_f32_to_u8(const float* src, unsigned char* dst, long long n_pixels, int swap_rb,
                           void* stream);
+/* Ingest WITH the resize of eval.py:80, `cv2.resize(frame / 255., (out_w, out_h))` (INTER_LINEAR on
+ * float64, then the fp32 feed): src [B,Hs,Ws,3] uint8 -> dst [B,h,w,3] fp32.  OpenCV's arithmetic
+ * restated in double; equal to the cv2 result after the fp32 cast (tests compare against cv2).   */
+int dvsg_frames_u8_resize_to_f32(const unsigned char* src, float* dst, int B, int Hs, int Ws, int h,
+                                 int w, int swap_rb, void* stream);
 /* Host pipeline with uint8 frames on the host side: U_host, out_host [B,H,W,3] uint8; ingest and
  * egress run on the device, so a frame crosses PCIe as 3 B/pixel each way.  C must be 3.     */
 int  dvsg_host_tps_warp_u8(dvsg_host_pipeline* p, const unsigned char* U_host,

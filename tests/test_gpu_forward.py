@@ -439,3 +439,23 @@ def test_host_pipeline_u8_matches_reference_loop():
     # and against the oracle end to end: the sampler stage is bit-exact on the kernel's coordinates
     ref = O.tps_interpolate(u, x, y, H, W).reshape(B, H, W, 3)
     np.testing.assert_array_equal(out8.numpy(), O.frames_f32_to_u8(ref, True))
+
+
+@pytest.mark.parametrize('sizes', [(720, 1280, 288, 512), (480, 640, 288, 512), (100, 150, 288, 512), (288, 512, 288, 512), (37, 53, 61, 19), (2, 2, 5, 7)])
+def test_read_frames_with_resize_matches_cv2(sizes):
+    """eval.py:76-81 including cv2.resize: the device ingest equals cv2's result after the fp32 feed cast.  Stated bar:
+    max-abs <= 1.2e-7 (one fp32 ulp at 1.0: the sums are formed in double in both, a different last double bit can move
+    the fp32 rounding); in practice bit-identical."""
+    import cv2
+    from coupe.dvsg_b200 import frame_io
+    hs, ws, h, w = sizes
+    rng = np.random.default_rng(sum(sizes))
+    f8 = rng.integers(0, 256, (2, hs, ws, 3), dtype=np.uint8)
+    got = frame_io.read_frames(cu(f8), (h, w)).cpu().numpy()
+    for i in range(2):
+        ref = cv2.resize(cv2.cvtColor(f8[i], cv2.COLOR_BGR2RGB) / 255., (w, h)).astype(np.float32)
+        assert np.abs(got[i] - ref).max() <= 1.2e-7
+        assert (got[i] != ref).mean() <= 1e-3
+        np.testing.assert_array_equal(got[i], O.read_frame(f8[i], w, h))      # the oracle's restatement: bit-exact
+    with pytest.raises(ValueError):
+        frame_io.read_frames(cu(f8[:, :1]), (h, w))          # one-row sources are outside the restated algorithm

@@ -196,3 +196,23 @@ def test_masked_mse_and_surf_loss_known_answers():
     surf[0, 0, 0] = [3, 2]                               # unstable feature two pixels to the right
     loss, _ = O.surf_loss(surf, xs, ys, np.array([3.0]), b, w, h)
     assert abs(loss - (2 * 2.0 / (w - 1)) ** 2 / 3.0) < 1e-6
+
+
+def test_resize_restatement_matches_cv2():
+    """eval.py:80 calls cv2.resize on the float64 frame: the oracle's restatement of OpenCV's INTER_LINEAR agrees with
+    cv2 itself to 1e-12 in float64 (the last double bits depend on OpenCV's own summation / FMA use), hence to at most
+    one fp32 ulp -- in practice bit for bit -- after the fp32 feed cast, for integer and non-integer ratios, up- and
+    down-scaling, and its impulse responses (the interpolation weights) are cv2's."""
+    import cv2
+    rng = np.random.default_rng(1)
+    for hs, ws, h, w in [(720, 1280, 288, 512), (480, 640, 288, 512), (100, 150, 288, 512), (288, 512, 288, 512), (37, 53, 61, 19),
+                         (719, 1279, 288, 512), (2, 2, 5, 7), (3, 5, 3, 5)]:
+        f8 = rng.integers(0, 256, (hs, ws, 3), dtype=np.uint8)
+        ref = cv2.resize(cv2.cvtColor(f8, cv2.COLOR_BGR2RGB) / 255., (w, h))
+        got = O.resize_linear_f64(f8[..., ::-1] / 255., w, h)
+        assert np.abs(ref - got).max() <= 1e-12
+        mine, ref32 = O.read_frame(f8, w, h), ref.astype(np.float32)
+        assert np.abs(mine - ref32).max() <= 1.2e-7 and (mine != ref32).mean() <= 1e-3
+    imp = np.zeros((2, 9, 1))
+    imp[:, 4, 0] = 1.0
+    np.testing.assert_allclose(O.resize_linear_f64(imp, 7, 2)[..., 0], cv2.resize(imp, (7, 2)), atol=1e-15)
