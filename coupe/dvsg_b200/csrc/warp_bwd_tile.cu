@@ -247,6 +247,55 @@ __device__ __forceinline__ float4 bwd_pair_clamped(const float2 xp, const float2
     return make_float4(dx.x, dx.y, dy.x, dy.y);
 }
 
+// Zero-padded samplers at the frame border (bilinear_interp / tf_warp): corners a, a+12, a+pitch, a+pitch+12 of the
+// staged footprint, whose out-of-frame parts the TMA copy filled with zeros -- the reference's zero padding -- and
+// red.global.add.f32 for the corners that lie inside the frame (the padding receives no gradient).  xp, yp are
+// clipped+1 coordinates in the padded frame; sb has the -1 pixel shift folded in.
+__device__ __forceinline__ float4 bwd_pair_padded(const float2 xp, const float2 yp, const float ga0, const float ga1, const float ga2, const float gb0,
+                                                  const float gb1, const float gb2, const unsigned char* __restrict__ sb, const int pitch, const int W,
+                                                  const int H, float* __restrict__ gsrcb, const bool ok_a, const bool ok_b) {
+    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
+    const float2 x0f = floor2_pos(xp), y0f = floor2_pos(yp);
+    const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
+    const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
+    const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
+    const float2 o00 = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
+    const float* p0[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o00.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o00.y) & 0x7fffff))};
+    const float* p1[2] = {reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[0]) + pitch),
+                          reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[1]) + pitch)};
+    // frame coordinates of the corners: padded index - 1
+    const int xa[2] = {(__float_as_int(x0f.x + MAGIC23) & 0x7fffff) - 1, (__float_as_int(x0f.y + MAGIC23) & 0x7fffff) - 1};
+    const int ya[2] = {(__float_as_int(y0f.x + MAGIC23) & 0x7fffff) - 1, (__float_as_int(y0f.y + MAGIC23) & 0x7fffff) - 1};
+    const bool ok[2] = {ok_a, ok_b};
+    const float gq[2][3] = {{ga0, ga1, ga2}, {gb0, gb1, gb2}};
+    float2 dx = f2dup(0.0f), dy = f2dup(0.0f);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float2 g = f2(gq[0][ch], gq[1][ch]);
+        const float2 i00 = f2(p0[0][ch], p0[1][ch]), i01 = f2(p0[0][3 + ch], p0[1][3 + ch]);
+        const float2 i10 = f2(p1[0][ch], p1[1][ch]), i11 = f2(p1[0][3 + ch], p1[1][3 + ch]);
+        const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
+        const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
+        dx = __ffma2_rn(g, ux, dx);
+        dy = __ffma2_rn(g, uy, dy);
+        if (gsrcb) {
+            const float2 c00 = __fmul2_rn(w00, g), c01 = __fmul2_rn(w01, g), c10 = __fmul2_rn(w10, g), c11 = __fmul2_rn(w11, g);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!ok[h]) continue;
+                const int x0 = xa[h], y0 = ya[h];
+                const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+                float* q = gsrcb + ((long long)y0 * W + x0) * 3 + ch;
+                if (vx0 && vy0) atomicAdd(q, h ? c00.y : c00.x);
+                if (vx1 && vy0) atomicAdd(q + 3, h ? c01.y : c01.x);
+                if (vx0 && vy1) atomicAdd(q + (size_t)W * 3, h ? c10.y : c10.x);
+                if (vx1 && vy1) atomicAdd(q + (size_t)W * 3 + 3, h ? c11.y : c11.x);
+            }
+        }
+    }
+    return make_float4(dx.x, dx.y, dy.x, dy.y);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTileParams p, const __grid_constant__ BwdTileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -367,8 +416,8 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
             fy_lo = min(max(y_lo, 0), H - 1); fy_hi = min(max(y_hi, 0), H - 1);
         } else {
             fx_lo = x_lo - 1; fx_hi = x_hi - 1; fy_lo = y_lo - 1; fy_hi = y_hi - 1;
-            // frame-border tiles (footprint reaching into the zero padding) take the per-pixel path: the TMA
-            // reduce-add faults on boxes that start outside the tensor
+            // frame-border tiles (footprint reaching into the zero padding) cannot use the accumulation buffer -- the TMA
+            // reduce-add faults on boxes that start outside the tensor -- they scatter with red.global (bwd_pair_padded)
             interior = fx_lo >= 0 && fy_lo >= 0 && fx_hi <= W - 1 && fy_hi <= H - 1;
         }
         const int fx0 = (fx_lo * 3) & ~3;
@@ -378,8 +427,7 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         else if (fw <= p.bw[2] && nrows <= p.bh[2]) box = 2;
         const int pitch = (box == 2 ? p.bw[2] : p.bw[0]) * 4;
         const int box_rows = box == 0 ? p.bh[0] : (box == 1 ? p.bh[1] : p.bh[2]);
-        bool staged = box >= 0 && all_sane && (MODE == TMODE_TPS || interior) &&
-                      (long long)(fy_hi + 3) * pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
+        bool staged = box >= 0 && all_sane && (long long)(fy_hi + 3) * pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
         // Two staged variants.  fast: no corner touches the frame border and the source columns of every row do not
         // decrease and never repeat more than twice (x scale >= 0.5, no fold) -- the read-modify-write rounds below.
         // Otherwise (TPS only): clamped corners and shared-memory atomics into the same accumulation buffer.
@@ -396,7 +444,6 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
             }
             fast = __all_sync(0xffffffffu, mono);
         }
-        if (MODE != TMODE_TPS) staged = fast;      // the padded samplers have no clamped variant: per-pixel path
 
         // ================= L: stage the source footprint, clear the accumulation buffer =================
         if (red_pending) {                 // the previous tile's reduce-add must have read the accumulation buffer
@@ -428,12 +475,17 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
                                                gq[2 * j + 1][1], gq[2 * j + 1][2], sb, pitch, gsrcb != nullptr);
                 GX[j] = f2(d.x, d.y); GY[j] = f2(d.z, d.w);
             }
-        } else if (MODE == TMODE_TPS && staged) {
-            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4);
+        } else if (staged) {
+            // frame-border tiles and folding maps: corners still come from the staged footprint, the scatter goes to global memory
+            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                const float4 d = bwd_pair_clamped(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1],
-                                                  gq[2 * j + 1][2], sb, pitch, W, H, gsrcb, col_ok && row0 + 2 * j < oh, col_ok && row0 + 2 * j + 1 < oh);
+                const bool ok_a = col_ok && row0 + 2 * j < oh, ok_b = col_ok && row0 + 2 * j + 1 < oh;
+                const float4 d = MODE == TMODE_TPS
+                    ? bwd_pair_clamped(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
+                                       sb, pitch, W, H, gsrcb, ok_a, ok_b)
+                    : bwd_pair_padded(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
+                                      sb, pitch, W, H, gsrcb, ok_a, ok_b);
                 GX[j] = f2(d.x, d.y); GY[j] = f2(d.z, d.w);
             }
         } else {

@@ -143,8 +143,35 @@ def c18():
 
 
 
+def bwd():
+    """backward kernels (CUDA events; grad_image zero fill not included in the time, counted in the bytes as in DESIGN.md)"""
+    for (B, H, W, tag) in ((32, 288, 512, 'training shape'), (16, 1080, 1920, '1080p')):
+        U, coord, T = tps_case(B, H, W, 4, 0.2)
+        g = torch.rand((B, H, W, 3), device=dev)
+        gU = torch.zeros_like(U)
+        px = B * H * W
+        ms = timeit(lambda: ops.tps_warp_bwd(U, coord, T, (H, W), g, None, None, need_grad_U=True, want_grid_grad=True, grad_U_out=gU))
+        rec('tps bwd 4x4 %s B=%d (grad image, grid, T)' % (tag, B), ms, px, 56)
+        ms = timeit(lambda: ops.tps_warp_bwd(U, coord, T, (H, W), g, None, None, need_grad_U=False, want_grid_grad=True))
+        rec('tps bwd 4x4 %s B=%d (grad grid, T only)' % (tag, B), ms, px, 32)
+        flow = smooth_flow(B, H, W)
+        gf = torch.empty_like(flow)
+        s = torch.cuda.current_stream().cuda_stream
+
+        def fb(want_flow):
+            rc = lib.dvsg_flow_warp_bwd(U.data_ptr(), flow.data_ptr(), g.data_ptr(), gU.data_ptr(), gf.data_ptr() if want_flow else None, B, H, W, 3, s)
+            assert rc == 0
+        ms = timeit(lambda: fb(False))
+        rec('tf_warp bwd %s B=%d smooth flow (grad image only, trainer.py:246-247)' % (tag, B), ms, px, 44)
+        ms = timeit(lambda: fb(True))
+        rec('tf_warp bwd %s B=%d smooth flow (grad image and flow)' % (tag, B), ms, px, 64)
+        del U, g, gU, flow, gf
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'c18':
         c18()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'bwd':
+        bwd()
     else:
         main()
