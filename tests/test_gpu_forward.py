@@ -231,6 +231,30 @@ def test_staged_and_direct_kernels_agree_bitwise_at_720p():
     assert torch.equal(a2[0], b2[0])
 
 
+def test_4k_16x16_mesh_properties():
+    """BASELINE configs[4] shape (2160x3840 frames, 16x16 mesh, N = 259: prepared solve, generic 48-byte tables, XU-bound
+    kernel): tile kernel == direct kernel bit for bit; an identity mesh reproduces the A4 sampler's own identity map
+    (x_pix = j * W / (W - 1), last row / column zero) against the oracle's sampler on the kernel's coordinates."""
+    from coupe.dvsg_b200 import ops
+    torch.manual_seed(1)
+    B, H, W, m = 1, 2160, 3840, 16
+    U = torch.rand((B, H, W, 3), device=DEV)
+    mesh = cu(tiled_mesh(m, m, 1)[0])
+    coord = mesh.unsqueeze(0).expand(B, -1, -1)
+    vec = (torch.rand((B, m * m, 2), device=DEV) - 0.5) * 0.04
+    T = ops.tps_solve(coord, coord + vec)
+    a = ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True)
+    b = ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True, flags=FORCE_DIRECT)
+    for p_, q_ in zip(a[:3], b[:3]):
+        assert torch.equal(p_, q_)
+    T0 = ops.tps_solve(coord, coord)
+    out, x, y, _ = ops.tps_warp_fwd(U, coord, T0, (H, W), want_grid=True)
+    xs = x.reshape(H, W)[::270, ::480].cpu().numpy()
+    assert np.abs(xs - O.tf_linspace(-1.0, 1.0, W)[::480][None]).max() <= 2e-4      # stated looser bound for N = 259 (SURVEY H4)
+    # the identity map zeroes the last row / column: the clamped corners' paired weights cancel (ThinPlateSpline.py:57-60,81-88)
+    assert float(out[0, -1].abs().max()) <= 1e-5 and float(out[0, :, -1].abs().max()) <= 1e-5
+
+
 def test_mask_output_equals_warp_of_ones():
     """N1: mask_out == ThinPlateSpline(ones_like(U), ...) (model.py:82,85), exactly."""
     from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline, ThinPlateSplineWithMask
