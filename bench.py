@@ -251,7 +251,18 @@ def run_ours(args, wl):
 
         bwd_pairs = []
 
+        online = ops.OnlineWarper(mesh, B, H, W) if (B == 1 and not train) else None     # cfg1: the per-frame loop of eval.py
+
         def step(sample=False):
+            if online is not None:
+                if sample:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                res = online.warp(U, vec)
+                if sample:
+                    e1.record(stream)
+                    ev_pairs.append((e0, e1))
+                return res
             target = coord + vec
             T = ops.tps_solve(coord, target)
             if sample:

@@ -458,3 +458,14 @@ extern "C" int dvsg_st_meshgrid(float* grid, int oh, int ow, void* stream) {
     count_launch();
     return check_launch("st_meshgrid_kernel");
 }
+
+// One call per batch of frames for the online loop (eval.py:106-110 runs the graph once per frame): coefficients from the
+// prepared inverse of the clip's constant mesh, then the fused warp -- two launches, one trip through the ABI.  `target`
+// is coord + vector (ThinPlateSpline.py:161); T [B,2,pn+3] is scratch the caller owns (and may read afterwards).
+extern "C" int dvsg_tps_warp_frames(const float* U, const float* coord, const float* target, void* prepared, size_t prepared_bytes,
+                                    float* T, float* out, float* x_out, float* y_out, float* mask_out, int B, int H, int W, int C, int oh,
+                                    int ow, int pn, void* stream) {
+    const int rc = dvsg_tps_solve_prepared(coord, 0, target, T, B, pn, prepared, prepared_bytes, stream);
+    if (rc) return rc;
+    return dvsg_tps_warp_fwd(U, coord, 0, T, out, x_out, y_out, mask_out, B, H, W, C, oh, ow, pn, 0, stream);
+}

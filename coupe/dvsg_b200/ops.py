@@ -50,7 +50,7 @@ def _mesh_args(coord, B, pn_expected=None):
     pn = coord.shape[1]
     if pn_expected is not None and pn != pn_expected:
         raise ValueError('coord has %d control points, expected %d' % (pn, pn_expected))
-    if B > 0 and coord.stride(0) == 0:
+    if B > 0 and (coord.stride(0) == 0 or B == 1):      # a single frame's mesh is "shared" too: prepared solve, one table
         return coord[0].contiguous(), 0, pn
     return coord.contiguous(), pn * 2, pn
 
@@ -336,6 +336,41 @@ def homography_warp(inp, theta, out_size, projective, want_grid=False):
                                           B, H, W, C, oh, ow, stream_ptr(inp.device))
     _lib.check(rc, 'dvsg_homography_warp_fwd')
     return (out, x, y) if want_grid else out
+
+
+# ---- online loop -----------------------------------------------------------------------------
+class OnlineWarper(object):
+    """ThinPlateSpline for the online loop of eval.py:106-110 (one small batch per call, constant mesh, inference only):
+    the mesh's system is inverted once, buffers are allocated once, and each call is ONE trip through the C ABI
+    (dvsg_tps_warp_frames = prepared solve + fused warp).  Same results as ThinPlateSpline(U, coord, vector, [h, w])."""
+
+    def __init__(self, mesh, B, H, W, C=3, device=None):
+        lib = _lib.load()
+        self.mesh = as_cuda_f32(mesh, 'mesh').reshape(-1, 2).contiguous()
+        dev = self.mesh.device if device is None else torch.device(device)
+        self.B, self.H, self.W, self.C, self.pn = int(B), int(H), int(W), int(C), self.mesh.shape[0]
+        self.nbytes = lib.dvsg_tps_prepare_workspace_bytes(self.B, self.pn, 0)
+        self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.dvsg_tps_prepare(ptr(self.mesh), 0, self.B, self.pn, ptr(self.ws), self.nbytes, stream_ptr(dev))
+        _lib.check(rc, 'dvsg_tps_prepare')
+        self.T = torch.empty((self.B, 2, self.pn + 3), dtype=torch.float32, device=dev)
+        self.target = torch.empty((self.B, self.pn, 2), dtype=torch.float32, device=dev)
+        self.out = torch.empty((self.B, self.H, self.W, self.C), dtype=torch.float32, device=dev)
+        self._fn = lib.dvsg_tps_warp_frames
+        self._args = (ptr(self.mesh), ptr(self.target), ptr(self.ws), self.nbytes, ptr(self.T), ptr(self.out), None, None, None,
+                      self.B, self.H, self.W, self.C, self.H, self.W, self.pn)
+
+    def warp(self, U, vector):
+        """U [B,H,W,C] and vector [B,pn,2]: contiguous fp32 CUDA tensors.  Returns the warped frames (a buffer owned by this
+        object, overwritten by the next call)."""
+        if U.shape != self.out.shape or U.dtype != torch.float32 or not U.is_cuda or not U.is_contiguous():
+            raise ValueError('U must be a contiguous fp32 CUDA tensor of shape %r' % (tuple(self.out.shape),))
+        torch.add(self.mesh, vector, out=self.target)                  # coord + vector, ThinPlateSpline.py:161
+        rc = self._fn(U.data_ptr(), *self._args, torch.cuda.current_stream(U.device).cuda_stream)
+        if rc:
+            _lib.check(rc, 'dvsg_tps_warp_frames')
+        return self.out
 
 
 # ---- host-buffer pipeline --------------------------------------------------------------------

@@ -93,6 +93,14 @@ int dvsg_tps_warp_fwd(const float* U, const float* coord, long long coord_batch_
                       int B, int H, int W, int C, int oh, int ow, int pn, int flags,
                       void* stream);
 
+/* Online loop (eval.py:106-110 runs the graph once per frame): dvsg_tps_solve_prepared followed
+ * by dvsg_tps_warp_fwd in one call.  coord [pn,2] is the clip's constant mesh, `prepared` its
+ * inverse from dvsg_tps_prepare, target = coord + vector [B,pn,2], T [B,2,pn+3] caller scratch. */
+int dvsg_tps_warp_frames(const float* U, const float* coord, const float* target, void* prepared,
+                         size_t prepared_bytes, float* T, float* out, float* x_out, float* y_out,
+                         float* mask_out, int B, int H, int W, int C, int oh, int ow, int pn,
+                         void* stream);
+
 /* ---- K4: backward of K2+K3 (TF autodiff of ThinPlateSpline.py:48-89,129) -------------
  *   grad_out [B,oh,ow,C]; grad_x_in / grad_y_in: optional upstream gradients on the
  *   returned x, y (surf loss, trainer.py:363-386);

@@ -483,3 +483,20 @@ def test_read_frames_with_resize_matches_cv2(sizes):
         np.testing.assert_array_equal(got[i], O.read_frame(f8[i], w, h))      # the oracle's restatement: bit-exact
     with pytest.raises(ValueError):
         frame_io.read_frames(cu(f8[:, :1]), (h, w))          # one-row sources are outside the restated algorithm
+
+
+def test_online_warper_equals_the_dropin():
+    """ops.OnlineWarper (prepared mesh, preallocated buffers, one C-ABI call per frame) == ThinPlateSpline, bit for bit."""
+    from coupe.dvsg_b200 import ops
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline
+    rng = np.random.default_rng(21)
+    B, H, W = 1, 96, 160
+    mesh = cu(tiled_mesh(5, 5, 1)[0])
+    warper = ops.OnlineWarper(mesh, B, H, W)
+    for _ in range(3):
+        U = cu(smooth_image(rng, B, H, W, 3))
+        vec = cu(rng.uniform(-0.1, 0.1, (B, 25, 2)).astype(np.float32))
+        ref, _, _ = ThinPlateSpline(U, mesh, vec, [H, W], return_grid=False)
+        assert torch.equal(warper.warp(U, vec), ref)
+    with pytest.raises(ValueError):
+        warper.warp(U[:, :10], vec)
