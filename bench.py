@@ -425,7 +425,7 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--e2e-frames', type=int, default=64)
-    ap.add_argument('--e2e-chunk', type=int, default=2, help='frames per staging chunk of the host pipeline')
+    ap.add_argument('--e2e-chunk', type=int, default=4, help='frames per staging chunk of the host pipeline')
     ap.add_argument('--e2e-slots', type=int, default=4, help='device staging slots (streams) of the host pipeline')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
