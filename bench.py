@@ -310,7 +310,10 @@ def run_ours(args, wl):
         barrier()
     elapsed_ms = t0.elapsed_time(t1)
     launches = _lib.launch_count() - l0
-    kern_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(len(ev_pairs), 1)
+    def median_ms(pairs):          # median of the per-launch samples: the first sampled step runs right after the barrier
+        ts = sorted(a.elapsed_time(b) for a, b in pairs)
+        return ts[len(ts) // 2] if ts else float('nan')
+    kern_ms = median_ms(ev_pairs)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -370,7 +373,7 @@ def run_ours(args, wl):
         if kind == 'tps_train':
             # the dominant kernel of the training shape is the backward: 56 B/px (grad_out 12 + source 12 +
             # grad_image zero fill 12 + grad_image accumulate 12 + grad_x,y 8)
-            bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_pairs) / max(len(bwd_pairs), 1)
+            bwd_ms = median_ms(bwd_pairs)
             extra = {'forward_kernel': {'kernel': kernel_name, 'kernel_ms': kern_ms, 'achieved': achieved, 'algorithmic_bytes_per_px': 32}}
             kernel_name, kern_ms, fwd_bpp = 'warp_bwd_tile_kernel<TMODE_TPS> (warp_bwd_tile.cu)', bwd_ms, 56
             achieved = pix_per_step * fwd_bpp / (kern_ms * 1e-3) / 1e9
