@@ -8,21 +8,24 @@
 //              chained to the caller's coordinates (A4: *W/2; ZP: *(W-1)/2 or 1, and the float
 //              clip_by_value mask -1 <= x_pix <= W)
 //   grad_im    scatter-add of w_k * grad_out over the four corners.  Float atomics on shared memory
-//              are CAS loops on this architecture, so the warp accumulates into a PRIVATE shared
-//              buffer shaped like its staged footprint with plain read-modify-write rounds: one
-//              round per (pixel row, corner class), inside a round every address is touched by one
-//              lane only (contributions of adjacent lanes that hit the same source pixel are merged
-//              with one shuffle first).  The buffer then goes to global memory with ONE TMA tensor
-//              reduce-add (cp.reduce.async.bulk.tensor .add.f32); out-of-frame parts -- the zero
-//              padding of the padded samplers -- are dropped by the hardware.
+//              are CAS loops on this architecture, but INTEGER ones are native (ATOMS.ADD): the warp
+//              accumulates into a PRIVATE shared buffer shaped like its staged footprint in 32-bit
+//              fixed point, scaled per tile by a power of two taken from max |grad_out| (22 significant
+//              bits; weights of an interior tile lie in [0, 1]) -- exact, order-independent sums with no
+//              ordering between lanes, rows or corner classes.  The buffer is converted to fp32 in
+//              place and goes to global memory with ONE TMA tensor reduce-add
+//              (cp.reduce.async.bulk.tensor .add.f32); box parts outside the frame are dropped by the
+//              hardware.
 //   grad_T     sum over pixels of grad(x_s, y_s) * basis: a second pass over the basis multiplies
 //              it with the per-pixel gradients in packed fp32x2, 8 control points x (x, y) = 16
 //              partial sums per lane are reduced across the warp with a 16-shuffle transpose
 //              reduction, accumulated per warp in shared memory, and issued as red.global once per
 //              warp at the end of its strip.
-// Tiles whose footprint does not fit a box, TPS tiles at the frame border and mappings that fold
-// (source columns not monotone along a row) take a per-pixel path with global gathers and
-// red.global.add.f32.  Atomic ordering makes grad_im reproducible to rounding only.
+// Frame-border tiles read their corners from the staged footprint too and scatter with red.global.add.f32 (the A4
+// sampler's clamped corners carry weights as large as the distance to the frame; the reduce-add box of the padded
+// samplers would start outside the tensor); tiles whose footprint fits no box, and tiles with non-finite gradients,
+// take a per-pixel path with global gathers and red.global.  grad_im is reproducible to the rounding of the fp32 adds
+// between tiles only.
 #include "tile_common.cuh"
 
 namespace dvsg {
@@ -120,78 +123,7 @@ __device__ __noinline__ void bwd_general_pixel(float xp, float yp, int W, int H,
     }
 }
 
-// one read-modify-write round of the private accumulation buffer: contribution c (3 channels) of every lane
-// to address q; `dupn` lanes first hand their contribution to... receive the contribution of the next lane,
-// only run heads write
-__device__ __forceinline__ void rmw_round(float* __restrict__ q, float c0, float c1, float c2, bool head, bool dupn) {
-    const float n0 = __shfl_down_sync(0xffffffffu, c0, 1), n1 = __shfl_down_sync(0xffffffffu, c1, 1), n2 = __shfl_down_sync(0xffffffffu, c2, 1);
-    if (dupn) { c0 += n0; c1 += n1; c2 += n2; }
-    if (head) {
-        const float o0 = q[0], o1 = q[1], o2 = q[2];
-        q[0] = o0 + c0; q[1] = o1 + c1; q[2] = o2 + c2;
-    }
-    __syncwarp();
-}
-
-// ---- one pixel pair (rows 2j, 2j+1 of the lane's column) of a staged tile, fast variant ---------------------------
-// Inlined four times per tile: out-of-line calls were measured and lose (caller-saved registers spill around every
-// call: 172 us instead of 157 us at the training shape), although the unrolled kernel is 110 KB of SASS.
-// Returns (d out/d x_pix of the two pixels, d out/d y_pix of the two pixels); scatters w_k * grad_out into the private
-// accumulation buffer (= staging buffer + TSTAGE_BYTES, same layout) with read-modify-write rounds.
-__device__ __forceinline__ float4 bwd_pair_fast(const float2 xp, const float2 yp, const float2 x0f, const float2 y0f, const float ga0, const float ga1,
-                                             const float ga2, const float gb0, const float gb1, const float gb2, const unsigned char* __restrict__ sb,
-                                             const int pitch, const bool scatter) {
-    const int lane = threadIdx.x & 31;
-    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
-    const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
-    const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
-    const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
-    const float2 o00 = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
-    const int ka = __float_as_int(o00.x) & 0x7fffff, kb = __float_as_int(o00.y) & 0x7fffff;
-    const float* __restrict__ pa = reinterpret_cast<const float*>(sb + ka);
-    const float* __restrict__ pb = reinterpret_cast<const float*>(sb + kb);
-    const float* __restrict__ qa = reinterpret_cast<const float*>(sb + ka + pitch);
-    const float* __restrict__ qb = reinterpret_cast<const float*>(sb + kb + pitch);
-    const float2 g[3] = {f2(ga0, gb0), f2(ga1, gb1), f2(ga2, gb2)};
-    float2 dx = f2dup(0.0f), dy = f2dup(0.0f);
-    float2 c00[3], c01[3], c10[3], c11[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float2 i00 = f2(pa[ch], pb[ch]), i01 = f2(pa[3 + ch], pb[3 + ch]);
-        const float2 i10 = f2(qa[ch], qb[ch]), i11 = f2(qa[3 + ch], qb[3 + ch]);
-        const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
-        const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
-        dx = __ffma2_rn(g[ch], ux, dx);
-        dy = __ffma2_rn(g[ch], uy, dy);
-        c00[ch] = __fmul2_rn(w00, g[ch]); c01[ch] = __fmul2_rn(w01, g[ch]);
-        c10[ch] = __fmul2_rn(w10, g[ch]); c11[ch] = __fmul2_rn(w11, g[ch]);
-    }
-    if (scatter) {
-        float* __restrict__ aa = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pa) + TSTAGE_BYTES));
-        float* __restrict__ ab = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(pb) + TSTAGE_BYTES));
-        float* __restrict__ ca = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(qa) + TSTAGE_BYTES));
-        float* __restrict__ cb2 = const_cast<float*>(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(qb) + TSTAGE_BYTES));
-        {   // row a: the four corner classes share one duplicate pattern (x1 = x0+1, y1 = y0+1)
-            const int nk = __shfl_down_sync(0xffffffffu, ka, 1), pk = __shfl_up_sync(0xffffffffu, ka, 1);
-            const bool head = lane == 0 || pk != ka, dupn = lane != 31 && nk == ka;
-            rmw_round(aa, c00[0].x, c00[1].x, c00[2].x, head, dupn);
-            rmw_round(aa + 3, c01[0].x, c01[1].x, c01[2].x, head, dupn);
-            rmw_round(ca, c10[0].x, c10[1].x, c10[2].x, head, dupn);
-            rmw_round(ca + 3, c11[0].x, c11[1].x, c11[2].x, head, dupn);
-        }
-        {   // row b
-            const int nk = __shfl_down_sync(0xffffffffu, kb, 1), pk = __shfl_up_sync(0xffffffffu, kb, 1);
-            const bool head = lane == 0 || pk != kb, dupn = lane != 31 && nk == kb;
-            rmw_round(ab, c00[0].y, c00[1].y, c00[2].y, head, dupn);
-            rmw_round(ab + 3, c01[0].y, c01[1].y, c01[2].y, head, dupn);
-            rmw_round(cb2, c10[0].y, c10[1].y, c10[2].y, head, dupn);
-            rmw_round(cb2 + 3, c11[0].y, c11[1].y, c11[2].y, head, dupn);
-        }
-    }
-    return make_float4(dx.x, dx.y, dy.x, dy.y);
-}
-
-// Clamped variant (TPS border tiles and folding maps): corners clamped first, weights FROM the clamped corners
+// Clamped variant (TPS tiles at the frame border): corners clamped first, weights FROM the clamped corners
 // (ThinPlateSpline.py:57-60, 81-88; the integer clamps pass no gradient).  The source pixels still come from the staged
 // footprint; the scatter goes straight to global memory as red.global.add.f32 (fire-and-forget, combined per sector
 // in L2): float atomics on shared memory are CAS loops and cost more than the whole per-pixel path.
@@ -241,6 +173,58 @@ __device__ __forceinline__ float4 bwd_pair_clamped(const float2 xp, const float2
                 atomicAdd(gsrcb + ((size_t)yb[h] * W + xa[h]) * 3 + ch, h ? c10.y : c10.x);
                 atomicAdd(gsrcb + ((size_t)ya[h] * W + xb[h]) * 3 + ch, h ? c01.y : c01.x);
                 atomicAdd(gsrcb + ((size_t)yb[h] * W + xb[h]) * 3 + ch, h ? c11.y : c11.x);
+            }
+        }
+    }
+    return make_float4(dx.x, dx.y, dy.x, dy.y);
+}
+
+// ---- one pixel pair (rows 2j, 2j+1 of the lane's column) of an interior staged tile ----------------------------------
+// Returns (d out/d x_pix of the two pixels, d out/d y_pix of the two pixels) and scatters w_k * grad_out.
+// The scatter accumulates in the warp's private buffer (= staging buffer + TSTAGE_BYTES, same layout) as 32-bit FIXED
+// POINT with the native integer shared-memory atomic (ATOMS.ADD; float atomics on shared memory are CAS loops on sm_100
+// and lose to everything else that was tried): no corner of an interior tile touches the frame border, so every weight
+// lies in [0, 1] and |contribution| <= max |grad_out| of the tile.  Contributions are scaled by a power of two chosen per
+// tile from that maximum so that they carry 22 significant bits (rounded to nearest by the 1.5 * 2^23 trick: absolute
+// error <= 2^-23 of the tile's largest gradient, fp32's own resolution there); integer sums are exact, independent of
+// the order, and cannot overflow below 512 contributions per source pixel.  No ordering between lanes, rows or corner
+// classes is needed -- the previous scheme (plain read-modify-write rounds, one per row and corner class, duplicates
+// merged by shuffles) cost ~170 instructions per pair, 32 warp barriers per tile and a monotonicity test.
+__device__ __forceinline__ float4 bwd_pair_fixed(const float2 xp, const float2 yp, const float ga0, const float ga1, const float ga2, const float gb0,
+                                                 const float gb1, const float gb2, const unsigned char* __restrict__ sb, const int pitch,
+                                                 const bool scatter, const float scale) {
+    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
+    const float2 x0f = floor2_pos(xp), y0f = floor2_pos(yp);
+    const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
+    const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
+    const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
+    const float2 o00 = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
+    const float* p0[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o00.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o00.y) & 0x7fffff))};
+    const float* p1[2] = {reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[0]) + pitch),
+                          reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[1]) + pitch)};
+    const float gq[2][3] = {{ga0, ga1, ga2}, {gb0, gb1, gb2}};
+    const float2 sc2 = f2dup(scale), m15 = f2dup(MAGIC15);
+    float2 dx = f2dup(0.0f), dy = f2dup(0.0f);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float2 g = f2(gq[0][ch], gq[1][ch]);
+        const float2 i00 = f2(p0[0][ch], p0[1][ch]), i01 = f2(p0[0][3 + ch], p0[1][3 + ch]);
+        const float2 i10 = f2(p1[0][ch], p1[1][ch]), i11 = f2(p1[0][3 + ch], p1[1][3 + ch]);
+        const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
+        const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
+        dx = __ffma2_rn(g, ux, dx);
+        dy = __ffma2_rn(g, uy, dy);
+        if (scatter) {
+            const float2 gs = __fmul2_rn(g, sc2);      // exact: scale is a power of two
+            const float2 q00 = __ffma2_rn(w00, gs, m15), q01 = __ffma2_rn(w01, gs, m15), q10 = __ffma2_rn(w10, gs, m15), q11 = __ffma2_rn(w11, gs, m15);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int* a0 = const_cast<int*>(reinterpret_cast<const int*>(p0[h])) + TSTAGE_BYTES / 4 + ch;
+                int* a1 = const_cast<int*>(reinterpret_cast<const int*>(p1[h])) + TSTAGE_BYTES / 4 + ch;
+                atomicAdd(a0, __float_as_int(h ? q00.y : q00.x) - 0x4B400000);
+                atomicAdd(a1, __float_as_int(h ? q10.y : q10.x) - 0x4B400000);
+                atomicAdd(a0 + 3, __float_as_int(h ? q01.y : q01.x) - 0x4B400000);
+                atomicAdd(a1 + 3, __float_as_int(h ? q11.y : q11.x) - 0x4B400000);
             }
         }
     }
@@ -431,19 +415,21 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         // Two staged variants.  fast: no corner touches the frame border and the source columns of every row do not
         // decrease and never repeat more than twice (x scale >= 0.5, no fold) -- the read-modify-write rounds below.
         // Otherwise (TPS only): clamped corners and shared-memory atomics into the same accumulation buffer.
-        bool fast = staged && interior;
-        float2 X0F[TR / 2], Y0F[TR / 2];
-        if (fast) {
-            bool mono = true;
+        // per-tile fixed-point scale of the scatter: 2^(21 - floor(log2 max|grad_out|)), from the exponent bits of the maximum
+        unsigned gmax_bits = 0;
 #pragma unroll
-            for (int j = 0; j < TR / 2; ++j) {
-                X0F[j] = floor2_pos(XP[j]); Y0F[j] = floor2_pos(YP[j]);
-                const float a1 = __shfl_down_sync(0xffffffffu, X0F[j].x, 1), a2 = __shfl_down_sync(0xffffffffu, X0F[j].x, 2);
-                const float b1 = __shfl_down_sync(0xffffffffu, X0F[j].y, 1), b2 = __shfl_down_sync(0xffffffffu, X0F[j].y, 2);
-                mono = mono && (lane == 31 || (a1 >= X0F[j].x && b1 >= X0F[j].y)) && (lane >= 30 || (a2 > X0F[j].x && b2 > X0F[j].y));
-            }
-            fast = __all_sync(0xffffffffu, mono);
-        }
+        for (int q = 0; q < TR; ++q)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) gmax_bits = max(gmax_bits, __float_as_uint(fabsf(gq[q][ch])));
+        gmax_bits = __reduce_max_sync(0xffffffffu, gmax_bits);
+        const int gexp = min(max((int)(gmax_bits >> 23), 40), 254);
+        const bool g_finite = (gmax_bits >> 23) < 255, g_zero = (gmax_bits >> 23) < 40;      // |g| < 2^-87 everywhere: nothing to scatter
+        // interior tiles accumulate in shared memory (fixed point); frame-border tiles scatter with red.global: the A4 sampler's
+        // clamped corners carry weights as large as the distance to the frame (outside the fixed-point range; they cancel in
+        // pairs), and the reduce-add box of the padded samplers would start outside the tensor
+        const bool fast = staged && g_finite && interior;
+        const float scale = __int_as_float((275 - gexp) << 23), inv_scale = __int_as_float((gexp - 21) << 23);
+        if (!g_finite) staged = false;              // inf / NaN gradients: per-pixel path (float red.global keeps their semantics)
 
         // ================= L: stage the source footprint, clear the accumulation buffer =================
         if (red_pending) {                 // the previous tile's reduce-add must have read the accumulation buffer
@@ -456,7 +442,7 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
                 mbar_arrive_expect_tx(mbar, (unsigned)(pitch * box_rows));
                 tma_load_3d(stage_s, &maps.src[box], fx0, fy_lo, b, mbar);
             }
-            if (gsrcb && fast) {
+            if (gsrcb && fast && !g_zero) {
                 float4* z = reinterpret_cast<float4*>(w_acc);
                 const int n16 = pitch * box_rows / 16;
                 for (int i = lane; i < n16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -469,14 +455,15 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         float2 GX[TR / 2], GY[TR / 2];     // gradient w.r.t. the sampler's pixel-space coordinate, then chained
         if (fast) {
             const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
+            const bool sc = gsrcb != nullptr && !g_zero;
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                const float4 d = bwd_pair_fast(XP[j], YP[j], X0F[j], Y0F[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0],
-                                               gq[2 * j + 1][1], gq[2 * j + 1][2], sb, pitch, gsrcb != nullptr);
+                const float4 d = bwd_pair_fixed(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
+                                                sb, pitch, sc, scale);
                 GX[j] = f2(d.x, d.y); GY[j] = f2(d.z, d.w);
             }
         } else if (staged) {
-            // frame-border tiles and folding maps: corners still come from the staged footprint, the scatter goes to global memory
+            // frame-border tiles: corners still come from the staged footprint, the scatter goes to global memory
             const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
@@ -534,7 +521,17 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         }
 
         // ================= S: accumulation buffer -> grad_im with one TMA tensor reduce-add =================
-        if (fast && gsrcb) {
+        if (fast && gsrcb && !g_zero) {
+            __syncwarp();
+            {   // fixed point -> fp32 in place (exact scaling by a power of two), then the reduce-add sees ordinary floats
+                int4* zi = reinterpret_cast<int4*>(w_acc);
+                const int n16 = pitch * box_rows / 16;
+                for (int i = lane; i < n16; i += 32) {
+                    const int4 v = zi[i];
+                    reinterpret_cast<float4*>(zi)[i] = make_float4(__int2float_rn(v.x) * inv_scale, __int2float_rn(v.y) * inv_scale,
+                                                                   __int2float_rn(v.z) * inv_scale, __int2float_rn(v.w) * inv_scale);
+                }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
