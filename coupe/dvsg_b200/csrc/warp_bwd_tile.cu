@@ -21,11 +21,12 @@
 //              partial sums per lane are reduced across the warp with a 16-shuffle transpose
 //              reduction, accumulated per warp in shared memory, and issued as red.global once per
 //              warp at the end of its strip.
-// Frame-border tiles read their corners from the staged footprint too and scatter with red.global.add.f32 (the A4
-// sampler's clamped corners carry weights as large as the distance to the frame; the reduce-add box of the padded
-// samplers would start outside the tensor); tiles whose footprint fits no box, and tiles with non-finite gradients,
-// take a per-pixel path with global gathers and red.global.  grad_im is reproducible to the rounding of the fp32 adds
-// between tiles only.
+// TPS tiles at the frame border take the same path: a sample outside the frame has both clamped corners of an axis on
+// one pixel with exactly opposite weights, so its contributions cancel exactly and are not scattered at all.  The padded
+// samplers' border tiles read their corners from the staged footprint too and scatter with red.global.add.f32 (their
+// reduce-add box would start outside the tensor); tiles whose footprint fits no box, and tiles with non-finite
+// gradients, take a per-pixel path with global gathers and red.global.  grad_im is reproducible to the rounding of the
+// fp32 adds between tiles only.
 #include "tile_common.cuh"
 
 namespace dvsg {
@@ -123,93 +124,69 @@ __device__ __noinline__ void bwd_general_pixel(float xp, float yp, int W, int H,
     }
 }
 
-// Clamped variant (TPS tiles at the frame border): corners clamped first, weights FROM the clamped corners
-// (ThinPlateSpline.py:57-60, 81-88; the integer clamps pass no gradient).  The source pixels still come from the staged
-// footprint; the scatter goes straight to global memory as red.global.add.f32 (fire-and-forget, combined per sector
-// in L2): float atomics on shared memory are CAS loops and cost more than the whole per-pixel path.
-__device__ __forceinline__ float4 bwd_pair_clamped(const float2 xp, const float2 yp, const float ga0, const float ga1, const float ga2, const float gb0,
-                                                const float gb1, const float gb2, const unsigned char* __restrict__ sb, const int pitch, const int W,
-                                                const int H, float* __restrict__ gsrcb, const bool ok_a, const bool ok_b) {
-    const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
-    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-    const float2 fx = floor2_any(xp), fy = floor2_any(yp);
-    const float2 hx = __fadd2_rn(fx, one2), hy = __fadd2_rn(fy, one2);
-    const float2 x0f = f2(fminf(fmaxf(fx.x, 0.0f), wm1), fminf(fmaxf(fx.y, 0.0f), wm1));
-    const float2 x1f = f2(fminf(fmaxf(hx.x, 0.0f), wm1), fminf(fmaxf(hx.y, 0.0f), wm1));
-    const float2 y0f = f2(fminf(fmaxf(fy.x, 0.0f), hm1), fminf(fmaxf(fy.y, 0.0f), hm1));
-    const float2 y1f = f2(fminf(fmaxf(hy.x, 0.0f), hm1), fminf(fmaxf(hy.y, 0.0f), hm1));
-    const float2 ax1 = sub2(x1f, xp), ax0 = sub2(xp, x0f), ay1 = sub2(y1f, yp), ay0 = sub2(yp, y0f);
-    const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
-    const float2 tx0 = __ffma2_rn(x0f, twelve, m23), tx1 = __ffma2_rn(x1f, twelve, m23);
-    const float2 o00 = __ffma2_rn(y0f, pitchf, tx0), o01 = __ffma2_rn(y0f, pitchf, tx1);
-    const float2 o10 = __ffma2_rn(y1f, pitchf, tx0), o11 = __ffma2_rn(y1f, pitchf, tx1);
-    const float* p00[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o00.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o00.y) & 0x7fffff))};
-    const float* p01[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o01.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o01.y) & 0x7fffff))};
-    const float* p10[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o10.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o10.y) & 0x7fffff))};
-    const float* p11[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o11.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o11.y) & 0x7fffff))};
-    // exact fp32 integers below 2^22 -> int through the 2^23 bit pattern (no F2I on the XU pipe)
-    const int xa[2] = {__float_as_int(x0f.x + MAGIC23) & 0x7fffff, __float_as_int(x0f.y + MAGIC23) & 0x7fffff};
-    const int xb[2] = {__float_as_int(x1f.x + MAGIC23) & 0x7fffff, __float_as_int(x1f.y + MAGIC23) & 0x7fffff};
-    const int ya[2] = {__float_as_int(y0f.x + MAGIC23) & 0x7fffff, __float_as_int(y0f.y + MAGIC23) & 0x7fffff};
-    const int yb[2] = {__float_as_int(y1f.x + MAGIC23) & 0x7fffff, __float_as_int(y1f.y + MAGIC23) & 0x7fffff};
-    const bool ok[2] = {ok_a, ok_b};
-    const float gq[2][3] = {{ga0, ga1, ga2}, {gb0, gb1, gb2}};
-    float2 dx = f2dup(0.0f), dy = f2dup(0.0f);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float2 g = f2(gq[0][ch], gq[1][ch]);
-        const float2 i00 = f2(p00[0][ch], p00[1][ch]), i01 = f2(p01[0][ch], p01[1][ch]);
-        const float2 i10 = f2(p10[0][ch], p10[1][ch]), i11 = f2(p11[0][ch], p11[1][ch]);
-        const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
-        const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
-        dx = __ffma2_rn(g, ux, dx);
-        dy = __ffma2_rn(g, uy, dy);
-        if (gsrcb) {
-            const float2 c00 = __fmul2_rn(w00, g), c01 = __fmul2_rn(w01, g), c10 = __fmul2_rn(w10, g), c11 = __fmul2_rn(w11, g);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (!ok[h]) continue;      // duplicated edge pixels carry a zero gradient anyway
-                atomicAdd(gsrcb + ((size_t)ya[h] * W + xa[h]) * 3 + ch, h ? c00.y : c00.x);
-                atomicAdd(gsrcb + ((size_t)yb[h] * W + xa[h]) * 3 + ch, h ? c10.y : c10.x);
-                atomicAdd(gsrcb + ((size_t)ya[h] * W + xb[h]) * 3 + ch, h ? c01.y : c01.x);
-                atomicAdd(gsrcb + ((size_t)yb[h] * W + xb[h]) * 3 + ch, h ? c11.y : c11.x);
-            }
-        }
-    }
-    return make_float4(dx.x, dx.y, dy.x, dy.y);
-}
-
-// ---- one pixel pair (rows 2j, 2j+1 of the lane's column) of an interior staged tile ----------------------------------
+// ---- one pixel pair (rows 2j, 2j+1 of the lane's column) of a staged tile --------------------------------------------
 // Returns (d out/d x_pix of the two pixels, d out/d y_pix of the two pixels) and scatters w_k * grad_out.
 // The scatter accumulates in the warp's private buffer (= staging buffer + TSTAGE_BYTES, same layout) as 32-bit FIXED
 // POINT with the native integer shared-memory atomic (ATOMS.ADD; float atomics on shared memory are CAS loops on sm_100
-// and lose to everything else that was tried): no corner of an interior tile touches the frame border, so every weight
-// lies in [0, 1] and |contribution| <= max |grad_out| of the tile.  Contributions are scaled by a power of two chosen per
+// and lose to everything else that was tried): every scattered weight lies in [0, 1] (see CLAMP below for the frame
+// border), so |contribution| <= max |grad_out| of the tile.  Contributions are scaled by a power of two chosen per
 // tile from that maximum so that they carry 22 significant bits (rounded to nearest by the 1.5 * 2^23 trick: absolute
 // error <= 2^-23 of the tile's largest gradient, fp32's own resolution there); integer sums are exact, independent of
 // the order, and cannot overflow below 512 contributions per source pixel.  No ordering between lanes, rows or corner
 // classes is needed -- the previous scheme (plain read-modify-write rounds, one per row and corner class, duplicates
 // merged by shuffles) cost ~170 instructions per pair, 32 warp barriers per tile and a monotonicity test.
+// CLAMP (TPS tiles at the frame border): corners clamped first, weights FROM the clamped corners (ThinPlateSpline.py:57-60,
+// 81-88).  A sample outside the frame in x has x0 == x1 after the clamp, so its weights are exact negatives of each other
+// (x1f - x == -(x - x0f) in floating point) and its two contributions to that one pixel cancel EXACTLY -- the reference's
+// scatter leaves their rounding noise instead, in whatever order its segment sum runs.  Such samples are therefore not
+// scattered at all; the others have unclamped corners and weights in [0, 1] like those of an interior tile.
+template <bool CLAMP>
 __device__ __forceinline__ float4 bwd_pair_fixed(const float2 xp, const float2 yp, const float ga0, const float ga1, const float ga2, const float gb0,
                                                  const float gb1, const float gb2, const unsigned char* __restrict__ sb, const int pitch,
-                                                 const bool scatter, const float scale) {
+                                                 const bool scatter, const float scale, const float wm1, const float hm1) {
     const float2 one2 = f2dup(1.0f), m23 = f2dup(MAGIC23), pitchf = f2dup((float)pitch), twelve = f2dup(12.0f);
-    const float2 x0f = floor2_pos(xp), y0f = floor2_pos(yp);
-    const float2 ax1 = sub2(__fadd2_rn(x0f, one2), xp), ax0 = sub2(xp, x0f);
-    const float2 ay1 = sub2(__fadd2_rn(y0f, one2), yp), ay0 = sub2(yp, y0f);
+    float2 x0f, y0f, x1f, y1f;
+    bool inside[2] = {true, true};
+    if (!CLAMP) {
+        x0f = floor2_pos(xp); y0f = floor2_pos(yp);
+        x1f = __fadd2_rn(x0f, one2); y1f = __fadd2_rn(y0f, one2);
+    } else {
+        const float2 fx = floor2_any(xp), fy = floor2_any(yp);
+        const float2 hx = __fadd2_rn(fx, one2), hy = __fadd2_rn(fy, one2);
+        x0f = f2(fminf(fmaxf(fx.x, 0.0f), wm1), fminf(fmaxf(fx.y, 0.0f), wm1));
+        x1f = f2(fminf(fmaxf(hx.x, 0.0f), wm1), fminf(fmaxf(hx.y, 0.0f), wm1));
+        y0f = f2(fminf(fmaxf(fy.x, 0.0f), hm1), fminf(fmaxf(fy.y, 0.0f), hm1));
+        y1f = f2(fminf(fmaxf(hy.x, 0.0f), hm1), fminf(fmaxf(hy.y, 0.0f), hm1));
+        inside[0] = x0f.x == fx.x && x1f.x == hx.x && y0f.x == fy.x && y1f.x == hy.x;
+        inside[1] = x0f.y == fx.y && x1f.y == hx.y && y0f.y == fy.y && y1f.y == hy.y;
+    }
+    const float2 ax1 = sub2(x1f, xp), ax0 = sub2(xp, x0f), ay1 = sub2(y1f, yp), ay0 = sub2(yp, y0f);
     const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
-    const float2 o00 = __ffma2_rn(y0f, pitchf, __ffma2_rn(x0f, twelve, m23));
+    const float2 tx0 = __ffma2_rn(x0f, twelve, m23);
+    const float2 o00 = __ffma2_rn(y0f, pitchf, tx0);
     const float* p0[2] = {reinterpret_cast<const float*>(sb + (__float_as_int(o00.x) & 0x7fffff)), reinterpret_cast<const float*>(sb + (__float_as_int(o00.y) & 0x7fffff))};
     const float* p1[2] = {reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[0]) + pitch),
                           reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[1]) + pitch)};
+    // corner (x1, y0) / (x1, y1): 12 bytes after (x0, .) unless the clamp folded them onto it; likewise the row
+    int dxo[2] = {12, 12}, dyo[2] = {pitch, pitch};
+    if (CLAMP) {
+        dxo[0] = x1f.x == x0f.x ? 0 : 12; dxo[1] = x1f.y == x0f.y ? 0 : 12;
+        dyo[0] = y1f.x == y0f.x ? 0 : pitch; dyo[1] = y1f.y == y0f.y ? 0 : pitch;
+        p1[0] = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[0]) + dyo[0]);
+        p1[1] = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[1]) + dyo[1]);
+    }
+    const float* p0x[2] = {reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[0]) + dxo[0]),
+                           reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p0[1]) + dxo[1])};
+    const float* p1x[2] = {reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p1[0]) + dxo[0]),
+                           reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p1[1]) + dxo[1])};
     const float gq[2][3] = {{ga0, ga1, ga2}, {gb0, gb1, gb2}};
     const float2 sc2 = f2dup(scale), m15 = f2dup(MAGIC15);
     float2 dx = f2dup(0.0f), dy = f2dup(0.0f);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float2 g = f2(gq[0][ch], gq[1][ch]);
-        const float2 i00 = f2(p0[0][ch], p0[1][ch]), i01 = f2(p0[0][3 + ch], p0[1][3 + ch]);
-        const float2 i10 = f2(p1[0][ch], p1[1][ch]), i11 = f2(p1[0][3 + ch], p1[1][3 + ch]);
+        const float2 i00 = f2(p0[0][ch], p0[1][ch]), i01 = f2(p0x[0][ch], p0x[1][ch]);
+        const float2 i10 = f2(p1[0][ch], p1[1][ch]), i11 = f2(p1x[0][ch], p1x[1][ch]);
         const float2 ux = __ffma2_rn(ay0, sub2(i11, i10), __fmul2_rn(ay1, sub2(i01, i00)));
         const float2 uy = __ffma2_rn(ax0, sub2(i11, i01), __fmul2_rn(ax1, sub2(i10, i00)));
         dx = __ffma2_rn(g, ux, dx);
@@ -219,6 +196,7 @@ __device__ __forceinline__ float4 bwd_pair_fixed(const float2 xp, const float2 y
             const float2 q00 = __ffma2_rn(w00, gs, m15), q01 = __ffma2_rn(w01, gs, m15), q10 = __ffma2_rn(w10, gs, m15), q11 = __ffma2_rn(w11, gs, m15);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+                if (CLAMP && !inside[h]) continue;      // clamped sample: its paired contributions cancel exactly (see above)
                 int* a0 = const_cast<int*>(reinterpret_cast<const int*>(p0[h])) + TSTAGE_BYTES / 4 + ch;
                 int* a1 = const_cast<int*>(reinterpret_cast<const int*>(p1[h])) + TSTAGE_BYTES / 4 + ch;
                 atomicAdd(a0, __float_as_int(h ? q00.y : q00.x) - 0x4B400000);
@@ -424,10 +402,8 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         gmax_bits = __reduce_max_sync(0xffffffffu, gmax_bits);
         const int gexp = min(max((int)(gmax_bits >> 23), 40), 254);
         const bool g_finite = (gmax_bits >> 23) < 255, g_zero = (gmax_bits >> 23) < 40;      // |g| < 2^-87 everywhere: nothing to scatter
-        // interior tiles accumulate in shared memory (fixed point); frame-border tiles scatter with red.global: the A4 sampler's
-        // clamped corners carry weights as large as the distance to the frame (outside the fixed-point range; they cancel in
-        // pairs), and the reduce-add box of the padded samplers would start outside the tensor
-        const bool fast = staged && g_finite && interior;
+        // the padded samplers scatter their frame-border tiles with red.global: the reduce-add box would start outside the tensor
+        const bool fast = staged && g_finite && (interior || MODE == TMODE_TPS);
         const float scale = __int_as_float((275 - gexp) << 23), inv_scale = __int_as_float((gexp - 21) << 23);
         if (!g_finite) staged = false;              // inf / NaN gradients: per-pixel path (float red.global keeps their semantics)
 
@@ -458,21 +434,22 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
             const bool sc = gsrcb != nullptr && !g_zero;
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                const float4 d = bwd_pair_fixed(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
-                                                sb, pitch, sc, scale);
+                float4 d;
+                if (MODE != TMODE_TPS || interior)
+                    d = bwd_pair_fixed<false>(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
+                                              sb, pitch, sc, scale, 0.0f, 0.0f);
+                else
+                    d = bwd_pair_fixed<true>(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
+                                             sb, pitch, sc, scale, (float)(W - 1), (float)(H - 1));
                 GX[j] = f2(d.x, d.y); GY[j] = f2(d.z, d.w);
             }
-        } else if (staged) {
-            // frame-border tiles: corners still come from the staged footprint, the scatter goes to global memory
-            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
+        } else if (MODE != TMODE_TPS && staged) {
+            // frame-border tiles of the padded samplers: corners still come from the staged footprint, the scatter goes to global memory
+            const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (pitch + 12);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                const bool ok_a = col_ok && row0 + 2 * j < oh, ok_b = col_ok && row0 + 2 * j + 1 < oh;
-                const float4 d = MODE == TMODE_TPS
-                    ? bwd_pair_clamped(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
-                                       sb, pitch, W, H, gsrcb, ok_a, ok_b)
-                    : bwd_pair_padded(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
-                                      sb, pitch, W, H, gsrcb, ok_a, ok_b);
+                const float4 d = bwd_pair_padded(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
+                                                 sb, pitch, W, H, gsrcb, col_ok && row0 + 2 * j < oh, col_ok && row0 + 2 * j + 1 < oh);
                 GX[j] = f2(d.x, d.y); GY[j] = f2(d.z, d.w);
             }
         } else {
