@@ -100,6 +100,26 @@ __device__ __forceinline__ int t_floor_i32(float f) {
     return fabsf(f) < 2147483648.0f ? v : (int)0x80000000;
 }
 
+// ---- tiles per CTA (host) ------------------------------------------------------------------------------------------
+// A strip of n_tx tiles is cut into CTAs of seg_len tiles (TNW warps; tile t of a CTA goes to warp t % TNW).  A CTA lasts
+// its prologue (tables, barrier, launch: cta_cost, in units of one tile time) plus ceil(seg_len / TNW) tile rounds; the
+// launch lasts (CTAs / slots) of those plus a tail that grows with the CTA's duration (0.4 of it fits the measurements).
+// The cut with the smallest product wins.  Measured: backward kernel at the 32 x 288 x 512 training shape, 3 CTAs of
+// 6 / 6 / 4 tiles per strip (two half-empty rounds each) 127 us, one CTA of 16 tiles 107 us; forward kernel there 45.4 ->
+// 40.4 us; flow warp 16 x 1080p, 60 / 30 / 20 tiles per CTA: 178.7 / 172.4 / 168.2 us.
+static inline int tile_pick_seg_len(long long strips, int n_tx, int slots, double cta_cost, const char* env_override) {
+    if (const char* e = getenv(env_override)) return max(atoi(e), 1);      // experiments only
+    const int max_segs = max(n_tx / TNW, 1);
+    int best_len = n_tx;
+    double best = 1e300;
+    for (int s = 1; s <= max_segs; ++s) {
+        const int len = (n_tx + s - 1) / s, segs = (n_tx + len - 1) / len;
+        const double cost = ((double)(strips * segs) / slots + 0.4) * (cta_cost + (double)((len + TNW - 1) / TNW));
+        if (cost < best * (1.0 - 1e-9)) { best = cost; best_len = len; }
+    }
+    return best_len;
+}
+
 // ---- TPS tables shared by the forward and backward tile kernels (identical coordinates in both) -----------------------
 // Per-strip tables of a tile kernel: s_lin[0..5] = affine rows (constant, x, y) of x_s and y_s, records of the pn8
 // (padded) control points for the TR rows starting at row0.  Called by the whole CTA (>= 2 warps) before its barrier.

@@ -465,32 +465,56 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         }
 
         // ================= chain to the caller's coordinates, write grad x / y / flow =================
+        // (per-tile base pointers + 32-bit row offsets: the flat 64-bit index per pixel and array cost 39 instructions per 32 px)
+        {
+            const int r_last = rows_ok - 1;
+            if (MODE == TMODE_TPS) {
+                // block-uniform bases + 32-bit per-lane offsets; rows / columns past the edge alias the edge pixel, so the
+                // loads need no guard (their values are zeroed below)
+                const size_t ubase = ((size_t)b * oh + row0) * ow;
+                const float* gxi = p.grad_x_in ? p.grad_x_in + ubase : nullptr;
+                const float* gyi = p.grad_x_in ? p.grad_y_in + ubase : nullptr;
+                float* gxo = p.grad_x ? p.grad_x + ubase : nullptr;
+                float* gyo = p.grad_x ? p.grad_y + ubase : nullptr;
+                const float2 wf = f2dup((float)W), hf = f2dup((float)H), half2 = f2dup(0.5f);
 #pragma unroll
-        for (int j = 0; j < TR / 2; ++j) {
+                for (int j = 0; j < TR / 2; ++j) {
+                    const unsigned oa = (unsigned)(min(2 * j, r_last) * ow + col), ob = (unsigned)(min(2 * j + 1, r_last) * ow + col);
+                    const bool oka = col_ok && 2 * j < rows_ok, okb = col_ok && 2 * j + 1 < rows_ok;
+                    float2 gx = __fmul2_rn(__fmul2_rn(GX[j], wf), half2);      // x_pix = (x+1)*W/2
+                    float2 gy = __fmul2_rn(__fmul2_rn(GY[j], hf), half2);
+                    if (gxi) {
+                        gx = __fadd2_rn(gx, f2(__ldg(gxi + oa), __ldg(gxi + ob)));
+                        gy = __fadd2_rn(gy, f2(__ldg(gyi + oa), __ldg(gyi + ob)));
+                    }
+                    if (!oka) { gx.x = 0.0f; gy.x = 0.0f; }
+                    if (!okb) { gx.y = 0.0f; gy.y = 0.0f; }
+                    if (gxo) {
+                        if (oka) { gxo[oa] = gx.x; gyo[oa] = gy.x; }
+                        if (okb) { gxo[ob] = gx.y; gyo[ob] = gy.y; }
+                    }
+                    GX[j] = gx; GY[j] = gy;
+                }
+            } else {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int q = 2 * j + h;
-                const bool ok = col_ok && q < rows_ok;
-                const size_t opix = opix0 + (size_t)(min(q, rows_ok - 1) * ow);
-                float gx = h ? GX[j].y : GX[j].x, gy = h ? GY[j].y : GY[j].x;
-                if (MODE == TMODE_TPS) {
-                    gx = gx * (float)W * 0.5f;                     // x_pix = (x+1)*W/2
-                    gy = gy * (float)H * 0.5f;
-                    if (ok && p.grad_x_in) { gx += __ldg(p.grad_x_in + opix); gy += __ldg(p.grad_y_in + opix); }
-                    if (!ok) { gx = 0.0f; gy = 0.0f; }
-                    if (ok && p.grad_x) { p.grad_x[opix] = gx; p.grad_y[opix] = gy; }
-                    if (h) { GX[j].y = gx; GY[j].y = gy; } else { GX[j].x = gx; GY[j].x = gy; }
-                } else {
-                    gx = (clipmask >> q) & 1u ? gx : 0.0f;
-                    gy = (clipmask >> (8 + q)) & 1u ? gy : 0.0f;
-                    if (ok) {
-                        if (MODE == TMODE_GIVEN) {
-                            if (p.grad_x) {
-                                p.grad_x[opix] = gx * ((float)W - 1.0f) * 0.5f;   // x_pix = (x+1)/2*(W-1)
-                                p.grad_y[opix] = gy * ((float)H - 1.0f) * 0.5f;
+                for (int j = 0; j < TR / 2; ++j) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int q = 2 * j + h;
+                        const bool ok = col_ok && q < rows_ok;
+                        const size_t opix = opix0 + (size_t)(min(q, rows_ok - 1) * ow);
+                        float gx = h ? GX[j].y : GX[j].x, gy = h ? GY[j].y : GY[j].x;
+                        gx = (clipmask >> q) & 1u ? gx : 0.0f;
+                        gy = (clipmask >> (8 + q)) & 1u ? gy : 0.0f;
+                        if (ok) {
+                            if (MODE == TMODE_GIVEN) {
+                                if (p.grad_x) {
+                                    p.grad_x[opix] = gx * ((float)W - 1.0f) * 0.5f;   // x_pix = (x+1)/2*(W-1)
+                                    p.grad_y[opix] = gy * ((float)H - 1.0f) * 0.5f;
+                                }
+                            } else if (p.grad_flow) {
+                                reinterpret_cast<float2*>(p.grad_flow)[opix] = make_float2(gx, gy);
                             }
-                        } else if (p.grad_flow) {
-                            reinterpret_cast<float2*>(p.grad_flow)[opix] = make_float2(gx, gy);
                         }
                     }
                 }
@@ -593,10 +617,7 @@ static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
     p.n_tx = (p.ow + TC - 1) / TC;
     p.n_ty = (p.oh + TR - 1) / TR;
     const long long strips = (long long)p.B * p.n_ty;
-    const int target = 148 * 4 * 4;
-    int segs = 1;
-    if (strips < target) segs = (int)min((long long)max(p.n_tx / TNW, 1), (target + strips - 1) / strips);
-    p.seg_len = (p.n_tx + segs - 1) / segs;
+    p.seg_len = tile_pick_seg_len(strips, p.n_tx, 148 * 4, 0.5, "DVSG_BWD_SEGLEN");
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "bwd tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
     BwdTileMaps maps;

@@ -420,7 +420,6 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
 
 // ---- host side ---------------------------------------------------------------------------------
 static float tile_lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
-static int g_tile_target_ctas = 148 * 5 * 4;
 static int g_tile_dbg = 0;
 // staging boxes of the forward kernel (floats x rows): box 0 = bw0 x bh0, box 1 = bw0 x bh1, box 2 = bw2 x bh2.
 // TPS / homography (smooth maps): 128 x 10 (5 KB) covers 60 % of the tiles of a +-0.1 TPS warp at 720p; 128 x 15 and
@@ -458,10 +457,8 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     p.n_tx = (p.ow + TC - 1) / TC;
     p.n_ty = (p.oh + TR - 1) / TR;
     const long long strips = (long long)p.B * p.n_ty;
-    // several CTAs per strip when the launch would otherwise be a few waves only; each warp keeps >= 1 tile
-    int segs = 1;
-    if (strips < g_tile_target_ctas) segs = (int)min((long long)max(p.n_tx / TNW, 1), (g_tile_target_ctas + strips - 1) / strips);
-    p.seg_len = (p.n_tx + segs - 1) / segs;
+    // tiles per CTA (tile_pick_seg_len): the TPS prologue builds the per-strip tables, the field samplers have none
+    p.seg_len = tile_pick_seg_len(strips, p.n_tx, 148 * 5, MODE == TMODE_TPS ? 0.75 : 0.2, "DVSG_FWD_SEGLEN");
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
     TileMaps maps;
@@ -530,7 +527,7 @@ int tile_homog(const float* im, const float* theta, int projective, float* out, 
 
 void tile_set_tuning(int stage_bytes, int target_ctas, int minb) {
     if (stage_bytes >= 0 && stage_bytes < 16) g_tile_dbg = stage_bytes;      // debug mask (the staging buffer is sized by the largest TMA box)
-    if (target_ctas > 0) g_tile_target_ctas = target_ctas;
+    (void)target_ctas;      // superseded by tile_pick_seg_len
     (void)minb;
 }
 

@@ -68,11 +68,6 @@ def main():
                 rec('tps720 4x4 amp=%.2f tile, no L2 prefetch of per-pixel tiles' % amp, ms, px, 24)
                 lib.dvsg_set_tile_tuning(0, -1, -1)
             if amp == 0.2:
-                for tc in (148 * 5 * 4, 148 * 5 * 24):
-                    lib.dvsg_set_tile_tuning(-1, tc, -1)
-                    ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False))
-                    rec('tps720 4x4 tile target_ctas=%d' % tc, ms, px, 24)
-                lib.dvsg_set_tile_tuning(-1, 148 * 5 * 4, -1)
                 ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True))
                 rec('tps720 4x4 tile +xy', ms, px, 32)
                 ms = timeit(lambda: ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=False, want_mask=True))
