@@ -432,16 +432,27 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         if (fast) {
             const unsigned char* sb = w_stage - (fy_lo * pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : pitch + 12);
             const bool sc = gsrcb != nullptr && !g_zero;
+            // two rounds of two pairs (the pair bodies are ~200 instructions each: four inlined copies per variant put the
+            // kernel's hot path past the instruction cache); the register arrays rotate between the rounds
+            const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+            GX[2] = GX[3] = GY[2] = GY[3] = f2dup(0.0f);
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it) {
+                float4 d0, d1;
+                if (MODE != TMODE_TPS || interior) {
+                    d0 = bwd_pair_fixed<false>(XP[0], YP[0], gq[0][0], gq[0][1], gq[0][2], gq[1][0], gq[1][1], gq[1][2], sb, pitch, sc, scale, 0.0f, 0.0f);
+                    d1 = bwd_pair_fixed<false>(XP[1], YP[1], gq[2][0], gq[2][1], gq[2][2], gq[3][0], gq[3][1], gq[3][2], sb, pitch, sc, scale, 0.0f, 0.0f);
+                } else {
+                    d0 = bwd_pair_fixed<true>(XP[0], YP[0], gq[0][0], gq[0][1], gq[0][2], gq[1][0], gq[1][1], gq[1][2], sb, pitch, sc, scale, wm1, hm1);
+                    d1 = bwd_pair_fixed<true>(XP[1], YP[1], gq[2][0], gq[2][1], gq[2][2], gq[3][0], gq[3][1], gq[3][2], sb, pitch, sc, scale, wm1, hm1);
+                }
+                GX[0] = GX[2]; GX[1] = GX[3]; GY[0] = GY[2]; GY[1] = GY[3];
+                GX[2] = f2(d0.x, d0.y); GY[2] = f2(d0.z, d0.w); GX[3] = f2(d1.x, d1.y); GY[3] = f2(d1.z, d1.w);
+                XP[0] = XP[2]; XP[1] = XP[3]; YP[0] = YP[2]; YP[1] = YP[3];
 #pragma unroll
-            for (int j = 0; j < TR / 2; ++j) {
-                float4 d;
-                if (MODE != TMODE_TPS || interior)
-                    d = bwd_pair_fixed<false>(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
-                                              sb, pitch, sc, scale, 0.0f, 0.0f);
-                else
-                    d = bwd_pair_fixed<true>(XP[j], YP[j], gq[2 * j][0], gq[2 * j][1], gq[2 * j][2], gq[2 * j + 1][0], gq[2 * j + 1][1], gq[2 * j + 1][2],
-                                             sb, pitch, sc, scale, (float)(W - 1), (float)(H - 1));
-                GX[j] = f2(d.x, d.y); GY[j] = f2(d.z, d.w);
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) gq[q][ch] = gq[q + 4][ch];
             }
         } else if (MODE != TMODE_TPS && staged) {
             // frame-border tiles of the padded samplers: corners still come from the staged footprint, the scatter goes to global memory
@@ -617,7 +628,9 @@ static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
     p.n_tx = (p.ow + TC - 1) / TC;
     p.n_ty = (p.oh + TR - 1) / TR;
     const long long strips = (long long)p.B * p.n_ty;
-    p.seg_len = tile_pick_seg_len(strips, p.n_tx, 148 * 4, 0.5, "DVSG_BWD_SEGLEN");
+    // the TPS prologue builds the per-strip tables; the field samplers have none and prefer short CTAs (tf_warp backward,
+    // 32 x 288 x 512: 16 / 8 / 4 tiles per CTA 156 / 144 / 138 us; 16 x 720p: 40 / 20 / 4 tiles 220 / 199 / 189 us)
+    p.seg_len = tile_pick_seg_len(strips, p.n_tx, 148 * 4, MODE == TMODE_TPS ? 0.5 : 0.05, "DVSG_BWD_SEGLEN");
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "bwd tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
     BwdTileMaps maps;
