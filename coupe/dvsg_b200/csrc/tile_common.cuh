@@ -103,7 +103,8 @@ __device__ __forceinline__ int t_floor_i32(float f) {
 // ---- tiles per CTA (host) ------------------------------------------------------------------------------------------
 // A strip of n_tx tiles is cut into CTAs of seg_len tiles (TNW warps; tile t of a CTA goes to warp t % TNW).  A CTA lasts
 // its prologue (tables, barrier, launch: cta_cost, in units of one tile time) plus ceil(seg_len / TNW) tile rounds; the
-// launch lasts (CTAs / slots) of those plus a tail that grows with the CTA's duration (0.4 of it fits the measurements).
+// launch lasts (CTAs / slots) of those (whole waves when there are fewer than four) plus a tail that grows with the
+// CTA's duration (0.4 of it fits the measurements).
 // The cut with the smallest product wins.  Measured: backward kernel at the 32 x 288 x 512 training shape, 3 CTAs of
 // 6 / 6 / 4 tiles per strip (two half-empty rounds each) 127 us, one CTA of 16 tiles 107 us; forward kernel there 45.4 ->
 // 40.4 us; flow warp 16 x 1080p, 60 / 30 / 20 tiles per CTA: 178.7 / 172.4 / 168.2 us.
@@ -114,7 +115,9 @@ static inline int tile_pick_seg_len(long long strips, int n_tx, int slots, doubl
     double best = 1e300;
     for (int s = 1; s <= max_segs; ++s) {
         const int len = (n_tx + s - 1) / s, segs = (n_tx + len - 1) / len;
-        const double cost = ((double)(strips * segs) / slots + 0.4) * (cta_cost + (double)((len + TNW - 1) / TNW));
+        double waves = (double)(strips * segs) / slots;
+        if (waves < 4.0) waves = ceil(waves);       // a launch of a few waves is quantised; longer ones even out
+        const double cost = (waves + 0.4) * (cta_cost + (double)((len + TNW - 1) / TNW));
         if (cost < best * (1.0 - 1e-9)) { best = cost; best_len = len; }
     }
     return best_len;
