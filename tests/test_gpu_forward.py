@@ -500,3 +500,42 @@ def test_online_warper_equals_the_dropin():
         assert torch.equal(warper.warp(U, vec), ref)
     with pytest.raises(ValueError):
         warper.warp(U[:, :10], vec)
+
+
+def test_results_do_not_depend_on_the_tiles_per_cta_cut(monkeypatch):
+    """The tile kernels cut every strip of tiles into CTAs with a cost model (tile_pick_seg_len); the cut is
+    scheduling only.  Forward outputs are bit-identical for any cut; the backward's grad_image goes through
+    per-tile TMA reduce-adds, so only its fp32 summation order may change."""
+    from coupe.dvsg_b200 import ops
+    torch.manual_seed(5)
+    B, H, W = 3, 288, 512
+    U = torch.rand((B, H, W, 3), device=DEV)
+    coord = cu(tiled_mesh(4, 4, 1)[0]).unsqueeze(0).expand(B, -1, -1)
+    vec = (torch.rand((B, 16, 2), device=DEV) - 0.5) * 0.2
+    T = ops.tps_solve(coord, coord + vec)
+    g = torch.randn((B, H, W, 3), device=DEV)
+    flow = cu(smooth_flow(np.random.default_rng(3), B, H, W).astype(np.float32))
+    from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+
+    def run():
+        f = ops.tps_warp_fwd(U, coord, T, (H, W), want_grid=True, want_mask=True)
+        b = ops.tps_warp_bwd(U, coord, T, (H, W), g, None, None, need_grad_U=True, want_grid_grad=True)
+        w = tf_warp(U, flow, H, W)
+        torch.cuda.synchronize()
+        return f, b, w
+
+    monkeypatch.delenv('DVSG_FWD_SEGLEN', raising=False)
+    monkeypatch.delenv('DVSG_BWD_SEGLEN', raising=False)
+    f0, b0, w0 = run()
+    for seg in ('1', '4', '7', '16'):
+        monkeypatch.setenv('DVSG_FWD_SEGLEN', seg)
+        monkeypatch.setenv('DVSG_BWD_SEGLEN', seg)
+        f1, b1, w1 = run()
+        for p, q in zip(f0, f1):
+            assert torch.equal(p, q), seg
+        assert torch.equal(w0, w1), seg
+        gU0, gT0, gx0, gy0 = b0
+        gU1, gT1, gx1, gy1 = b1
+        assert torch.equal(gx0, gx1) and torch.equal(gy0, gy1), seg
+        assert float((gU0 - gU1).abs().max()) <= 2e-5 * float(gU0.abs().max()), seg
+        assert float((gT0 - gT1).abs().max()) <= 2e-5 * float(gT0.abs().max()), seg
