@@ -390,9 +390,8 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         const int pitch = (box == 2 ? p.bw[2] : p.bw[0]) * 4;
         const int box_rows = box == 0 ? p.bh[0] : (box == 1 ? p.bh[1] : p.bh[2]);
         bool staged = box >= 0 && all_sane && (long long)(fy_hi + 3) * pitch + (long long)(fx_hi + 3) * 12 < (1LL << 22);
-        // Two staged variants.  fast: no corner touches the frame border and the source columns of every row do not
-        // decrease and never repeat more than twice (x scale >= 0.5, no fold) -- the read-modify-write rounds below.
-        // Otherwise (TPS only): clamped corners and shared-memory atomics into the same accumulation buffer.
+        // Staged tiles accumulate grad_im in the warp's shared buffer in fixed point ("fast"; TPS border tiles with the
+        // clamped-corner variant), except the padded samplers' border tiles, which scatter with red.global.
         // per-tile fixed-point scale of the scatter: 2^(21 - floor(log2 max|grad_out|)), from the exponent bits of the maximum
         unsigned gmax_bits = 0;
 #pragma unroll
