@@ -54,6 +54,7 @@ PROTOTYPES = {
 TUNING_PROTOTYPES = {
     'dvsg_set_bwd_tuning': (c_int, [c_int]),
     'dvsg_set_tile_tuning': (c_int, [c_int, c_int, c_int]),
+    'dvsg_debug_seg_len': (c_int, [c_longlong, c_int, c_int, ctypes.c_double]),
 }
 
 _lib = None

@@ -532,3 +532,9 @@ void tile_set_tuning(int stage_bytes, int target_ctas, int minb) {
 }
 
 }  // namespace dvsg
+
+// tuning ABI (exported, not in the public header): the tiles-per-CTA cut of a launch, so that the host logic is testable
+// without a device
+extern "C" int dvsg_debug_seg_len(long long strips, int n_tx, int slots, double cta_cost) {
+    return dvsg::tile_pick_seg_len(strips, n_tx, slots, cta_cost, "DVSG_DEBUG_SEGLEN");
+}

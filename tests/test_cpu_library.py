@@ -143,3 +143,23 @@ def test_two_rank_gloo_sharding_and_timing_reduce():
     assert [(r[1], r[2]) for r in res] == [(0, 6), (6, 11)]
     assert sum(r[3] for r in res) == sum(range(11))     # host-side gather of per-rank checksums
     assert all(r[4] == 11.0 for r in res)               # max over ranks seen by every rank
+
+
+def test_tiles_per_cta_cut_of_the_tile_kernels(built_lib):
+    """Host logic of the tile kernels (tile_common.cuh: tile_pick_seg_len): a strip of n_tx tiles is cut into CTAs of
+    seg_len tiles.  Pure host code, so it is checked here without a device: bounds, and the cuts the measurements in
+    profiles/README.md were taken with."""
+    f = built_lib.dvsg_debug_seg_len
+    fwd, bwd = 148 * 5, 148 * 4
+    for strips in (1, 36, 1152, 5760, 100000):
+        for n_tx in (1, 3, 4, 5, 16, 40, 60, 120, 1000):
+            for slots, cost in ((fwd, 0.75), (fwd, 0.2), (bwd, 0.5), (bwd, 0.05)):
+                n = f(strips, n_tx, slots, cost)
+                assert 1 <= n <= n_tx
+                assert n == n_tx or n >= 4, 'every warp of a CTA keeps at least one tile'
+    assert f(32 * 36, 16, fwd, 0.75) == 16      # training shape: one CTA per strip (forward and TPS backward)
+    assert f(32 * 36, 16, bwd, 0.5) == 16
+    assert f(32 * 36, 16, bwd, 0.05) == 4       # tf_warp backward at the training shape: short CTAs
+    assert f(36, 16, fwd, 0.75) == 4            # one 288x512 frame: as many CTAs as there are warps' worth of tiles
+    assert f(64 * 90, 40, fwd, 0.75) == 40      # cfg2: enough strips, one CTA each
+    assert f(16 * 135, 60, fwd, 0.2) == 20      # cfg4 flow warp: three CTAs per strip
