@@ -539,3 +539,28 @@ def test_results_do_not_depend_on_the_tiles_per_cta_cut(monkeypatch):
         assert torch.equal(gx0, gx1) and torch.equal(gy0, gy1), seg
         assert float((gU0 - gU1).abs().max()) <= 2e-5 * float(gU0.abs().max()), seg
         assert float((gT0 - gT1).abs().max()) <= 2e-5 * float(gT0.abs().max()), seg
+
+
+def test_tps_forward_vs_oracle_at_the_north_star_shape():
+    """One frame at the headline shape (1080 x 1920 x 3, 4x4 mesh, offsets +-0.1; BASELINE north_star) against the
+    oracle itself, not only through size-independent properties: coordinates <= 2e-5, pixels <= 1e-4 where both
+    coordinate sets pick the same corners, sampler stage bit-exact on the kernel's own coordinates."""
+    b, h, w, c, m = 1, 1080, 1920, 3, 4
+    rng = np.random.default_rng(1080)
+    # the coordinate noise (2e-6 normalised) is 4x larger in pixels than at 288 x 512: periods >= 64 px keep the pixel bar meaningful
+    u = smooth_image(rng, b, h, w, c, period=64.0)
+    coord = tiled_mesh(m, m, b)
+    vec = rng.uniform(-0.1, 0.1, coord.shape).astype(np.float32)
+    out, x, y, T = run_tps(u, coord, vec, (h, w), 1, 0)
+    r_out, r_x, r_y = O.thin_plate_spline(u, coord, vec, (h, w))
+    ex = max(np.abs(x - r_x).max(), np.abs(y - r_y).max())
+    # all four clamped corners must agree: at x_pix = 0- / 0+ the low corner is pixel 0 on both sides (clamped from -1 or
+    # not) while the high one flips between 0 (weights cancel) and 1 (interpolation)
+    _, _, x0, x1, y0, y1 = O.tps_sample_indices(x, y, h, w)
+    _, _, rx0, rx1, ry0, ry1 = O.tps_sample_indices(r_x, r_y, h, w)
+    same = ((x0 == rx0) & (y0 == ry0) & (x1 == rx1) & (y1 == ry1)).reshape(b, h, w)
+    flips = 1.0 - float(same.mean())
+    eo_same = np.abs(out - r_out)[same].max()
+    print('1080p coord err %.2e  pixel err %.2e (same corners)  corner flips %.4f%%' % (ex, eo_same, 100 * flips))
+    assert ex <= 2e-5 and eo_same <= 1e-4 and flips <= 5e-3
+    np.testing.assert_array_equal(out, O.tps_interpolate(u, x, y, h, w).reshape(out.shape))
