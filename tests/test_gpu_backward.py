@@ -82,7 +82,8 @@ def test_tps_autograd_dropin():
     assert torch.isfinite(V2.grad).all() and V2.grad.abs().max() > 0
 
 
-@pytest.mark.parametrize('shape', [(2, 96, 128, 3, 4), (1, 45, 50, 3, 5), (1, 32, 48, 2, 4)])
+# (2, 288, 512, 3, 4): the training shape of BASELINE configs[2] (two frames of it: the oracle's backward is NumPy)
+@pytest.mark.parametrize('shape', [(2, 96, 128, 3, 4), (1, 45, 50, 3, 5), (1, 32, 48, 2, 4), (2, 288, 512, 3, 4)])
 def test_tps_backward_vs_oracle_seeded(shape):
     from coupe.dvsg_b200 import ops
     b, h, w, c, m = shape

@@ -160,14 +160,14 @@ def test_tps_forward_vs_oracle_seeded(shape, flags):
     ex = max(np.abs(x - r_x).max(), np.abs(y - r_y).max())
     eo = np.abs(out - r_out).max()
     xp, yp, x0, x1, y0, y1 = O.tps_sample_indices(x, y, h, w)
-    _, _, rx0, _, ry0, _ = O.tps_sample_indices(r_x, r_y, h, w)
-    flips = float(np.mean((x0 != rx0) | (y0 != ry0)))
+    _, _, rx0, rx1, ry0, ry1 = O.tps_sample_indices(r_x, r_y, h, w)
+    flips = float(np.mean((x0 != rx0) | (y0 != ry0) | (x1 != rx1) | (y1 != ry1)))
     # The reference sampler is DISCONTINUOUS at the edge of its support: crossing x_pix = W-1 (or 0)
     # switches from "interpolate pixels W-2, W-1" to "clamped corners whose weights cancel" (~0).
     # A pixel whose coordinate differs by one fp32 ulp can land on either side, so pixels whose
     # integer corner differs between the two coordinate sets are excluded from the value tolerance
     # (they are still covered by the bit-exact sampler check below, on the kernel's own x, y).
-    same = ((x0 == rx0) & (y0 == ry0)).reshape(b, h, w)
+    same = ((x0 == rx0) & (y0 == ry0) & (x1 == rx1) & (y1 == ry1)).reshape(b, h, w)
     eo_same = np.abs(out - r_out)[same].max()
     print('%s coord err %.2e  pixel err %.2e (all) %.2e (same corners)  corner flips vs oracle coords %.4f%%' %
           (shape, ex, eo, eo_same, 100 * flips))
