@@ -348,6 +348,12 @@ def test_tf_warp_1080p_properties():
     assert rc == 0
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+    # and against the oracle itself at this size: one frame, smooth flow with jitter, bit-exact
+    rng = np.random.default_rng(4)
+    fl = smooth_flow(rng, 1, H, W).astype(np.float32)
+    u = im[:1].cpu().numpy()
+    got = tf_warp(im[:1].contiguous(), cu(fl), H, W).cpu().numpy()
+    np.testing.assert_array_equal(got, O.tf_warp(u, fl, H, W))
 
 
 def test_st_meshgrid_and_transformers_vs_golden():
