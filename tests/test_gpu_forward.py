@@ -570,3 +570,26 @@ def test_tps_forward_vs_oracle_at_the_north_star_shape():
     print('1080p coord err %.2e  pixel err %.2e (same corners)  corner flips %.4f%%' % (ex, eo_same, 100 * flips))
     assert ex <= 2e-5 and eo_same <= 1e-4 and flips <= 5e-3
     np.testing.assert_array_equal(out, O.tps_interpolate(u, x, y, h, w).reshape(out.shape))
+
+
+@pytest.mark.parametrize('m,size', [(16, (135, 240)), (8, (90, 160))])
+def test_large_mesh_grid_stage_vs_oracle_on_the_kernels_coefficients(m, size):
+    """Large meshes (16x16 = BASELINE configs[4], N = 259): the solve is ill-conditioned, so the grid stage
+    is compared on its own -- the oracle's `_transform` arithmetic (ThinPlateSpline.py:92-133) fed with the KERNEL's
+    coefficients T.  Bar: the kernel's coordinates are no farther from the fp64 evaluation of that stage than twice the
+    fp32 oracle's own distance to it (sequential fp32 sum of N terms), and <= 2e-4 absolute."""
+    from coupe.dvsg_b200 import ops
+    h, w = size
+    rng = np.random.default_rng(m)
+    coord = tiled_mesh(m, m, 1)
+    vec = rng.uniform(-0.02, 0.02, coord.shape).astype(np.float32)
+    U = cu(smooth_image(rng, 1, h, w, 3))
+    T = ops.tps_solve(cu(coord), cu(coord + vec))
+    _, x, y, _ = ops.tps_warp_fwd(U, cu(coord), T, (h, w), want_grid=True)
+    x, y, Tn = x.cpu().numpy(), y.cpu().numpy(), T.cpu().numpy()
+    x32, y32 = O.tps_grid(Tn, coord, h, w)
+    x64, y64 = O.tps_grid(Tn.astype(np.float64), coord.astype(np.float64), h, w, dtype=np.float64)
+    e_k = max(np.abs(x - x64.reshape(-1)).max(), np.abs(y - y64.reshape(-1)).max())
+    e_o = max(np.abs(x32.reshape(-1) - x64.reshape(-1)).max(), np.abs(y32.reshape(-1) - y64.reshape(-1)).max())
+    print('mesh %dx%d grid stage: |kernel - fp64| %.2e, |fp32 oracle - fp64| %.2e, max |T| %.1f' % (m, m, e_k, e_o, np.abs(Tn).max()))
+    assert e_k <= max(2.0 * e_o, 2e-5) and e_k <= 2e-4
