@@ -2,10 +2,11 @@
 import csv, collections, subprocess, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r01d'
-PX = {'cfg2': 64 * 720 * 1280, 'hd1080': 64 * 1080 * 1920, 'cfg4': 16 * 1080 * 1920, 'cfg3': 32 * 288 * 512}
+PX = {'cfg2': 64 * 720 * 1280, 'hd1080': 64 * 1080 * 1920, 'cfg4': 16 * 1080 * 1920, 'cfg3': 32 * 288 * 512, 'cfg5': 16 * 2160 * 3840, 'mesh5': 64 * 720 * 1280}
 TITLE = {'cfg2': 'warp_fwd_tile_kernel<TMODE_TPS> at cfg2 (64 x 720p, 4x4 mesh)', 'hd1080': 'warp_fwd_tile_kernel<TMODE_TPS> at the north-star shape (64 x 1080p, 4x4 mesh)', 'cfg4': 'warp_fwd_tile_kernel<TMODE_FLOW> at cfg4 (16 x 1080p + flow)',
-         'cfg3': 'warp_bwd_tile_kernel<TMODE_TPS> at cfg3 (32 x 288x512, 4x4 mesh, grads wrt image, grid and T)'}
-for wl in ('cfg2', 'hd1080', 'cfg4', 'cfg3'):
+         'cfg3': 'warp_bwd_tile_kernel<TMODE_TPS> at cfg3 (32 x 288x512, 4x4 mesh, grads wrt image, grid and T)',
+         'cfg5': 'warp_fwd_tile_kernel<TMODE_TPS, G = 0> at cfg5 (16 x 2160x3840, 16x16 mesh, generic tables)', 'mesh5': 'warp_fwd_tile_kernel<TMODE_TPS, G = 5> at mesh5 (64 x 720p, 5x5 mesh)'}
+for wl in (sys.argv[2:] or ['cfg2', 'hd1080', 'cfg4', 'cfg3']):
     raw = os.path.join(ROOT, 'gpurun_out', 'final_%s_raw.csv' % wl)
     sass = os.path.join(ROOT, 'gpurun_out', 'final_%s_sass.csv' % wl)
     if not os.path.exists(raw):
