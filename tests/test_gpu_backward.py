@@ -83,7 +83,8 @@ def test_tps_autograd_dropin():
 
 
 # (2, 288, 512, 3, 4): the training shape of BASELINE configs[2] (two frames of it: the oracle's backward is NumPy)
-@pytest.mark.parametrize('shape', [(2, 96, 128, 3, 4), (1, 45, 50, 3, 5), (1, 32, 48, 2, 4), (2, 288, 512, 3, 4)])
+# (1, 44, 52, 3, 4): tile kernel with a ragged last strip (4 of 8 rows) and a ragged last tile (20 of 32 columns)
+@pytest.mark.parametrize('shape', [(2, 96, 128, 3, 4), (1, 45, 50, 3, 5), (1, 32, 48, 2, 4), (2, 288, 512, 3, 4), (1, 44, 52, 3, 4)])
 def test_tps_backward_vs_oracle_seeded(shape):
     from coupe.dvsg_b200 import ops
     b, h, w, c, m = shape
@@ -95,9 +96,13 @@ def test_tps_backward_vs_oracle_seeded(shape):
     U, C_ = cu(u), cu(coord)
     T = ops.tps_solve(C_, C_ + cu(vec))
     _, x, y, _ = ops.tps_warp_fwd(U, C_, T, (h, w))
-    gU, gT, gxs, gys = ops.tps_warp_bwd(U, C_, T, (h, w), cu(g_out), None, None, want_grid_grad=True)
+    # upstream gradients on the returned x, y (surf loss, trainer.py:363-386) add to the sampler's own
+    gx_in = rng.standard_normal(b * h * w).astype(np.float32)
+    gy_in = rng.standard_normal(b * h * w).astype(np.float32)
+    gU, gT, gxs, gys = ops.tps_warp_bwd(U, C_, T, (h, w), cu(g_out), cu(gx_in), cu(gy_in), want_grid_grad=True)
     x, y = x.cpu().numpy(), y.cpu().numpy()
     r_gim, r_gx, r_gy = O.tps_interpolate_bwd(u, x, y, h, w, g_out)
+    r_gx, r_gy = r_gx.reshape(-1) + gx_in, r_gy.reshape(-1) + gy_in
     assert rel(gU.cpu().numpy(), r_gim) <= 1e-4
     assert rel(gxs.cpu().numpy(), r_gx) <= 1e-4 and rel(gys.cpu().numpy(), r_gy) <= 1e-4
     assert rel(gT.cpu().numpy(), O.tps_grid_bwd(coord, h, w, gxs.cpu().numpy(), gys.cpu().numpy())) <= 1e-4
