@@ -147,7 +147,8 @@ def test_tps_identity_and_affine_known_answers():
     assert np.abs(T[0, :, 3:]).max() < 1e-6 and np.abs(T[0, :, 0] - off).max() < 1e-6 and np.abs(T[0, :, 1:3] - a).max() < 1e-6
 
 
-@pytest.mark.parametrize('shape', [(2, 288, 512, 3, 4), (2, 288, 512, 3, 5), (1, 37, 53, 3, 4), (2, 40, 64, 1, 3), (1, 33, 48, 18, 4)])
+# (1, 44, 52, 3, m): tile kernel with a ragged last strip (4 of 8 rows) and a ragged last tile (20 of 32 columns)
+@pytest.mark.parametrize('shape', [(2, 288, 512, 3, 4), (2, 288, 512, 3, 5), (1, 37, 53, 3, 4), (2, 40, 64, 1, 3), (1, 33, 48, 18, 4), (1, 44, 52, 3, 4), (1, 44, 52, 3, 6)])
 @pytest.mark.parametrize('flags', [0, FORCE_DIRECT], ids=['strip', 'direct'])
 def test_tps_forward_vs_oracle_seeded(shape, flags):
     b, h, w, c, m = shape
