@@ -133,15 +133,16 @@ def test_flow_warp_backward_vs_golden(name):
     assert rel(flow.grad.cpu().numpy(), g['grad_flow']) <= 1e-4
 
 
+@pytest.mark.parametrize('shape', [(2, 72, 100, 3), (1, 44, 52, 3)], ids=['72x100', '44x52'])
 @pytest.mark.parametrize('merge', [1, 0], ids=['merged', 'plain'])
-def test_flow_and_bilinear_backward_vs_oracle_seeded(merge):
+def test_flow_and_bilinear_backward_vs_oracle_seeded(merge, shape):
     from coupe.dvsg_b200 import _lib
     from coupe.dvsg_b200.spatial_transformer import bilinear_interp
     from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
     _lib.load().dvsg_set_bwd_tuning(merge)
     try:
         rng = np.random.default_rng(7)
-        b, h, w, c = 2, 72, 100, 3
+        b, h, w, c = shape
         im = rng.random((b, h, w, c), dtype=np.float32)
         flow = smooth_flow(rng, b, h, w)
         g_out = rng.standard_normal((b, h, w, c)).astype(np.float32)
