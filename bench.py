@@ -274,8 +274,7 @@ def run_ours(args, wl):
                 zero_stream.wait_stream(stream)      # the backward that last accumulated into this buffer has been issued
                 with torch.cuda.stream(zero_stream):
                     gU.zero_()
-            target = coord + vec
-            T = ops.tps_solve(coord, target)
+            T = ops.tps_solve(coord, vec, offsets=True)      # target = coord + vec is formed inside the prepared solve
             if sample:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)

@@ -35,8 +35,8 @@ def ThinPlateSpline(U, coord, vector, out_size, return_grid=True):
     if coord_t.dim() == 2:
         coord_t = coord_t.unsqueeze(0).expand(U.shape[0], -1, -1)
     _check_mesh(coord_t, vector)
-    target = coord_t + vector          # ThinPlateSpline.py:161 (tiny [B,pn,2] tensor op; keeps autograd to `vector`)
-    return ops.thin_plate_spline(U, coord_t, target, out_size, want_grid=return_grid)
+    # target = coord + vector (ThinPlateSpline.py:161) is formed inside the solve: same fp32 add, one launch less
+    return ops.thin_plate_spline(U, coord_t, vector, out_size, want_grid=return_grid, offsets=True)
 
 
 def ThinPlateSplineWithMask(U, coord, vector, out_size, return_grid=True):
@@ -50,4 +50,4 @@ def ThinPlateSplineWithMask(U, coord, vector, out_size, return_grid=True):
     if coord_t.dim() == 2:
         coord_t = coord_t.unsqueeze(0).expand(U.shape[0], -1, -1)
     _check_mesh(coord_t, vector)
-    return ops.thin_plate_spline_with_mask(U, coord_t, coord_t + vector, out_size, want_grid=return_grid)
+    return ops.thin_plate_spline_with_mask(U, coord_t, vector, out_size, want_grid=return_grid, offsets=True)

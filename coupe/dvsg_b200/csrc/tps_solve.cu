@@ -298,9 +298,12 @@ __global__ void __launch_bounds__(INV_THREADS) tps_inverse_kernel(const float* _
 
 // forward : T[b][c][i]           = sum_{j<pn} Winv[i][j]     * target[b][j][c]
 // backward: grad_target[b][j][c] = sum_{i<N}  Winv[i][j]     * grad_T[b][c][i]     (j < pn)
-template <bool TRANSPOSED>
+// OFFSETS (forward only): rhs holds the regressed offsets `vector` and the right-hand side is coord + vector
+// (ThinPlateSpline.py:161), added here in fp32 exactly as the separate elementwise add would
+template <bool TRANSPOSED, bool OFFSETS = false>
 __global__ void tps_apply_kernel(const double* __restrict__ work, int shared_sys, const float* __restrict__ rhs,
-                                 float* __restrict__ out, int B, int pn) {
+                                 float* __restrict__ out, int B, int pn, const float* __restrict__ coord = nullptr,
+                                 long long coord_stride = 0) {
     const int N = pn + 3, M = 2 * N;
     const int n_out = TRANSPOSED ? pn : N;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -317,10 +320,13 @@ __global__ void tps_apply_kernel(const double* __restrict__ work, int shared_sys
         out[((size_t)b * pn + o) * 2 + 0] = (float)a0;
         out[((size_t)b * pn + o) * 2 + 1] = (float)a1;
     } else {
+        const float* cb = OFFSETS ? coord + (size_t)b * coord_stride : nullptr;
         for (int j = 0; j < pn; ++j) {
             const double w = winv[(size_t)o * M + j];
-            a0 += w * (double)rhs[((size_t)b * pn + j) * 2 + 0];
-            a1 += w * (double)rhs[((size_t)b * pn + j) * 2 + 1];
+            float r0 = rhs[((size_t)b * pn + j) * 2 + 0], r1 = rhs[((size_t)b * pn + j) * 2 + 1];
+            if (OFFSETS) { r0 = __fadd_rn(cb[2 * j], r0); r1 = __fadd_rn(cb[2 * j + 1], r1); }
+            a0 += w * (double)r0;
+            a1 += w * (double)r1;
         }
         out[((size_t)b * 2 + 0) * N + o] = (float)a0;
         out[((size_t)b * 2 + 1) * N + o] = (float)a1;
@@ -337,7 +343,7 @@ static size_t big_workspace_bytes(int B, int pn, long long stride) {
 // (dvsg_tps_prepare), apply only; 2 = invert only
 template <bool TRANSPOSED>
 static int solve_impl(const float* coord, long long stride, const float* rhs, float* out, int B, int pn, void* ws,
-                      size_t ws_bytes, cudaStream_t st, const char* what, int prepared = 0) {
+                      size_t ws_bytes, cudaStream_t st, const char* what, int prepared = 0, bool offsets = false) {
     DVSG_REQUIRE(B >= 0 && pn >= 3, "%s: need B >= 0 and at least 3 control points (got B=%d pn=%d)", what, B, pn);
     if (B == 0) return DVSG_OK;
     DVSG_REQUIRE(coord && (prepared == 2 || (rhs && out)), "%s: null pointer", what);
@@ -369,7 +375,10 @@ static int solve_impl(const float* coord, long long stride, const float* rhs, fl
         if (rc || prepared == 2) return rc;
     }
     const long long n_out = (long long)B * (TRANSPOSED ? pn : N);
-    tps_apply_kernel<TRANSPOSED><<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(work, stride == 0, rhs, out, B, pn);
+    if (offsets && !TRANSPOSED)
+        tps_apply_kernel<false, true><<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(work, stride == 0, rhs, out, B, pn, coord, stride);
+    else
+        tps_apply_kernel<TRANSPOSED><<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(work, stride == 0, rhs, out, B, pn);
     count_launch();
     return check_launch("tps_apply_kernel");
 }
@@ -405,6 +414,13 @@ extern "C" int dvsg_tps_prepare(const float* coord, long long coord_batch_stride
 extern "C" int dvsg_tps_solve_prepared(const float* coord, long long coord_batch_stride, const float* target, float* T, int B, int pn,
                                        void* workspace, size_t workspace_bytes, void* stream) {
     return solve_impl<false>(coord, coord_batch_stride, target, T, B, pn, workspace, workspace_bytes, (cudaStream_t)stream, "tps_solve_prepared", 1);
+}
+
+// same with the regressed offsets as the argument: the right-hand side coord + vector is formed inside the apply kernel
+extern "C" int dvsg_tps_solve_offsets_prepared(const float* coord, long long coord_batch_stride, const float* vector, float* T, int B, int pn,
+                                               void* workspace, size_t workspace_bytes, void* stream) {
+    return solve_impl<false>(coord, coord_batch_stride, vector, T, B, pn, workspace, workspace_bytes, (cudaStream_t)stream,
+                             "tps_solve_offsets_prepared", 1, true);
 }
 
 extern "C" int dvsg_tps_solve_bwd_prepared(const float* coord, long long coord_batch_stride, const float* grad_T, float* grad_target, int B,

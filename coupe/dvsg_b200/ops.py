@@ -83,8 +83,10 @@ def _prepared_workspace(lib, cbuf, cstride, B, pn):
 
 
 # ---- K1 ------------------------------------------------------------------------------------
-def tps_solve(coord, target):
-    """_solve_system (ThinPlateSpline.py:143-166) -> T [B, 2, pn+3]."""
+def tps_solve(coord, target, offsets=False):
+    """_solve_system (ThinPlateSpline.py:143-166) -> T [B, 2, pn+3].  offsets=True: `target` holds the regressed offsets
+    `vector` and the right-hand side coord + vector (ThinPlateSpline.py:161) is formed inside the solve (same fp32 add,
+    one launch less) when the mesh is shared by the batch; per-frame meshes add here."""
     lib = _lib.load()
     target = as_cuda_f32(target, 'target')
     B = target.shape[0]
@@ -96,8 +98,12 @@ def tps_solve(coord, target):
         raise ValueError('TPS needs at least 3 control points, got %d' % pn)
     T = torch.empty((B, 2, pn + 3), dtype=torch.float32, device=target.device)
     pws, pbytes = _prepared_workspace(lib, cbuf, cstride, B, pn) if B > 0 else (None, 0)
+    if offsets and pws is None and B > 0:
+        target = coord.to(target.device) + target
     with torch.cuda.device(target.device):
-        if pws is not None:
+        if pws is not None and offsets:
+            rc = lib.dvsg_tps_solve_offsets_prepared(ptr(cbuf), cstride, ptr(target), ptr(T), B, pn, ptr(pws), pbytes, stream_ptr(target.device))
+        elif pws is not None:
             rc = lib.dvsg_tps_solve_prepared(ptr(cbuf), cstride, ptr(target), ptr(T), B, pn, ptr(pws), pbytes, stream_ptr(target.device))
         else:
             nbytes = lib.dvsg_tps_solve_workspace_bytes(B, pn, cstride)
@@ -173,8 +179,8 @@ class _TpsWarp(torch.autograd.Function):
     (model.py:62-68)."""
 
     @staticmethod
-    def forward(ctx, U, coord, target, out_size, want_grid):
-        T = tps_solve(coord, target)
+    def forward(ctx, U, coord, target, out_size, want_grid, offsets=False):
+        T = tps_solve(coord, target, offsets=offsets)       # offsets: `target` is the regressed `vector` (d target / d vector = I)
         out, x, y, _ = tps_warp_fwd(U, coord, T, out_size, want_grid=want_grid)
         ctx.save_for_backward(U, coord, T)
         ctx.out_size = out_size
@@ -193,10 +199,12 @@ class _TpsWarp(torch.autograd.Function):
         need_t = ctx.needs_input_grad[2]
         gU, gT, _, _ = tps_warp_bwd(U, coord, T, ctx.out_size, grad_out.contiguous(), grad_x, grad_y, need_grad_U=need_U)
         g_target = tps_solve_bwd(coord, gT) if need_t else None
-        return gU, None, g_target, None, None
+        return gU, None, g_target, None, None, None
 
 
-def thin_plate_spline(U, coord, target, out_size, want_grid=True):
+def thin_plate_spline(U, coord, target, out_size, want_grid=True, offsets=False):
+    """offsets=True: `target` holds the offsets `vector` of ThinPlateSpline(U, coord, vector, out_size); the sum
+    coord + vector is formed inside the solve."""
     U = as_cuda_f32(U, 'U')
     if U.dim() != 4:
         raise ValueError('U must have shape [num_batch, height, width, num_channels], got %s' % (tuple(U.shape),))
@@ -205,18 +213,18 @@ def thin_plate_spline(U, coord, target, out_size, want_grid=True):
     if coord.requires_grad:
         raise NotImplementedError('gradient w.r.t. the control-point positions is not implemented: every reference '
                                   'call site passes a constant mesh (model.py:62-68)')
-    out, x, y = _TpsWarp.apply(U, coord, target, tuple(out_hw(out_size)), bool(want_grid))
+    out, x, y = _TpsWarp.apply(U, coord, target, tuple(out_hw(out_size)), bool(want_grid), bool(offsets))
     return (out, x, y) if want_grid else (out, None, None)
 
 
-def thin_plate_spline_with_mask(U, coord, target, out_size, want_grid=True):
+def thin_plate_spline_with_mask(U, coord, target, out_size, want_grid=True, offsets=False):
     """N1: the image warp and the warp of an all-ones image (model.py:82,85,121)
     from ONE pass.  Inference-style (no autograd through the mask, matching the reference where the
     mask only gates losses)."""
     U = as_cuda_f32(U, 'U')
     target = as_cuda_f32(target, 'target', like=U)
     coord = _as_mesh(coord, U)
-    T = tps_solve(coord, target)
+    T = tps_solve(coord, target, offsets=offsets)
     out, x, y, mask = tps_warp_fwd(U, coord, T, out_hw(out_size), want_grid=want_grid, want_mask=True)
     return out, mask.unsqueeze(-1).expand(-1, -1, -1, U.shape[3]), x, y
 

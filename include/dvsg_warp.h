@@ -76,6 +76,11 @@ int dvsg_tps_prepare(const float* coord, long long coord_batch_stride, int B, in
 int dvsg_tps_solve_prepared(const float* coord, long long coord_batch_stride, const float* target,
                             float* T, int B, int pn, void* workspace, size_t workspace_bytes,
                             void* stream);
+/* dvsg_tps_solve_prepared with target = coord + vector (ThinPlateSpline.py:161) formed inside
+ * the call: `vector` [B,pn,2] are the regressed offsets (networks.py:44).                    */
+int dvsg_tps_solve_offsets_prepared(const float* coord, long long coord_batch_stride,
+                                    const float* vector, float* T, int B, int pn, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 int dvsg_tps_solve_bwd_prepared(const float* coord, long long coord_batch_stride,
                                 const float* grad_T, float* grad_target, int B, int pn,
                                 void* workspace, size_t workspace_bytes, void* stream);

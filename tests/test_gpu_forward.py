@@ -594,3 +594,18 @@ def test_large_mesh_grid_stage_vs_oracle_on_the_kernels_coefficients(m, size):
     e_o = max(np.abs(x32.reshape(-1) - x64.reshape(-1)).max(), np.abs(y32.reshape(-1) - y64.reshape(-1)).max())
     print('mesh %dx%d grid stage: |kernel - fp64| %.2e, |fp32 oracle - fp64| %.2e, max |T| %.1f' % (m, m, e_k, e_o, np.abs(Tn).max()))
     assert e_k <= max(2.0 * e_o, 2e-5) and e_k <= 2e-4
+
+
+@pytest.mark.parametrize('m', [4, 5, 16])
+def test_solve_from_offsets_equals_solve_from_the_sum(m):
+    """dvsg_tps_solve_offsets_prepared forms target = coord + vector (ThinPlateSpline.py:161) inside the apply kernel:
+    the same fp32 add, so T is bit-identical to adding first; per-frame meshes fall back to the explicit add."""
+    from coupe.dvsg_b200 import ops
+    B = 5
+    rng = np.random.default_rng(m)
+    mesh = cu(tiled_mesh(m, m, 1)[0])
+    vec = cu(rng.uniform(-0.1, 0.1, (B, m * m, 2)).astype(np.float32))
+    shared = mesh.unsqueeze(0).expand(B, -1, -1)
+    assert torch.equal(ops.tps_solve(shared, vec, offsets=True), ops.tps_solve(shared, shared + vec))
+    per_frame = shared.contiguous()
+    assert torch.equal(ops.tps_solve(per_frame, vec, offsets=True), ops.tps_solve(per_frame, per_frame + vec))
