@@ -469,3 +469,12 @@ extern "C" int dvsg_tps_warp_frames(const float* U, const float* coord, const fl
     if (rc) return rc;
     return dvsg_tps_warp_fwd(U, coord, 0, T, out, x_out, y_out, mask_out, B, H, W, C, oh, ow, pn, 0, stream);
 }
+
+// Same with the regressed offsets `vector` [B,pn,2] as the argument (coord + vector is formed inside the prepared solve)
+extern "C" int dvsg_tps_warp_frames_offsets(const float* U, const float* coord, const float* vector, void* prepared, size_t prepared_bytes,
+                                            float* T, float* out, float* x_out, float* y_out, float* mask_out, int B, int H, int W, int C,
+                                            int oh, int ow, int pn, void* stream) {
+    const int rc = dvsg_tps_solve_offsets_prepared(coord, 0, vector, T, B, pn, prepared, prepared_bytes, stream);
+    if (rc) return rc;
+    return dvsg_tps_warp_fwd(U, coord, 0, T, out, x_out, y_out, mask_out, B, H, W, C, oh, ow, pn, 0, stream);
+}

@@ -350,7 +350,8 @@ def homography_warp(inp, theta, out_size, projective, want_grid=False):
 class OnlineWarper(object):
     """ThinPlateSpline for the online loop of eval.py:106-110 (one small batch per call, constant mesh, inference only):
     the mesh's system is inverted once, buffers are allocated once, and each call is ONE trip through the C ABI
-    (dvsg_tps_warp_frames = prepared solve + fused warp).  Same results as ThinPlateSpline(U, coord, vector, [h, w])."""
+    (dvsg_tps_warp_frames_offsets = prepared solve of coord + vector + fused warp).  Same results as
+    ThinPlateSpline(U, coord, vector, [h, w])."""
 
     def __init__(self, mesh, B, H, W, C=3, device=None):
         lib = _lib.load()
@@ -363,10 +364,10 @@ class OnlineWarper(object):
             rc = lib.dvsg_tps_prepare(ptr(self.mesh), 0, self.B, self.pn, ptr(self.ws), self.nbytes, stream_ptr(dev))
         _lib.check(rc, 'dvsg_tps_prepare')
         self.T = torch.empty((self.B, 2, self.pn + 3), dtype=torch.float32, device=dev)
-        self.target = torch.empty((self.B, self.pn, 2), dtype=torch.float32, device=dev)
         self.out = torch.empty((self.B, self.H, self.W, self.C), dtype=torch.float32, device=dev)
-        self._fn = lib.dvsg_tps_warp_frames
-        self._args = (ptr(self.mesh), ptr(self.target), ptr(self.ws), self.nbytes, ptr(self.T), ptr(self.out), None, None, None,
+        self._fn = lib.dvsg_tps_warp_frames_offsets
+        self._mesh_ptr = ptr(self.mesh)
+        self._args = (ptr(self.ws), self.nbytes, ptr(self.T), ptr(self.out), None, None, None,
                       self.B, self.H, self.W, self.C, self.H, self.W, self.pn)
 
     def warp(self, U, vector):
@@ -374,10 +375,12 @@ class OnlineWarper(object):
         object, overwritten by the next call)."""
         if U.shape != self.out.shape or U.dtype != torch.float32 or not U.is_cuda or not U.is_contiguous():
             raise ValueError('U must be a contiguous fp32 CUDA tensor of shape %r' % (tuple(self.out.shape),))
-        torch.add(self.mesh, vector, out=self.target)                  # coord + vector, ThinPlateSpline.py:161
-        rc = self._fn(U.data_ptr(), *self._args, torch.cuda.current_stream(U.device).cuda_stream)
+        if tuple(vector.shape) != (self.B, self.pn, 2) or vector.dtype != torch.float32 or not vector.is_cuda or not vector.is_contiguous():
+            raise ValueError('vector must be a contiguous fp32 CUDA tensor of shape %r' % ((self.B, self.pn, 2),))
+        # coord + vector (ThinPlateSpline.py:161) is formed inside the prepared solve
+        rc = self._fn(U.data_ptr(), self._mesh_ptr, vector.data_ptr(), *self._args, torch.cuda.current_stream(U.device).cuda_stream)
         if rc:
-            _lib.check(rc, 'dvsg_tps_warp_frames')
+            _lib.check(rc, 'dvsg_tps_warp_frames_offsets')
         return self.out
 
 

@@ -105,6 +105,11 @@ int dvsg_tps_warp_frames(const float* U, const float* coord, const float* target
                          size_t prepared_bytes, float* T, float* out, float* x_out, float* y_out,
                          float* mask_out, int B, int H, int W, int C, int oh, int ow, int pn,
                          void* stream);
+/* same, taking the regressed offsets `vector` [B,pn,2] (networks.py:44) instead of target      */
+int dvsg_tps_warp_frames_offsets(const float* U, const float* coord, const float* vector,
+                                 void* prepared, size_t prepared_bytes, float* T, float* out,
+                                 float* x_out, float* y_out, float* mask_out, int B, int H, int W,
+                                 int C, int oh, int ow, int pn, void* stream);
 
 /* ---- K4: backward of K2+K3 (TF autodiff of ThinPlateSpline.py:48-89,129) -------------
  *   grad_out [B,oh,ow,C]; grad_x_in / grad_y_in: optional upstream gradients on the
