@@ -26,6 +26,7 @@ PROTOTYPES = {
     'dvsg_tps_solve_bwd': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     'dvsg_tps_prepare_workspace_bytes': (c_size_t, [c_int, c_int, c_longlong]),
     'dvsg_tps_prepare': (c_int, [_P, c_longlong, c_int, c_int, _P, c_size_t, _P]),
+    'dvsg_tps_prepare_status': (c_int, [_P, c_size_t, c_int, c_int, c_longlong, _P, ctypes.POINTER(c_int)]),
     'dvsg_tps_solve_prepared': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     'dvsg_tps_solve_offsets_prepared': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     'dvsg_tps_solve_bwd_prepared': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),

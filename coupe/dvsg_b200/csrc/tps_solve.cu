@@ -199,10 +199,10 @@ __global__ void __launch_bounds__(SH_THREADS) tps_solve_shared_kernel(const floa
         }
         __syncthreads();                                       // every row group has read rows k and piv
         if (act) {
-            if (g == 0) {
-                if (piv != k) s_a[piv * SH_LD + j] = rowk_old; // swap
-                s_a[k * SH_LD + j] = pr;
-            }
+            if (g == 0) s_a[k * SH_LD + j] = pr;
+            // the swap k <-> piv needs no store of its own: slot piv receives row k's old value minus its elimination
+            // term from the ONE thread that owns (piv, j) below (a separate `s_a[piv] = rowk_old` by row group 0 raced
+            // with that store whenever piv % SH_ROWG != 0)
             for (int i = g; i < N; i += SH_ROWG) {
                 if (i == k) continue;
                 const double base = (i == piv && piv != k) ? rowk_old : s_a[i * SH_LD + j];
@@ -369,7 +369,14 @@ static int solve_impl(const float* coord, long long stride, const float* rhs, fl
     const int nsys = stride == 0 ? 1 : B;
     double* work = reinterpret_cast<double*>(ws);
     if (prepared != 1) {
-        tps_inverse_kernel<<<nsys, INV_THREADS, (size_t)3 * N * sizeof(double), st>>>(coord, stride, pn, work, nullptr);
+        // singular systems (duplicate / collinear control points; tf.matrix_inverse raises there) set the status word kept
+        // in the last 256 bytes of the workspace: read it back with dvsg_tps_prepare_status
+        int* status = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + need - 256);
+        if (cudaMemsetAsync(status, 0, sizeof(int), st) != cudaSuccess) return check_launch("tps_inverse status reset");
+        const size_t inv_smem = (size_t)3 * N * sizeof(double);      // 48 KB at the maximum N = 2048: above the default limit with the static arrays
+        static bool attr_done = false;
+        if (!attr_done) { cudaFuncSetAttribute(tps_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * (int)sizeof(double)); attr_done = true; }
+        tps_inverse_kernel<<<nsys, INV_THREADS, inv_smem, st>>>(coord, stride, pn, work, status);
         count_launch();
         const int rc = check_launch("tps_inverse_kernel");
         if (rc || prepared == 2) return rc;
@@ -409,6 +416,20 @@ extern "C" size_t dvsg_tps_prepare_workspace_bytes(int B, int pn, long long coor
 extern "C" int dvsg_tps_prepare(const float* coord, long long coord_batch_stride, int B, int pn, void* workspace, size_t workspace_bytes,
                                 void* stream) {
     return solve_impl<false>(coord, coord_batch_stride, nullptr, nullptr, B, pn, workspace, workspace_bytes, (cudaStream_t)stream, "tps_prepare", 2);
+}
+
+// 0 = every system prepared in this workspace was invertible, 1 = at least one pivot was exactly zero (the reference's
+// tf.matrix_inverse raises InvalidArgument there, ThinPlateSpline.py:159).  Synchronises `stream`.
+extern "C" int dvsg_tps_prepare_status(const void* workspace, size_t workspace_bytes, int B, int pn, long long coord_batch_stride,
+                                       void* stream, int* singular_out) {
+    DVSG_REQUIRE(workspace && singular_out && B > 0 && pn >= 3, "tps_prepare_status: bad argument");
+    const size_t need = big_workspace_bytes(B, pn, coord_batch_stride);
+    DVSG_REQUIRE(workspace_bytes >= need, "tps_prepare_status: workspace of %zu bytes required, %zu given", need, workspace_bytes);
+    const int* status = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(workspace) + need - 256);
+    if (cudaMemcpyAsync(singular_out, status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+        return check_launch("tps_prepare_status");
+    return DVSG_OK;
 }
 
 extern "C" int dvsg_tps_solve_prepared(const float* coord, long long coord_batch_stride, const float* target, float* T, int B, int pn,

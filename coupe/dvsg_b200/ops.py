@@ -56,40 +56,63 @@ def _mesh_args(coord, B, pn_expected=None):
 
 
 # Inverse of the system of a constant shared mesh, kept per mesh so that a clip inverts it once: per
-# call only W^-1 is applied (4x4 mesh: a ~3 us product instead of a 23 us factorisation; 16x16: instead of 7.6 ms).  The entry holds the mesh storage alive, so its address cannot be recycled,
-# and is keyed on the tensor version, so an in-place update of the mesh invalidates it.
+# call only W^-1 is applied (4x4 mesh: a ~3 us product instead of a 23 us factorisation; 16x16: instead of 7.6 ms).
+# The entry holds the mesh storage alive, so its address cannot be recycled, and is keyed on the tensor version, so an
+# in-place update of the mesh through torch invalidates it.  Meshes that arrive through DLPack (cupy / jax / numba
+# producers: every import is a fresh tensor with version 0, and the producer may rewrite the memory behind torch's back)
+# are never cached: their system is inverted on every call.  The inverse is produced on the stream of the call that
+# missed; a later call on another stream waits for that event first.
 _prepared = collections.OrderedDict()
 
 
-def _prepared_workspace(lib, cbuf, cstride, B, pn):
+def _prepare(lib, cbuf, B, pn, nbytes):
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=cbuf.device)
+    with torch.cuda.device(cbuf.device):
+        sp = stream_ptr(cbuf.device)
+        _lib.check(lib.dvsg_tps_prepare(ptr(cbuf), 0, B, pn, ptr(ws), nbytes, sp), 'dvsg_tps_prepare')
+        singular = ctypes.c_int(0)
+        _lib.check(lib.dvsg_tps_prepare_status(ptr(ws), nbytes, B, pn, 0, sp, ctypes.byref(singular)), 'dvsg_tps_prepare_status')
+    if singular.value:
+        # tf.matrix_inverse (ThinPlateSpline.py:159) raises InvalidArgumentError("Input is not invertible.") here
+        raise ValueError('ThinPlateSpline: the TPS system of this control mesh is not invertible (duplicate control points?)')
+    return ws
+
+
+def _prepared_workspace(lib, cbuf, cstride, B, pn, cache=True):
     """(workspace holding W^-1 for this shared mesh, its size), or (None, 0) for per-frame meshes (plain solve)."""
     if cstride != 0:
         return None, 0
     nbytes = lib.dvsg_tps_prepare_workspace_bytes(B, pn, 0)
+    if not cache:
+        return _prepare(lib, cbuf, B, pn, nbytes), nbytes
     st = cbuf.untyped_storage()
     key = (cbuf.device.index, st.data_ptr(), cbuf.storage_offset(), cbuf._version, pn)
     hit = _prepared.get(key)
+    cur = torch.cuda.current_stream(cbuf.device)
     if hit is None:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=cbuf.device)
-        with torch.cuda.device(cbuf.device):
-            rc = lib.dvsg_tps_prepare(ptr(cbuf), 0, B, pn, ptr(ws), nbytes, stream_ptr(cbuf.device))
-        _lib.check(rc, 'dvsg_tps_prepare')
-        _prepared[key] = hit = (ws, st)
+        ws = _prepare(lib, cbuf, B, pn, nbytes)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        _prepared[key] = hit = (ws, st, ev, cur.cuda_stream)
         while len(_prepared) > 4:
             _prepared.popitem(last=False)
     else:
         _prepared.move_to_end(key)
+        if hit[3] != cur.cuda_stream:
+            cur.wait_event(hit[2])
     return hit[0], nbytes
 
 
 # ---- K1 ------------------------------------------------------------------------------------
-def tps_solve(coord, target, offsets=False):
+def tps_solve(coord, target, offsets=False, cache_mesh=None):
     """_solve_system (ThinPlateSpline.py:143-166) -> T [B, 2, pn+3].  offsets=True: `target` holds the regressed offsets
     `vector` and the right-hand side coord + vector (ThinPlateSpline.py:161) is formed inside the solve (same fp32 add,
     one launch less) when the mesh is shared by the batch; per-frame meshes add here."""
     lib = _lib.load()
     target = as_cuda_f32(target, 'target')
     B = target.shape[0]
+    if cache_mesh is None:
+        cache_mesh = isinstance(coord, torch.Tensor)      # DLPack imports are never cached (see _prepared)
     coord = _as_mesh(coord, target)
     cbuf, cstride, pn = _mesh_args(coord, B)
     if tuple(target.shape) != (B, pn, 2):
@@ -97,7 +120,7 @@ def tps_solve(coord, target, offsets=False):
     if pn < 3:
         raise ValueError('TPS needs at least 3 control points, got %d' % pn)
     T = torch.empty((B, 2, pn + 3), dtype=torch.float32, device=target.device)
-    pws, pbytes = _prepared_workspace(lib, cbuf, cstride, B, pn) if B > 0 else (None, 0)
+    pws, pbytes = _prepared_workspace(lib, cbuf, cstride, B, pn, cache_mesh) if B > 0 else (None, 0)
     if offsets and pws is None and B > 0:
         target = coord.to(target.device) + target
     with torch.cuda.device(target.device):
@@ -113,13 +136,13 @@ def tps_solve(coord, target, offsets=False):
     return T
 
 
-def tps_solve_bwd(coord, grad_T):
+def tps_solve_bwd(coord, grad_T, cache_mesh=True):
     lib = _lib.load()
     grad_T = as_cuda_f32(grad_T, 'grad_T')
     B, _, N = grad_T.shape
     cbuf, cstride, pn = _mesh_args(coord, B, N - 3)
     g = torch.empty((B, pn, 2), dtype=torch.float32, device=grad_T.device)
-    pws, pbytes = _prepared_workspace(lib, cbuf, cstride, B, pn) if B > 0 else (None, 0)
+    pws, pbytes = _prepared_workspace(lib, cbuf, cstride, B, pn, cache_mesh) if B > 0 else (None, 0)
     with torch.cuda.device(grad_T.device):
         if pws is not None:
             rc = lib.dvsg_tps_solve_bwd_prepared(ptr(cbuf), cstride, ptr(grad_T), ptr(g), B, pn, ptr(pws), pbytes, stream_ptr(grad_T.device))
@@ -175,58 +198,70 @@ def tps_warp_bwd(U, coord, T, out_size, grad_out, grad_x=None, grad_y=None, need
 
 
 class _TpsWarp(torch.autograd.Function):
-    """(U, target) -> (output, x, y) with coord a constant, as in every reference call site
-    (model.py:62-68)."""
+    """(U, target) -> (output, x, y, mask) with coord a constant, as in every reference call site
+    (model.py:62-68).  mask (N1) is the warp of an all-ones image from the same pass."""
 
     @staticmethod
-    def forward(ctx, U, coord, target, out_size, want_grid, offsets=False):
-        T = tps_solve(coord, target, offsets=offsets)       # offsets: `target` is the regressed `vector` (d target / d vector = I)
-        out, x, y, _ = tps_warp_fwd(U, coord, T, out_size, want_grid=want_grid)
+    def forward(ctx, U, coord, target, out_size, want_grid, offsets=False, want_mask=False, cache_mesh=True):
+        T = tps_solve(coord, target, offsets=offsets, cache_mesh=cache_mesh)   # offsets: `target` is the regressed `vector` (d target / d vector = I)
+        out, x, y, mask = tps_warp_fwd(U, coord, T, out_size, want_grid=want_grid, want_mask=want_mask)
         ctx.save_for_backward(U, coord, T)
         ctx.out_size = out_size
         ctx.want_grid = want_grid
+        ctx.cache_mesh = cache_mesh
         if not want_grid:
             x, y = out.new_empty(0), out.new_empty(0)
             ctx.mark_non_differentiable(x, y)
-        return out, x, y
+        if not want_mask:
+            mask = out.new_empty(0)
+        # d mask / d (x, y) is identically zero: the four weights sum to (x1f - x0f) * (y1f - y0f), a piecewise
+        # constant of the coordinates (and the warp of ones does not depend on U)
+        ctx.mark_non_differentiable(mask)
+        return out, x, y, mask
 
     @staticmethod
-    def backward(ctx, grad_out, grad_x, grad_y):
+    def backward(ctx, grad_out, grad_x, grad_y, _grad_mask):
         U, coord, T = ctx.saved_tensors
         if not ctx.want_grid:
             grad_x = grad_y = None
         need_U = ctx.needs_input_grad[0]
         need_t = ctx.needs_input_grad[2]
         gU, gT, _, _ = tps_warp_bwd(U, coord, T, ctx.out_size, grad_out.contiguous(), grad_x, grad_y, need_grad_U=need_U)
-        g_target = tps_solve_bwd(coord, gT) if need_t else None
-        return gU, None, g_target, None, None, None
+        g_target = tps_solve_bwd(coord, gT, cache_mesh=ctx.cache_mesh) if need_t else None
+        return gU, None, g_target, None, None, None, None, None
 
 
-def thin_plate_spline(U, coord, target, out_size, want_grid=True, offsets=False):
-    """offsets=True: `target` holds the offsets `vector` of ThinPlateSpline(U, coord, vector, out_size); the sum
-    coord + vector is formed inside the solve."""
+def _tps_args(U, coord, target):
     U = as_cuda_f32(U, 'U')
     if U.dim() != 4:
         raise ValueError('U must have shape [num_batch, height, width, num_channels], got %s' % (tuple(U.shape),))
+    cache_mesh = isinstance(coord, torch.Tensor)
     coord = _as_mesh(coord, U)
     target = as_cuda_f32(target, 'target', like=U)
     if coord.requires_grad:
         raise NotImplementedError('gradient w.r.t. the control-point positions is not implemented: every reference '
                                   'call site passes a constant mesh (model.py:62-68)')
-    out, x, y = _TpsWarp.apply(U, coord, target, tuple(out_hw(out_size)), bool(want_grid), bool(offsets))
+    return U, coord, target, cache_mesh
+
+
+def thin_plate_spline(U, coord, target, out_size, want_grid=True, offsets=False):
+    """offsets=True: `target` holds the offsets `vector` of ThinPlateSpline(U, coord, vector, out_size); the sum
+    coord + vector is formed inside the solve."""
+    U, coord, target, cache_mesh = _tps_args(U, coord, target)
+    out, x, y, _ = _TpsWarp.apply(U, coord, target, tuple(out_hw(out_size)), bool(want_grid), bool(offsets), False, cache_mesh)
     return (out, x, y) if want_grid else (out, None, None)
 
 
 def thin_plate_spline_with_mask(U, coord, target, out_size, want_grid=True, offsets=False):
-    """N1: the image warp and the warp of an all-ones image (model.py:82,85,121)
-    from ONE pass.  Inference-style (no autograd through the mask, matching the reference where the
-    mask only gates losses)."""
-    U = as_cuda_f32(U, 'U')
-    target = as_cuda_f32(target, 'target', like=U)
-    coord = _as_mesh(coord, U)
-    T = tps_solve(coord, target, offsets=offsets)
-    out, x, y, mask = tps_warp_fwd(U, coord, T, out_hw(out_size), want_grid=want_grid, want_mask=True)
-    return out, mask.unsqueeze(-1).expand(-1, -1, -1, U.shape[3]), x, y
+    """N1: the image warp and the warp of an all-ones image -- the pair of stn() calls at every
+    training call site, model.py:81-85,120-121 -- from ONE pass.  Returns (output, mask, x, y).  output, x and y carry
+    gradients to U and target exactly like thin_plate_spline; the mask is returned without a graph: in the reference it
+    is differentiable too (trainer.py:232-243 multiplies by it), but its gradient w.r.t. the coordinates is identically
+    zero (the four weights sum to a piecewise constant) and it does not depend on U."""
+    U, coord, target, cache_mesh = _tps_args(U, coord, target)
+    out, x, y, mask = _TpsWarp.apply(U, coord, target, tuple(out_hw(out_size)), bool(want_grid), bool(offsets), True, cache_mesh)
+    mask = mask.unsqueeze(-1).expand(-1, -1, -1, U.shape[3])
+    return (out, mask, x, y) if want_grid else (out, mask, None, None)
 
 
 # ---- K5 --------------------------------------------------------------------------------------
@@ -378,7 +413,8 @@ class OnlineWarper(object):
         if tuple(vector.shape) != (self.B, self.pn, 2) or vector.dtype != torch.float32 or not vector.is_cuda or not vector.is_contiguous():
             raise ValueError('vector must be a contiguous fp32 CUDA tensor of shape %r' % ((self.B, self.pn, 2),))
         # coord + vector (ThinPlateSpline.py:161) is formed inside the prepared solve
-        rc = self._fn(U.data_ptr(), self._mesh_ptr, vector.data_ptr(), *self._args, torch.cuda.current_stream(U.device).cuda_stream)
+        with torch.cuda.device(self.out.device):
+            rc = self._fn(U.data_ptr(), self._mesh_ptr, vector.data_ptr(), *self._args, torch.cuda.current_stream(U.device).cuda_stream)
         if rc:
             _lib.check(rc, 'dvsg_tps_warp_frames_offsets')
         return self.out

@@ -73,6 +73,10 @@ int dvsg_tps_solve_bwd(const float* coord, long long coord_batch_stride, const f
 size_t dvsg_tps_prepare_workspace_bytes(int B, int pn, long long coord_batch_stride);
 int dvsg_tps_prepare(const float* coord, long long coord_batch_stride, int B, int pn,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* *singular_out = 1 when a pivot of a system prepared in this workspace was exactly zero (duplicate control
+ * points: tf.matrix_inverse, ThinPlateSpline.py:159, raises InvalidArgument there), else 0.  Synchronises. */
+int dvsg_tps_prepare_status(const void* workspace, size_t workspace_bytes, int B, int pn,
+                            long long coord_batch_stride, void* stream, int* singular_out);
 int dvsg_tps_solve_prepared(const float* coord, long long coord_batch_stride, const float* target,
                             float* T, int B, int pn, void* workspace, size_t workspace_bytes,
                             void* stream);

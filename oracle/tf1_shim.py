@@ -6,6 +6,7 @@ enough of the `tensorflow` 1.x module surface for the UNMODIFIED reference files
 
     /root/reference/ThinPlateSpline.py, ThinPlateSpline2.py,
     /root/reference/spatial_transformer.py, /root/reference/warp_with_optical_flow.py
+    (+ the methods masked_MSE, temporal_loss, get_surf_loss of /root/reference/trainer.py)
 
 to execute eagerly (each tf.* call computes immediately on torch CPU fp32/int32 tensors).
 `tests/golden/make_golden.py` installs it as `sys.modules['tensorflow']`, imports the
@@ -206,6 +207,21 @@ def reduce_sum(x, axis=None):
     return x.sum() if axis is None else x.sum(dim=axis)
 
 
+def reduce_mean(x, axis=None, name=None):
+    x = _t(x)
+    return x.mean() if axis is None else x.mean(dim=axis)
+
+
+def squared_difference(a, b):
+    d = _t(a) - _t(b)
+    return d * d
+
+
+def batch_gather(params, indices):
+    # params [B, N], indices [B, P] -> params[b, indices[b, p]]   (trainer.py:379-380)
+    return torch.gather(_t(params), 1, _t(indices).to(torch.int64))
+
+
 def add_n(values):
     out = values[0]
     for v in values[1:]:
@@ -267,6 +283,24 @@ def install():
     mod = sys.modules[__name__]
     sys.modules['tensorflow'] = mod
     return mod
+
+
+def load_reference_methods(path, class_name, method_names, namespace):
+    """Compile the UNMODIFIED source of selected methods of a reference class (its file imports packages that do not
+    exist here, so the file cannot be executed whole): the method bodies are cut out of the file's AST with their
+    original line numbers and executed against `namespace` (+ this shim as `tf`).  Returns {name: function}."""
+    import ast
+    install()
+    with open(path, 'r') as fh:
+        tree = ast.parse(fh.read(), path)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name][0]
+    funcs = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in method_names]
+    assert len(funcs) == len(method_names), 'reference methods not found'
+    mod = ast.Module(body=funcs, type_ignores=[])
+    ns = dict(namespace)
+    ns['tf'] = sys.modules[__name__]
+    exec(compile(mod, path, 'exec'), ns)
+    return {n: ns[n] for n in method_names}
 
 
 def load_reference(path, name):

@@ -147,11 +147,65 @@ def sampler_cases(rng):
     return cases
 
 
+def loss_cases():
+    """N3: Trainer.masked_MSE / temporal_loss / get_surf_loss, trainer.py:232-250,363-386 --
+    the method bodies executed UNMODIFIED (cut out of trainer.py's AST: the file itself imports tensorlayer).
+    Own generator, so that adding these cases leaves the older fixtures bit-identical."""
+    import types
+    rng = np.random.default_rng(20261019)
+    fl = tf.load_reference(os.path.join(REF, 'warp_with_optical_flow.py'), 'ref_warp_with_optical_flow')
+    fns = tf.load_reference_methods(os.path.join(REF, 'trainer.py'), 'Trainer', ['masked_MSE', 'temporal_loss', 'get_surf_loss'],
+                                    {'tf_warp': fl.tf_warp})
+    me = types.SimpleNamespace()
+    for k, f in fns.items():
+        setattr(me, k, types.MethodType(f, me))
+    cases = {}
+    # masked_MSE: fractional validity mask (a warp of ones), one frame fully masked out (div_no_nan)
+    b, h, w, c = 3, 20, 28, 3
+    pred, gt = smooth_image(rng, b, h, w, c), smooth_image(rng, b, h, w, c)
+    mask = np.clip(smooth_image(rng, b, h, w, c) * 1.6 - 0.3, 0.0, 1.0).astype(np.float32)
+    mask[1] = 0.0
+    p_t, g_t, m_t = (tt(a).requires_grad_(True) for a in (pred, gt, mask))
+    loss = me.masked_MSE(p_t, g_t, m_t, 'loss')
+    (loss * 1.5).backward()
+    cases['loss_masked_mse'] = dict(pred=pred, gt=gt, mask=mask, loss=loss.detach().numpy(), grad_scale=np.float32(1.5),
+                                    grad_pred=p_t.grad.numpy(), grad_gt=g_t.grad.numpy(), grad_mask=m_t.grad.numpy())
+    # temporal_loss: tf_warp of the prediction and of its mask, then the masked MSE
+    b, h, w, c = 2, 18, 24, 3
+    pred, gt = smooth_image(rng, b, h, w, c), smooth_image(rng, b, h, w, c)
+    mask_pred = np.clip(smooth_image(rng, b, h, w, c) * 1.5 - 0.2, 0.0, 1.0).astype(np.float32)
+    mask_gt = (rng.random((b, h, w, c)) > 0.25).astype(np.float32)
+    flow = rng.uniform(-2.5, 2.5, (b, h, w, 2)).astype(np.float32)
+    p_t, mp_t = tt(pred).requires_grad_(True), tt(mask_pred).requires_grad_(True)
+    loss = me.temporal_loss(p_t, tt(gt), mp_t, tt(mask_gt), tt(flow), h, w, 'loss')
+    loss.backward()
+    cases['loss_temporal'] = dict(pred=pred, gt=gt, mask_pred=mask_pred, mask_gt=mask_gt, flow=flow, loss=loss.detach().numpy(),
+                                  grad_pred=p_t.grad.numpy(), grad_mask_pred=mp_t.grad.numpy())
+    # get_surf_loss: dense grids x, y (flat [B*h*w]), feature lists padded with the sentinel index h*w
+    b, h, w, p, n_pad = 3, 16, 22, 40, 6
+    x = (np.tile(np.linspace(-1, 1, w), (b, h, 1)) + rng.uniform(-0.05, 0.05, (b, h, w))).astype(np.float32).reshape(-1)
+    y = (np.tile(np.linspace(-1, 1, h)[:, None], (b, 1, w)) + rng.uniform(-0.05, 0.05, (b, h, w))).astype(np.float32).reshape(-1)
+    surf = np.zeros((b, 2, p, 2), np.int32)
+    surf[:, :, :, 0] = rng.integers(0, w, (b, 2, p))
+    surf[:, :, :, 1] = rng.integers(0, h, (b, 2, p))
+    surf[:, 0, -n_pad:, :] = 0                  # data_loader.py:295-308 pads: unstable (0,0), stable index h*w
+    surf[:, 1, -n_pad:, 0] = 0
+    surf[:, 1, -n_pad:, 1] = h
+    max_dim = np.array([p - n_pad, 0, p], np.float32)
+    x_t, y_t = tt(x).requires_grad_(True), tt(y).requires_grad_(True)
+    loss = me.get_surf_loss(tt(surf), x_t, y_t, tt(max_dim), b, w, h)
+    loss.backward()
+    cases['loss_surf'] = dict(surf=surf, x=x, y=y, max_dim=max_dim, hw=np.array([h, w]), loss=loss.detach().numpy(),
+                              grad_x=x_t.grad.numpy(), grad_y=y_t.grad.numpy())
+    return cases
+
+
 def main():
     rng = np.random.default_rng(20261018)
     allc = {}
     allc.update(tps_cases(rng))
     allc.update(sampler_cases(rng))
+    allc.update(loss_cases())
     for name, arrays in allc.items():
         path = os.path.join(OUT, name + '.npz')
         np.savez_compressed(path, **arrays)

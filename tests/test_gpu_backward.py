@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from helpers import smooth_flow, smooth_image, tiled_mesh
+from helpers import close_elementwise, rel_max, smooth_flow, smooth_image, tiled_mesh, tps_flip_correction
 from oracle import dvsg_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -53,13 +53,28 @@ def test_tps_backward_stages_vs_golden(name, merge):
         _, w_inv = O.tps_solve(g['coord'].astype(np.float64), (g['coord'] + g['second']).astype(np.float64), dtype=np.float64, return_inverse=True)
         r_gvec = O.tps_solve_bwd(w_inv, gT.cpu().numpy().astype(np.float64))
         assert rel(gvec.cpu().numpy(), r_gvec) <= 1e-4
-        # end to end against TF-autodiff-equivalent goldens, when no sampling corner flipped
-        _, _, x0, _, y0, _ = O.tps_sample_indices(x, y, g['u'].shape[1], g['u'].shape[2])
-        _, _, gx0, _, gy0, _ = O.tps_sample_indices(g['x'], g['y'], g['u'].shape[1], g['u'].shape[2])
-        if np.array_equal(x0, gx0) and np.array_equal(y0, gy0):
-            tol = 2e-3 if name == 'tps_8x8' else 3e-4
-            assert rel(gvec.cpu().numpy(), g['grad_second']) <= tol
-            assert rel(gU.cpu().numpy(), g['grad_u']) <= tol
+        # element-wise beside the max-norm: |a-b| <= 1e-4 |b| + 1e-5 max|b| on every element of every stage
+        for nm, a, b in (('grad_U', gU, r_gim), ('grad_xs', gxs, r_gx), ('grad_ys', gys, r_gy), ('grad_T', gT, r_gT), ('grad_vector', gvec, r_gvec)):
+            ok, worst, at = close_elementwise(a.cpu().numpy(), b, rtol=1e-4, atol_frac=1e-5)
+            print('%s %s: element-wise worst error / allowance = %.3f' % (name, nm, worst))
+            assert ok, (nm, worst, at)
+        # ---- end to end against the reference's own autodiff (goldens), UNCONDITIONALLY ----
+        # Pixels whose sampling corner differs between the two evaluations (floor of a coordinate within rounding noise
+        # of an integer) change d out/d x discontinuously; their exact effect on grad_vector is computed and removed
+        # (helpers.tps_flip_correction), everything else is compared on all elements.  Yardstick: the fp64 run of the
+        # reference graph -- this kernel must be no farther from it than max(1e-4, 2x the reference's own fp32 run).
+        tgt = g['coord'] + g['second']
+        x64, y64 = g['x64'].astype(np.float32), g['y64'].astype(np.float32)
+        n_k, corr_k = tps_flip_correction(O, g['u'], g['coord'], tgt, (oh, ow), x, y, x64, y64, g['g_out'])
+        n_r, corr_r = tps_flip_correction(O, g['u'], g['coord'], tgt, (oh, ow), g['x'], g['y'], x64, y64, g['g_out'])
+        for nm, ours, ref32, ref64 in (('grad_vector', gvec.cpu().numpy() + corr_k, g['grad_second'] + corr_r, g['grad_second64']),
+                                       ('grad_U', gU.cpu().numpy(), g['grad_u'], g['grad_u64'])):
+            d_ours, d_ref = rel_max(ours, ref64), rel_max(ref32, ref64)
+            print('%s %s e2e: kernel-fp64 %.2e, reference fp32-fp64 %.2e (corner flips excluded exactly: kernel %d, reference %d of %d px)'
+                  % (name, nm, d_ours, d_ref, n_k, n_r, x.size))
+            assert d_ours <= max(1e-4, 2.0 * d_ref), (nm, d_ours, d_ref)
+            ok, worst, at = close_elementwise(ours, ref64, rtol=1e-4, atol_frac=max(1e-4, 2.0 * d_ref))
+            assert ok, (nm, worst, at)
     finally:
         _lib.load().dvsg_set_bwd_tuning(1)
 
@@ -73,8 +88,13 @@ def test_tps_autograd_dropin():
     out, x, y = ThinPlateSpline(U, cu(g['coord']), V, [int(v) for v in g['out_size']])
     loss = (out * cu(g['g_out'])).sum() + (x * cu(g['g_x'])).sum() + (y * cu(g['g_y'])).sum()
     loss.backward()
-    assert rel(V.grad.cpu().numpy(), g['grad_second']) <= 5e-3     # e2e: a flipped corner moves this by O(1e-3)
-    assert rel(U.grad.cpu().numpy(), g['grad_u']) <= 5e-3
+    # end to end through autograd: corner flips removed exactly (see test_tps_backward_stages_vs_golden), then rel <= 1e-4
+    oh, ow = (int(v) for v in g['out_size'])
+    n, corr = tps_flip_correction(O, g['u'], g['coord'], g['coord'] + g['second'], (oh, ow), x.detach().cpu().numpy(), y.detach().cpu().numpy(),
+                                  g['x'], g['y'], g['g_out'])
+    print('dropin e2e: %d corner flips of %d px' % (n, x.numel()))
+    assert rel(V.grad.cpu().numpy() + corr, g['grad_second']) <= 1e-4
+    assert rel(U.grad.cpu().numpy(), g['grad_u']) <= 1e-4
     # grid-only loss (surf loss shape): no image gradient requested
     V2 = cu(g['second']).requires_grad_(True)
     _, x2, y2 = ThinPlateSpline(cu(g['u']), cu(g['coord']), V2, [int(v) for v in g['out_size']])
@@ -105,7 +125,11 @@ def test_tps_backward_vs_oracle_seeded(shape):
     r_gx, r_gy = r_gx.reshape(-1) + gx_in, r_gy.reshape(-1) + gy_in
     assert rel(gU.cpu().numpy(), r_gim) <= 1e-4
     assert rel(gxs.cpu().numpy(), r_gx) <= 1e-4 and rel(gys.cpu().numpy(), r_gy) <= 1e-4
-    assert rel(gT.cpu().numpy(), O.tps_grid_bwd(coord, h, w, gxs.cpu().numpy(), gys.cpu().numpy())) <= 1e-4
+    r_gT = O.tps_grid_bwd(coord, h, w, gxs.cpu().numpy(), gys.cpu().numpy())
+    assert rel(gT.cpu().numpy(), r_gT) <= 1e-4
+    for nm, a, b_ in (('grad_U', gU, r_gim), ('grad_xs', gxs, r_gx), ('grad_ys', gys, r_gy), ('grad_T', gT, r_gT)):
+        ok, worst, at = close_elementwise(a.cpu().numpy().reshape(-1), np.asarray(b_).reshape(-1), rtol=1e-4, atol_frac=1e-5)
+        assert ok, (nm, worst, at)
 
 
 @pytest.mark.parametrize('name', ['bilinear_c18', 'bilinear_c3'])
@@ -285,3 +309,85 @@ def test_flow_warp_backward_vs_oracle_at_720p():
     (tf_warp(I, F, h, w) * cu(g_out)).sum().backward()
     r_gim, r_gflow = O.tf_warp_bwd(im, flow, h, w, g_out)
     assert rel(I.grad.cpu().numpy(), r_gim) <= 1e-4 and rel(F.grad.cpu().numpy(), r_gflow) <= 1e-4
+
+
+def test_mask_variant_is_differentiable_like_the_plain_dropin():
+    """N1 (model.py:81-85): ThinPlateSplineWithMask returns output, x, y WITH a graph -- gradients to U and vector are
+    bit-identical to ThinPlateSpline's (same kernels, same arguments) -- and the mask without one (its gradient is
+    identically zero: the four weights sum to a piecewise constant of the coordinates)."""
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline, ThinPlateSplineWithMask
+    g = load_golden('tps_4x4')
+    osz = [int(v) for v in g['out_size']]
+    grads = []
+    for fn in (ThinPlateSpline, ThinPlateSplineWithMask):
+        U = cu(g['u']).requires_grad_(True)
+        V = cu(g['second']).requires_grad_(True)
+        res = fn(U, cu(g['coord']), V, osz)
+        out, x, y = (res[0], res[1], res[2]) if fn is ThinPlateSpline else (res[0], res[2], res[3])
+        if fn is ThinPlateSplineWithMask:
+            mask = res[1]
+            assert not mask.requires_grad and out.requires_grad and x.requires_grad
+            ones, _, _ = ThinPlateSpline(torch.ones_like(U), cu(g['coord']), cu(g['second']), osz)
+            assert torch.equal(mask.contiguous(), ones.detach())
+            loss = (out * mask * cu(g['g_out'])).sum()           # the mask gates a loss, as in trainer.py:232-243
+        else:
+            ones, _, _ = ThinPlateSpline(torch.ones_like(U), cu(g['coord']), cu(g['second']), osz)
+            loss = (out * ones.detach() * cu(g['g_out'])).sum()
+        (loss + (x * cu(g['g_x'])).sum() + (y * cu(g['g_y'])).sum()).backward()
+        grads.append((U.grad.clone(), V.grad.clone()))
+    # grad_U is accumulated with atomics (order-dependent at the ulp level): compare within fp32 noise; grad_vector too
+    assert rel(grads[1][0].cpu().numpy(), grads[0][0].cpu().numpy()) <= 1e-6
+    assert rel(grads[1][1].cpu().numpy(), grads[0][1].cpu().numpy()) <= 1e-5
+
+
+def test_grad_image_fixed_point_bound_with_1e6_dynamic_range_inside_a_tile():
+    """grad_image of the tile kernel is accumulated in 32-bit fixed point scaled per 32x8 tile from max|grad_out|
+    (DESIGN.md K4): each contribution is rounded to 2^-23 of the TILE's largest gradient -- an ABSOLUTE bound, stated
+    and checked here against the generic kernel's fp32 scatter with grad_out spanning 1e6 inside every tile."""
+    from coupe.dvsg_b200 import _lib, ops
+    torch.manual_seed(11)
+    B, H, W = 2, 64, 128
+    U = torch.rand((B, H, W, 3), device=DEV)
+    coord = cu(tiled_mesh(4, 4, 1)[0]).unsqueeze(0).expand(B, -1, -1)
+    vec = (torch.rand((B, 16, 2), device=DEV) - 0.5) * 0.1
+    T = ops.tps_solve(coord, coord + vec)
+    g = torch.randn((B, H, W, 3), device=DEV) * torch.pow(10.0, -6.0 * torch.rand((B, H, W, 1), device=DEV))
+    lib = _lib.load()
+    try:
+        lib.dvsg_set_bwd_tuning(1)
+        a = ops.tps_warp_bwd(U, coord, T, (H, W), g, None, None)[0]
+        lib.dvsg_set_bwd_tuning(1 | 2)
+        b = ops.tps_warp_bwd(U, coord, T, (H, W), g, None, None)[0]
+    finally:
+        lib.dvsg_set_bwd_tuning(1)
+    # up to ~16 contributions per source pixel, each within 2^-23 of the tile maximum (<= the global maximum here)
+    bound = 16 * 2.0 ** -23 * float(g.abs().max())
+    err = float((a - b).abs().max())
+    print('fixed-point grad_image: max abs deviation %.3e (bound %.3e, max|grad_out| %.3e)' % (err, bound, float(g.abs().max())))
+    assert err <= bound
+
+
+def test_shared_mesh_solve_equals_per_frame_solve_bitwise_on_the_5x5_mesh():
+    """the batched shared-mesh elimination (one CTA, row groups) had a racing store at pivot steps with
+    piv % 8 != 0 (5x5 mesh, k = 1).  Same fp64 Gauss-Jordan, same pivot rule, same operation order as the one-warp-per-
+    frame kernel: the coefficients must agree BIT FOR BIT, run after run."""
+    from coupe.dvsg_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(55)
+    for n in (5, 4, 3):
+        B, pn = 67, n * n
+        mesh = tiled_mesh(n, n, 1)[0]
+        target = (mesh[None] + rng.uniform(-0.1, 0.1, (B, pn, 2))).astype(np.float32)
+        C1, Cb, Tg = cu(mesh), cu(np.tile(mesh[None], (B, 1, 1))), cu(target)
+        outs = []
+        for rep in range(8):
+            Ts = torch.empty((B, 2, pn + 3), device=DEV)
+            assert lib.dvsg_tps_solve(C1.data_ptr(), 0, Tg.data_ptr(), Ts.data_ptr(), B, pn, 0, 0, 0) == 0       # shared kernel
+            outs.append(Ts)
+        Tw = torch.empty((B, 2, pn + 3), device=DEV)
+        assert lib.dvsg_tps_solve(Cb.data_ptr(), 2 * pn, Tg.data_ptr(), Tw.data_ptr(), B, pn, 0, 0, 0) == 0          # warp kernel
+        torch.cuda.synchronize()
+        for Ts in outs:
+            assert torch.equal(Ts, outs[0])
+        # the shared kernel takes 1/pivot by Newton steps and compares pivot magnitudes in fp32: equal up to the last fp32 bit
+        assert float((outs[0] - Tw).abs().max()) <= 2e-7 * float(Tw.abs().max())

@@ -609,3 +609,88 @@ def test_solve_from_offsets_equals_solve_from_the_sum(m):
     assert torch.equal(ops.tps_solve(shared, vec, offsets=True), ops.tps_solve(shared, shared + vec))
     per_frame = shared.contiguous()
     assert torch.equal(ops.tps_solve(per_frame, vec, offsets=True), ops.tps_solve(per_frame, per_frame + vec))
+
+
+def _same_corner_mask(x, y, rx, ry, h, w):
+    _, _, x0, x1, y0, y1 = O.tps_sample_indices(x, y, h, w)
+    _, _, a0, a1, b0, b1 = O.tps_sample_indices(rx, ry, h, w)
+    return (x0 == a0) & (y0 == b0) & (x1 == a1) & (y1 == b1)
+
+
+def test_tps_forward_vs_oracle_one_full_cfg2_frame():
+    """BASELINE configs[1] shape, one whole 720 x 1280 frame, 4x4 mesh, offsets +-0.1, against O.thin_plate_spline ITSELF:
+    coordinates <= 2e-5, pixels <= 1e-4 where both coordinate sets pick the same corners, flips <= 0.5 % and
+    the flipped pixels' error bounded too (bilinear interpolation is C0 across a flip); sampler bit-exact."""
+    b, h, w, c, m = 1, 720, 1280, 3, 4
+    rng = np.random.default_rng(720)
+    u = smooth_image(rng, b, h, w, c, period=48.0)
+    coord = tiled_mesh(m, m, b)
+    vec = rng.uniform(-0.1, 0.1, coord.shape).astype(np.float32)
+    out, x, y, T = run_tps(u, coord, vec, (h, w), 1, 0)
+    r_out, r_x, r_y = O.thin_plate_spline(u, coord, vec, (h, w))
+    ex = max(np.abs(x - r_x).max(), np.abs(y - r_y).max())
+    same = _same_corner_mask(x, y, r_x, r_y, h, w).reshape(b, h, w)
+    err = np.abs(out - r_out).max(axis=-1)
+    e_same, e_flip = err[same].max(), (err[~same].max() if (~same).any() else 0.0)
+    print('720p full frame: coord err %.2e, pixel err %.2e on same corners, %.2e on the %d flipped px (%.4f%%)' %
+          (ex, e_same, e_flip, int((~same).sum()), 100.0 * (1.0 - same.mean())))
+    assert ex <= 2e-5 and e_same <= 1e-4 and e_flip <= 2e-4 and (1.0 - same.mean()) <= 5e-3
+    np.testing.assert_array_equal(out, O.tps_interpolate(u, x, y, h, w).reshape(out.shape))
+
+
+def test_tps_forward_vs_oracle_one_full_cfg5_frame():
+    """BASELINE configs[4] shape: ONE WHOLE 2160 x 3840 frame with the 16x16 mesh (N = 259) against the oracle, in row
+    bands (the reference's basis for this frame is 8.6 GB; O.tps_grid(rows=...) evaluates the same element-wise ops band by
+    band).  The fp32 SOLVE of the reference is ill-conditioned here (cond 3.9e4: its coefficients carry 1.6e-3 of noise,
+    SURVEY H4), so the grid stage is fed with the kernel's own coefficients, as in
+    test_large_mesh_grid_stage_vs_oracle_on_the_kernels_coefficients.  Bars, every pixel of the frame:
+      * coordinates no farther from the fp64 evaluation than 2x the fp32 oracle's own distance to it, and <= 3e-5;
+      * pixels on same-corner samples <= 1e-4 + 2x the fp32 oracle's own pixel distance to the fp64 run (one fp32 ulp of a
+        coordinate is 2.4e-4 px at W = 3840: SURVEY H3);
+      * sampler stage bit-exact on the kernel's own coordinates."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    from coupe.dvsg_b200 import ops
+    b, h, w, c, m = 1, 2160, 3840, 3, 16
+    rng = np.random.default_rng(2160)
+    # periods >= 512 px: |dI/dx| <~ 0.006 per px, so that the 1e-4 pixel bar is about the arithmetic and not about the
+    # 0.02 px of fp32 noise any 259-term fp32 sum carries at this width
+    u = smooth_image(rng, b, h, w, c, period=512.0)
+    coord = tiled_mesh(m, m, b)
+    vec = rng.uniform(-0.02, 0.02, coord.shape).astype(np.float32)
+    U, C_ = cu(u), cu(coord)
+    T = ops.tps_solve(C_, C_ + cu(vec))
+    out, x, y, _ = ops.tps_warp_fwd(U, C_, T, (h, w), want_grid=True)
+    torch.cuda.synchronize()
+    out, x, y, Tn = out.cpu().numpy(), x.cpu().numpy().reshape(h, w), y.cpu().numpy().reshape(h, w), T.cpu().numpy()
+    np.testing.assert_array_equal(out, O.tps_interpolate(u, x.reshape(-1), y.reshape(-1), h, w).reshape(out.shape))
+    T64, c64 = Tn.astype(np.float64), coord.astype(np.float64)
+    band = 36
+
+    def one(r0):
+        rows = (r0, min(r0 + band, h))
+        x32, y32 = O.tps_grid(Tn, coord, h, w, rows=rows)
+        x64, y64 = O.tps_grid(T64, c64, h, w, dtype=np.float64, rows=rows)
+        xk, yk = x[rows[0]:rows[1]].reshape(-1), y[rows[0]:rows[1]].reshape(-1)
+        e_k = max(np.abs(xk - x64).max(), np.abs(yk - y64).max())
+        e_o = max(np.abs(x32 - x64).max(), np.abs(y32 - y64).max())
+        nb = rows[1] - rows[0]
+        o32 = O.tps_interpolate(u, x32, y32, nb, w)
+        o64 = O.tps_interpolate(u.astype(np.float64), x64, y64, nb, w, dtype=np.float64)
+        ok = out[0, rows[0]:rows[1]].reshape(-1, c)
+        s_k = _same_corner_mask(xk, yk, x32, y32, h, w)
+        s_o = _same_corner_mask(x32, y32, x64.astype(np.float32), y64.astype(np.float32), h, w)
+        p_k = np.abs(ok - o32).max(axis=1)
+        p_o = np.abs(o32 - o64).max(axis=1)
+        return e_k, e_o, (p_k[s_k].max() if s_k.any() else 0.0), (p_o[s_o].max() if s_o.any() else 0.0), int((~s_k).sum())
+
+    with ThreadPoolExecutor(max_workers=max(1, min(os.cpu_count() or 1, 12))) as ex:
+        res = list(ex.map(one, range(0, h, band)))
+    e_k, e_o = max(r[0] for r in res), max(r[1] for r in res)
+    p_k, p_o = max(r[2] for r in res), max(r[3] for r in res)
+    flips = sum(r[4] for r in res)
+    print('4K 16x16 full frame: |kernel - fp64| %.2e vs |fp32 oracle - fp64| %.2e; pixels (same corners) kernel-oracle %.2e, '
+          'oracle fp32-fp64 %.2e; corner flips %d of %d px' % (e_k, e_o, p_k, p_o, flips, h * w))
+    assert e_k <= max(2.0 * e_o, 1e-5) and e_k <= 3e-5
+    assert p_k <= 1e-4 + 2.0 * p_o
+    assert flips <= 5e-3 * h * w

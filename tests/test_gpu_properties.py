@@ -1,0 +1,96 @@
+"""Property tests (hypothesis) of the forward path against the oracle -- SURVEY.md section 4 "Property" tier: random
+meshes and offsets, odd sizes (H, W not multiples of 4 or of the 32x8 tile), C in {1, 3, 18}, out_size != in_size,
+coordinates far outside the frame.  Every example is checked against the oracle at the stated bars: coordinates <= 2e-5,
+pixels <= 1e-4 on band-limited frames where the corners agree, sampler / tf_warp / bilinear_interp BIT-EXACT."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from helpers import smooth_image, tiled_mesh
+from oracle import dvsg_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+SETTINGS = dict(max_examples=25, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+sizes = st.tuples(st.integers(1, 3), st.integers(2, 75), st.integers(2, 90))
+
+
+@settings(**SETTINGS)
+@given(shape=sizes, c=st.sampled_from([1, 3, 18]), m=st.integers(2, 6), amp=st.sampled_from([0.0, 0.05, 0.2, 0.6]),
+       resize=st.booleans(), jitter=st.booleans(), seed=st.integers(0, 2 ** 16))
+def test_thin_plate_spline_matches_the_oracle(shape, c, m, amp, resize, jitter, seed):
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline
+    b, h, w = shape
+    rng = np.random.default_rng(seed)
+    oh, ow = (int(rng.integers(1, 70)), int(rng.integers(1, 80))) if resize else (h, w)
+    u = smooth_image(rng, b, h, w, c, period=max(8.0, min(h, w) / 2.0))
+    coord = tiled_mesh(m, m, b)
+    if jitter:      # irregular, per-frame meshes (kept apart: distinct control points)
+        coord = (coord + rng.uniform(-0.3, 0.3, coord.shape) / m).astype(np.float32)
+    vec = rng.uniform(-amp, amp, coord.shape).astype(np.float32)
+    from coupe.dvsg_b200 import ops
+    out, x, y = ThinPlateSpline(cu(u), cu(coord), cu(vec), [oh, ow])
+    T = ops.tps_solve(cu(coord), cu(coord) + cu(vec)).cpu().numpy()
+    torch.cuda.synchronize()
+    out, x, y = out.cpu().numpy(), x.cpu().numpy(), y.cpu().numpy()
+    assert out.shape == (b, oh, ow, c) and x.shape == (b * oh * ow,)
+    r_out, r_x, r_y = O.thin_plate_spline(u, coord, vec, (oh, ow))
+    # Coordinates: <= 2e-5 in every reference-like setting.  The fp32 noise of ANY evaluation of the spline (the
+    # reference's own sequential fp32 sum included: measured 2e-7 + 4e-7 * sum|c_k| against fp64) grows with the mass of
+    # the radial coefficients, which only strongly folded meshes (offsets +-0.6 on 6x6) push past 10: scale the bar there.
+    mass = float(np.abs(T[:, :, 3:]).sum(axis=2).max())
+    tol = max(2e-5, 1e-5 + 1.5e-6 * mass)
+    assert max(np.abs(x - r_x).max(), np.abs(y - r_y).max()) <= tol, (mass, tol)
+    np.testing.assert_array_equal(out, O.tps_interpolate(u, x, y, oh, ow).reshape(out.shape))
+    _, _, x0, x1, y0, y1 = O.tps_sample_indices(x, y, h, w)
+    _, _, a0, a1, b0, b1 = O.tps_sample_indices(r_x, r_y, h, w)
+    same = ((x0 == a0) & (y0 == b0) & (x1 == a1) & (y1 == b1)).reshape(b, oh, ow)
+    if same.any():
+        # outside the frame the clamped corners' weights are +-|distance|: the pixel is a difference of products that
+        # large, so the bar scales with the distance there (the reference's own rounding noise does)
+        xp, yp, _, _, _, _ = O.tps_sample_indices(r_x, r_y, h, w)
+        far = np.maximum(np.maximum(-xp, xp - (w - 1)), np.maximum(-yp, yp - (h - 1))).reshape(b, oh, ow)
+        allow = 1e-4 * np.maximum(1.0, far) ** 2
+        assert np.all((np.abs(out - r_out).max(axis=-1) <= allow)[same])
+
+
+@settings(**SETTINGS)
+@given(shape=sizes, c=st.sampled_from([1, 3, 18]), resize=st.booleans(), spread=st.sampled_from([0.9, 1.3, 40.0]),
+       seed=st.integers(0, 2 ** 16))
+def test_bilinear_interp_is_bit_exact(shape, c, resize, spread, seed):
+    from coupe.dvsg_b200.spatial_transformer import bilinear_interp
+    b, h, w = shape
+    rng = np.random.default_rng(seed)
+    oh, ow = (int(rng.integers(1, 70)), int(rng.integers(1, 80))) if resize else (h, w)
+    im = rng.random((b, h, w, c), dtype=np.float32)
+    n = b * oh * ow
+    x = rng.uniform(-spread, spread, n).astype(np.float32)
+    y = rng.uniform(-spread, spread, n).astype(np.float32)
+    k = min(n, 5)       # exact borders, the 1-px fade, infinities (clipped to the padding like any far coordinate)
+    x[:k] = np.array([-1.0, 1.0, 1.0 + 2.0 / max(w - 1, 1), np.inf, -np.inf], np.float32)[:k]
+    y[:k] = np.array([1.0, -1.0, 0.0, 0.0, 0.3], np.float32)[:k]
+    out = bilinear_interp(cu(im), cu(x), cu(y), [oh, ow]).cpu().numpy()
+    with np.errstate(invalid='ignore'):
+        ref = O.bilinear_interp(im, x, y, (oh, ow))
+    np.testing.assert_array_equal(out, ref)
+
+
+@settings(**SETTINGS)
+@given(shape=sizes, c=st.sampled_from([1, 3, 18]), amp=st.sampled_from([0.0, 0.7, 5.0, 300.0]), seed=st.integers(0, 2 ** 16))
+def test_tf_warp_is_bit_exact(shape, c, amp, seed):
+    from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+    b, h, w = shape
+    rng = np.random.default_rng(seed)
+    im = rng.random((b, h, w, c), dtype=np.float32)
+    flow = rng.uniform(-amp, amp, (b, h, w, 2)).astype(np.float32)
+    if amp == 0.7:
+        flow = np.round(flow)       # integer shifts: exact copies of source pixels (or zeros from the padding)
+    out = tf_warp(cu(im), cu(flow), h, w).cpu().numpy()
+    np.testing.assert_array_equal(out, O.tf_warp(im, flow, h, w))

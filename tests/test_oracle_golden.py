@@ -90,3 +90,29 @@ def test_tf_warp(name):
     g_im, g_flow = O.tf_warp_bwd(g['im'], g['flow'], h, w, g['g_out'])
     assert np.abs(g_im - g['grad_im']).max() <= 2e-6
     assert np.abs(g_flow - g['grad_flow']).max() <= 2e-6
+
+
+# ---- N3: the loss consumers of the warp outputs, pinned by trainer.py's own method bodies (make_golden.loss_cases) ----
+def test_masked_mse_vs_reference_golden():
+    g = load_golden('loss_masked_mse')
+    loss, sq, ms = O.masked_mse(g['pred'], g['gt'], g['mask'])
+    assert abs(loss - float(g['loss'])) <= 1e-6 * abs(float(g['loss']))
+    assert ms[1] == 0.0 and sq[1] == 0.0            # the fully masked frame: div_no_nan -> 0
+
+
+def test_temporal_loss_vs_reference_golden():
+    g = load_golden('loss_temporal')
+    h, w = g['pred'].shape[1:3]
+    pw = O.tf_warp(g['pred'], g['flow'], h, w)
+    mw = O.tf_warp(g['mask_pred'], g['flow'], h, w)
+    loss, _, _ = O.masked_mse(pw, g['gt'], (mw * g['mask_gt']).astype(np.float32))
+    assert abs(loss - float(g['loss'])) <= 1e-6 * abs(float(g['loss']))
+
+
+def test_surf_loss_vs_reference_golden():
+    g = load_golden('loss_surf')
+    h, w = (int(v) for v in g['hw'])
+    b = g['surf'].shape[0]
+    loss, idx = O.surf_loss(g['surf'], g['x'], g['y'], g['max_dim'], b, w, h)
+    assert abs(loss - float(g['loss'])) <= 1e-6 * abs(float(g['loss']))
+    assert idx.max() == h * w                        # padded features hit the appended -1 entry (trainer.py:364-365)
