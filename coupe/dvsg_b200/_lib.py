@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get('DVSG_LIB') or os.path.join(HERE, 'libdvsg_warp.so')
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 FLAG_FORCE_DIRECT = 1
+FLAG_TPS_EXACT = 2
 
 _P = c_void_p
 # name -> (restype, argtypes); mirrors include/dvsg_warp.h one to one
@@ -33,6 +34,8 @@ PROTOTYPES = {
     'dvsg_tps_warp_fwd': (c_int, [_P, _P, c_longlong, _P, _P, _P, _P, _P] + [c_int] * 8 + [_P]),
     'dvsg_tps_warp_frames': (c_int, [_P, _P, _P, _P, c_size_t, _P, _P, _P, _P, _P] + [c_int] * 7 + [_P]),
     'dvsg_tps_warp_frames_offsets': (c_int, [_P, _P, _P, _P, c_size_t, _P, _P, _P, _P, _P] + [c_int] * 7 + [_P]),
+    'dvsg_tps_coords_mode': (c_int, [c_int] * 7),
+    'dvsg_tps_warp_bwd_ex': (c_int, [_P, _P, c_longlong, _P, _P, _P, _P, _P, _P, _P, _P] + [c_int] * 8 + [_P]),
     'dvsg_tps_warp_bwd': (c_int, [_P, _P, c_longlong, _P, _P, _P, _P, _P, _P, _P, _P] + [c_int] * 7 + [_P]),
     'dvsg_bilinear_fwd': (c_int, [_P, _P, _P, _P] + [c_int] * 7 + [_P]),
     'dvsg_bilinear_bwd': (c_int, [_P, _P, _P, _P, _P, _P, _P] + [c_int] * 6 + [_P]),

@@ -5,6 +5,7 @@
 
 #include "dvsg_common.cuh"
 #include "sampler_math.cuh"
+#include "node_tables.cuh"
 
 namespace dvsg {
 
@@ -43,6 +44,7 @@ struct TileParams {
     int n_tx, n_ty;       // tiles per strip / strips per frame
     int segs, seg_len;    // CTAs per strip, tiles per CTA
     float one;            // 1.0f, opaque to ptxas: add2x() below
+    int nodes;            // TPS: tile-node evaluation of the map (default) instead of the per-pixel one
 };
 
 // staging boxes (floats wide x rows): pitch = 512 or 640 B keeps the row pitch a multiple of 128 B, so the
@@ -243,6 +245,243 @@ __device__ __forceinline__ void tile_tps_basis_sep(const unsigned char* __restri
                 X[j] = __ffma2_rn(cfx, r, X[j]);
                 Y[j] = __ffma2_rn(cfy, r, Y[j]);
             }
+        }
+    }
+}
+
+// ---- tile-node evaluation of the TPS map (the default of the tile kernels; DVSG_FLAG_TPS_EXACT selects the per-pixel one) ---
+// The radial part of the spline, sum_k c_k d2_k log(d2_k + 1e-6), is smooth away from the control points (its fourth
+// derivative falls off like 1/d2), and a 32 x 8-pixel tile is small against the spacing of the control mesh.  So instead
+// of one logarithm per (pixel, control point) -- the XU pipe's and the issue slots' largest customer, 8 x pn MUFU.LG2 per
+// lane and tile -- the FAR field of a tile is evaluated at NNX x NNY = 6 x 5 Chebyshev nodes (one node per lane: pn
+// logarithms per lane and tile) and interpolated to the 256 pixels with the tensor-product Lagrange basis of
+// node_tables.cuh, while the few control points NEAR the tile (inside the tile's box grown by NODE_NEAR_X / NODE_NEAR_Y
+// pixels: 0.3 per tile on average for a 4x4 mesh at 1080p) are evaluated per pixel with the reference's own formula
+// d2 log(d2 + 1e-6).  Approximation error of the far field (fp64 study, tools/proto_nodes.py): <= 2e-7 normalised units
+// at 288 x 512 for every mesh of BASELINE.json, <= 1e-8 from 720p up -- below the fp32 rounding noise of the
+// reference's own pn-term sum (2e-6 at 4x4, 1e-5 at 16x16).  The forward and the backward tile kernels share this code
+// and the tile grid, so both see bit-identical coordinates.
+constexpr float NODE_NEAR_X = 48.0f, NODE_NEAR_Y = 24.0f;     // margins of the near box, pixels
+constexpr int NODE_MAX_NEAR = 32;                             // row-near control points kept per strip (more: all-exact strip)
+constexpr float TPS_EPS_LG2 = 1.4426950408889634e-6f;         // 1e-6 / ln 2
+
+struct NodeTables {             // per CTA, in dynamic shared memory (all offsets 16-byte aligned)
+    float4* cp;                 // [pn4] (px, py, cx ln2, cy ln2); padding entries have zero coefficients
+    float* gxy;                 // [2][TKS] separable meshes: x of the mesh columns, y of the mesh rows
+    int* near_cnt;              // [0] number of row-near control points of this strip; < 0: treat ALL control points as near
+                                // [1] 1 when the frame's mesh is separable (G x G, control point k = (gx[k % G], gy[k / G]))
+    int* near_idx;              // [NODE_MAX_NEAR] their indices, ascending
+    float* near_col;            // [NODE_MAX_NEAR] their column position in output pixels
+};
+constexpr int TKS = 16;         // largest separable mesh side with a specialised node pass
+__host__ __device__ inline size_t node_tables_bytes(int pn) {
+    return (size_t)((pn + 3) & ~3) * 16 + 2 * TKS * 4 + 16 + NODE_MAX_NEAR * 8;
+}
+__device__ __forceinline__ NodeTables node_tables_at(unsigned char* base, int pn) {
+    NodeTables t;
+    const int pn4 = (pn + 3) & ~3;
+    t.cp = reinterpret_cast<float4*>(base);
+    t.gxy = reinterpret_cast<float*>(base + (size_t)pn4 * 16);
+    t.near_cnt = reinterpret_cast<int*>(base + (size_t)pn4 * 16 + 2 * TKS * 4);
+    t.near_idx = t.near_cnt + 4;
+    t.near_col = reinterpret_cast<float*>(t.near_idx + NODE_MAX_NEAR);
+    return t;
+}
+// Tables of one strip (rows row0 .. row0+TR-1).  Called by the whole CTA (>= 2 warps) before its barrier; contains one CTA
+// barrier of its own when G > 0 (separability test).
+template <int G>
+__device__ __forceinline__ void tile_node_tables(const float* __restrict__ Tb, const float* __restrict__ cb, int pn, int row0, int oh,
+                                                 float step_x, float step_y, int tid, int nthreads, float* s_lin, const NodeTables& nt) {
+    const int N = pn + 3, pn4 = (pn + 3) & ~3, lane = tid & 31, warp = tid >> 5;
+    if (G > 0) {
+        bool ok = true;
+        for (int k = tid; k < G * G; k += nthreads)
+            ok = ok && __ldg(cb + 2 * k) == __ldg(cb + 2 * (k % G)) && __ldg(cb + 2 * k + 1) == __ldg(cb + 2 * (k / G * G) + 1);
+        const int sep = __syncthreads_and(ok);
+        if (tid == 0) nt.near_cnt[1] = sep;
+        if (tid < G) { nt.gxy[tid] = __ldg(cb + 2 * tid); nt.gxy[TKS + tid] = __ldg(cb + 2 * (tid * G) + 1); }
+    } else if (tid == 0) {
+        nt.near_cnt[1] = 0;
+    }
+    if (warp < 2) {
+        const float c0 = tps_affine0(Tb + warp * N, pn, lane);      // constant + 1e-6 * sum_k c_k (the far field's folded epsilon)
+        if (lane == 0) s_lin[3 * warp] = c0;
+        else if (lane < 3) s_lin[3 * warp + lane] = __ldg(Tb + warp * N + lane);
+    }
+    for (int k = tid; k < pn4; k += nthreads) {
+        const bool real = k < pn;
+        nt.cp[k] = real ? make_float4(__ldg(cb + 2 * k), __ldg(cb + 2 * k + 1), __ldg(Tb + 3 + k) * TLN2, __ldg(Tb + N + 3 + k) * TLN2)
+                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    if (warp == nthreads / 32 - 1) {
+        // row-near control points, in index order (ballot compaction: the order fixes the summation order of the near field)
+        const float inv_sy = step_y > 0.0f ? 1.0f / step_y : 0.0f, inv_sx = step_x > 0.0f ? 1.0f / step_x : 0.0f;
+        const float lo = (float)row0 - NODE_NEAR_Y, hi = (float)(row0 + TR - 1) + NODE_NEAR_Y;
+        int cnt = 0;
+        for (int base = 0; base < pn; base += 32) {
+            const int k = base + lane;
+            bool f = false;
+            float ccol = 0.0f;
+            if (k < pn) {
+                const float crow = (__ldg(cb + 2 * k + 1) + 1.0f) * inv_sy;
+                ccol = (__ldg(cb + 2 * k) + 1.0f) * inv_sx;
+                f = crow > lo && crow < hi;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+            if (f && pos < NODE_MAX_NEAR) { nt.near_idx[pos] = k; nt.near_col[pos] = ccol; }
+            cnt += __popc(m);
+        }
+        if (lane == 0) nt.near_cnt[0] = cnt <= NODE_MAX_NEAR ? cnt : -1;
+    }
+}
+// exact contribution of control point cp to the lane's 8 pixels: c * d2 * log(d2 + 1e-6) as the reference writes it
+// (ThinPlateSpline.py:104-105), minus the 1e-6 * c that the affine constant already carries for every control point
+__device__ __forceinline__ void node_near_term(const float4 cp, const float xt, const float* __restrict__ s_yt, float2 (&X)[TR / 2],
+                                               float2 (&Y)[TR / 2]) {
+    const float dx = xt - cp.x;
+    const float2 dxx = f2dup(dx * dx), npy = f2dup(-cp.y), cfx = f2dup(cp.z), cfy = f2dup(cp.w);
+#pragma unroll
+    for (int j = 0; j < TR / 2; ++j) {
+        const float2 dy = __fadd2_rn(*reinterpret_cast<const float2*>(s_yt + 2 * j), npy);
+        const float2 d2 = __ffma2_rn(dy, dy, dxx);
+        const float2 t = __fadd2_rn(d2, f2dup(TPS_EPS));
+        const float2 r = __ffma2_rn(d2, f2(lg2_approx(t.x), lg2_approx(t.y)), f2dup(-TPS_EPS_LG2));
+        X[j] = __ffma2_rn(cfx, r, X[j]);
+        Y[j] = __ffma2_rn(cfy, r, Y[j]);
+    }
+}
+// far-field value of one control point at this lane's node (the same expression is added for every control point and
+// subtracted again for the tile's near ones, so the two cancel to the last bit of the running sum's rounding)
+__device__ __forceinline__ void node_far_term(const float4 cp, const float xn, const float yn, const float sign, float& fx, float& fy) {
+    const float dx = xn - cp.x, dy = yn - cp.y;
+    const float d2 = fmaf(dx, dx, fmaf(dy, dy, TPS_TINY));
+    const float r = d2 * lg2_approx(d2) * sign;
+    fx = fmaf(cp.z, r, fx);
+    fy = fmaf(cp.w, r, fy);
+}
+// Lagrange weights of this lane's column (li = local column; lanes past the frame edge take the edge pixel's)
+__device__ __forceinline__ void node_load_lx(const int li, float (&lx)[NNX]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(&NODE_LX[li][0]));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(&NODE_LX[li][4]));
+    lx[0] = a.x; lx[1] = a.y; lx[2] = a.z; lx[3] = a.w; lx[4] = b.x; lx[5] = b.y;
+}
+// Normalised sampling coordinates of the lane's 8 pixels (column `xt`, rows of s_yt) of the tile starting at column col0.
+//   lx      Lagrange weights of this lane's column (node_load_lx)
+//   xoff_l  NODE_XOFF of this lane's node, yn: normalised y of this lane's node (strip constants)
+//   rows_ok rows of the strip inside the frame (rows past it repeat the last one, as the exact evaluation does)
+//   w_nodes per-warp exchange buffer, 32 float2
+// Warp-collective (contains __syncwarp); every lane of the warp must call it.
+template <int G>
+__device__ __forceinline__ void tile_node_coords(const NodeTables& nt, const int pn, const float* __restrict__ s_lin, const float* __restrict__ s_yt,
+                                                 const int col0, const float (&lx)[NNX], const float xt, const float xoff_l, const float yn,
+                                                 const float step_x, const int rows_ok, float2* __restrict__ w_nodes, const int lane,
+                                                 float2 (&X)[TR / 2], float2 (&Y)[TR / 2]) {
+    const int pn4 = (pn + 3) & ~3;
+    const int n_row_near = nt.near_cnt[0];
+    if (n_row_near < 0) {      // degenerate strip (tiny frame under a dense mesh): every control point per pixel
+        const float bx = fmaf(s_lin[1], xt, s_lin[0]), by = fmaf(s_lin[4], xt, s_lin[3]);
+#pragma unroll
+        for (int j = 0; j < TR / 2; ++j) {
+            const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
+            X[j] = __ffma2_rn(f2dup(s_lin[2]), ytp, f2dup(bx));
+            Y[j] = __ffma2_rn(f2dup(s_lin[5]), ytp, f2dup(by));
+        }
+        for (int k = 0; k < pn; ++k) node_near_term(nt.cp[k], xt, s_yt, X, Y);
+        return;
+    }
+    // the tile's near control points: row-near ones whose column lies within the grown tile box (warp-uniform bit mask)
+    unsigned near = 0;
+    {
+        const float lo = (float)col0 - NODE_NEAR_X, hi = (float)(col0 + TC - 1) + NODE_NEAR_X;
+        for (int i = 0; i < n_row_near; ++i) {
+            const float c = nt.near_col[i];
+            if (c > lo && c < hi) near |= 1u << i;
+        }
+    }
+    // far field at this lane's node: all control points, then the near ones taken out again
+    float fx = 0.0f, fy = 0.0f;
+    {
+        const float xn = fmaf(step_x, (float)col0 + xoff_l, -1.0f);
+        const float4* __restrict__ cp = nt.cp;
+        if (G > 0 && nt.near_cnt[1]) {
+            // separable mesh: (x_n - gx)^2 once per mesh column, (y_n - gy)^2 once per mesh row, 5 instructions per control point
+            constexpr int GG = G > 0 ? G : 1;
+            float dx2[GG];
+#pragma unroll
+            for (int g = 0; g < GG; ++g) { const float d = xn - nt.gxy[g]; dx2[g] = d * d; }
+#pragma unroll 1
+            for (int gy = 0; gy < GG; ++gy) {
+                const float d = yn - nt.gxy[TKS + gy];
+                const float dy2 = fmaf(d, d, TPS_TINY);
+#pragma unroll
+                for (int g = 0; g < GG; ++g) {
+                    const float2 c = *reinterpret_cast<const float2*>(&cp[gy * GG + g].z);
+                    const float d2 = dx2[g] + dy2;
+                    const float r = d2 * lg2_approx(d2);
+                    fx = fmaf(c.x, r, fx);
+                    fy = fmaf(c.y, r, fy);
+                }
+            }
+        } else {
+            for (int k = 0; k < pn4; k += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) node_far_term(cp[k + u], xn, yn, 1.0f, fx, fy);
+            }
+        }
+        for (unsigned m = near; m; m &= m - 1) node_far_term(cp[nt.near_idx[__ffs(m) - 1]], xn, yn, -1.0f, fx, fy);
+    }
+    w_nodes[lane] = make_float2(fx, fy);
+    __syncwarp();
+    // interpolation, x direction: G[b] = sum_a Lx[a](column) * F[a + NNX b]
+    float gx[NNY], gy[NNY];
+    {
+        const float4* __restrict__ f4 = reinterpret_cast<const float4*>(w_nodes);      // two nodes per 16-byte load
+#pragma unroll
+        for (int b = 0; b < NNY; ++b) { gx[b] = 0.0f; gy[b] = 0.0f; }
+#pragma unroll
+        for (int q = 0; q < NNX * NNY / 2; ++q) {
+            const float4 v = f4[q];
+            const int n0 = 2 * q, n1 = 2 * q + 1;
+            gx[n0 / NNX] = fmaf(lx[n0 % NNX], v.x, gx[n0 / NNX]);
+            gy[n0 / NNX] = fmaf(lx[n0 % NNX], v.y, gy[n0 / NNX]);
+            gx[n1 / NNX] = fmaf(lx[n1 % NNX], v.z, gx[n1 / NNX]);
+            gy[n1 / NNX] = fmaf(lx[n1 % NNX], v.w, gy[n1 / NNX]);
+        }
+    }
+    // affine part + y direction onto the lane's 8 rows (row weights are compile-time constants)
+    {
+        const float bx = fmaf(s_lin[1], xt, s_lin[0]), by = fmaf(s_lin[4], xt, s_lin[3]);
+        const float2 l2 = f2dup(s_lin[2]), l5 = f2dup(s_lin[5]);
+#pragma unroll
+        for (int j = 0; j < TR / 2; ++j) {
+            const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
+            X[j] = __ffma2_rn(l2, ytp, f2dup(bx));
+            Y[j] = __ffma2_rn(l5, ytp, f2dup(by));
+        }
+#pragma unroll
+        for (int b = 0; b < NNY; ++b) {
+            const float2 gxb = f2dup(gx[b]), gyb = f2dup(gy[b]);
+#pragma unroll
+            for (int j = 0; j < TR / 2; ++j) {
+                const float2 m = f2(NODE_MY[b][2 * j], NODE_MY[b][2 * j + 1]);
+                X[j] = __ffma2_rn(m, gxb, X[j]);
+                Y[j] = __ffma2_rn(m, gyb, Y[j]);
+            }
+        }
+    }
+    // near field, per pixel
+    for (unsigned m = near; m; m &= m - 1) node_near_term(nt.cp[nt.near_idx[__ffs(m) - 1]], xt, s_yt, X, Y);
+    if (rows_ok < TR) {      // last strip of a frame whose height is not a multiple of 8: rows past the frame repeat its last row
+        const int rl = rows_ok - 1;
+        float xl = X[0].x, yl = Y[0].x;
+#pragma unroll
+        for (int q = 1; q < TR; ++q)
+            if (q == rl) { xl = (q & 1) ? X[q >> 1].y : X[q >> 1].x; yl = (q & 1) ? Y[q >> 1].y : Y[q >> 1].x; }
+#pragma unroll
+        for (int j = 0; j < TR / 2; ++j) {
+            if (2 * j > rl) { X[j].x = xl; Y[j].x = yl; }
+            if (2 * j + 1 > rl) { X[j].y = xl; Y[j].y = yl; }
         }
     }
 }

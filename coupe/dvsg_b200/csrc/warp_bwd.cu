@@ -333,7 +333,7 @@ static int g_bwd_notile = 0;   // experiments: force this generic kernel
 bool bwd_tile_path_ok(const void* src, const void* grad_src, int H, int W, int C, int oh, int ow, int pn_or_0);
 int bwd_tile_tps(const float* U, const float* coord, long long cstride, const float* T, const float* grad_out, const float* grad_x_in,
                  const float* grad_y_in, float* grad_U, float* grad_T, float* grad_xs, float* grad_ys, int B, int H, int W, int oh, int ow,
-                 int pn, cudaStream_t st);
+                 int pn, int flags, cudaStream_t st);
 int bwd_tile_given(const float* im, const float* x, const float* y, const float* grad_out, float* grad_im, float* grad_x, float* grad_y,
                    int B, int H, int W, int oh, int ow, cudaStream_t st);
 int bwd_tile_flow(const float* im, const float* flow, const float* grad_out, float* grad_im, float* grad_flow, int B, int H, int W,
@@ -361,10 +361,22 @@ extern "C" int dvsg_set_bwd_tuning(int merge) {
     return DVSG_OK;
 }
 
+extern "C" int dvsg_tps_warp_bwd_ex(const float* U, const float* coord, long long coord_batch_stride, const float* T,
+                                    const float* grad_out, const float* grad_x_in, const float* grad_y_in, float* grad_U,
+                                    float* grad_T, float* grad_xs, float* grad_ys, int B, int H, int W, int C, int oh, int ow,
+                                    int pn, int flags, void* stream);
 extern "C" int dvsg_tps_warp_bwd(const float* U, const float* coord, long long coord_batch_stride, const float* T,
                                  const float* grad_out, const float* grad_x_in, const float* grad_y_in, float* grad_U,
                                  float* grad_T, float* grad_xs, float* grad_ys, int B, int H, int W, int C, int oh, int ow,
                                  int pn, void* stream) {
+    return dvsg_tps_warp_bwd_ex(U, coord, coord_batch_stride, T, grad_out, grad_x_in, grad_y_in, grad_U, grad_T, grad_xs, grad_ys, B, H, W, C, oh,
+                                ow, pn, 0, stream);
+}
+
+extern "C" int dvsg_tps_warp_bwd_ex(const float* U, const float* coord, long long coord_batch_stride, const float* T,
+                                    const float* grad_out, const float* grad_x_in, const float* grad_y_in, float* grad_U,
+                                    float* grad_T, float* grad_xs, float* grad_ys, int B, int H, int W, int C, int oh, int ow,
+                                    int pn, int flags, void* stream) {
     DVSG_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && oh >= 0 && ow >= 0 && pn > 0, "tps_warp_bwd: bad shape");
     DVSG_REQUIRE(B == 0 || (U && coord && T && grad_out), "tps_warp_bwd: null pointer");
     DVSG_REQUIRE((grad_x_in == nullptr) == (grad_y_in == nullptr), "tps_warp_bwd: grad_x_in and grad_y_in go together");
@@ -380,7 +392,7 @@ extern "C" int dvsg_tps_warp_bwd(const float* U, const float* coord, long long c
     }
     if (!g_bwd_notile && bwd_tile_path_ok(U, grad_U, H, W, C, oh, ow, pn))
         return B == 0 ? DVSG_OK : bwd_tile_tps(U, coord, coord_batch_stride, T, grad_out, grad_x_in, grad_y_in, grad_U, grad_T, grad_xs, grad_ys,
-                                               B, H, W, oh, ow, pn, st);
+                                               B, H, W, oh, ow, pn, flags, st);
     BwdParams p = {};
     p.src = U; p.grad_out = grad_out; p.grad_src = grad_U; p.grad_x = grad_xs; p.grad_y = grad_ys;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow;

@@ -31,6 +31,8 @@
 
 namespace dvsg {
 
+bool tps_nodes_ok(int H, int W, int C, int oh, int ow, int pn, int flags);      // warp_fwd_tile.cu
+
 struct BwdTileParams {
     const float* src;        // [B,H,W,3]
     const float* grad_out;   // [B,oh,ow,3]
@@ -52,6 +54,7 @@ struct BwdTileParams {
     const float* flow;
     int n_tx, n_ty, segs, seg_len;
     int bw[3], bh[3];
+    int nodes;               // TPS: coordinates from the tile-node evaluation (must match the forward call)
 };
 
 struct alignas(64) BwdTileMaps {
@@ -258,13 +261,16 @@ __device__ __forceinline__ float4 bwd_pair_padded(const float2 xp, const float2 
     return make_float4(dx.x, dx.y, dy.x, dy.y);
 }
 
-template <int MODE>
+// NM: 0 = every radial term per pixel; 1 = tile-node evaluation, any mesh; 4 / 5 / 16 = with the separable node pass
+template <int MODE, int NM>
 __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTileParams p, const __grid_constant__ BwdTileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_mbar[TNW];
     __shared__ float s_lin[12];
     __shared__ __align__(16) float s_yt[TR];
 
+    constexpr bool NODES = NM > 0;
+    constexpr int NG = NM > 1 ? NM : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, oh = p.oh, ow = p.ow;
     const int seg = blockIdx.x, b = blockIdx.z;
@@ -279,6 +285,10 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
     const unsigned char* recs = smem + (size_t)TNW * (2 * TSTAGE_BYTES);
     float* w_gt = reinterpret_cast<float*>(smem + (size_t)TNW * (2 * TSTAGE_BYTES) + (size_t)pn8 * sizeof(TpsRec)) + warp * (2 * pn8 + 16);
     const uint32_t stage_s = smem_u32(w_stage), acc_s = smem_u32(w_acc), mbar = smem_u32(&s_mbar[warp]);
+    // node mode: [node tables][per-warp exchange buffers] follow the grad_T accumulators
+    unsigned char* const node_base = smem + (size_t)TNW * (2 * TSTAGE_BYTES) + (size_t)pn8 * sizeof(TpsRec) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float);
+    const NodeTables nt = node_tables_at(node_base, p.pn);
+    float2* const w_nodes = reinterpret_cast<float2*>(node_base + node_tables_bytes(p.pn)) + warp * 32;
 
     // ---- prologue -----------------------------------------------------------------------------------
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
@@ -287,8 +297,18 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         tile_tps_tables(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, pn8, row0, oh, p.step_y, tid, TNT,
                         s_lin, reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (2 * TSTAGE_BYTES)));
         if (want_gT) for (int i = lane; i < 2 * pn8 + 16; i += 32) w_gt[i] = 0.0f;
+        if (NODES) {
+            __syncthreads();          // tile_tps_tables wrote s_lin: tile_node_tables rewrites it identically
+            tile_node_tables<NG>(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, row0, oh, p.step_x, p.step_y, tid, TNT,
+                                 s_lin, nt);
+        }
     }
     __syncthreads();
+    const int node_l = min(lane, NNX * NNY - 1);
+    const float node_xoff = NODES ? NODE_XOFF[node_l % NNX] : 0.0f;
+    const float node_yn = NODES ? fmaf(p.step_y, (float)row0 + NODE_YOFF[node_l / NNX], -1.0f) : 0.0f;
+    float node_lx[NNX];
+    if (NODES) node_load_lx(lane, node_lx);
 
     const float* srcb = p.src + (size_t)b * H * W * 3;
     float* gsrcb = p.grad_src ? p.grad_src + (size_t)b * H * W * 3 : nullptr;
@@ -321,15 +341,20 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         float2 XP[TR / 2], YP[TR / 2];
         unsigned clipmask = 0;      // padded modes: bit q = x inside the clip range, bit 8+q = y inside
         if (MODE == TMODE_TPS) {
-            const float bx = fmaf(s_lin[1], xt, s_lin[0]), by = fmaf(s_lin[4], xt, s_lin[3]);
-            const float2 l2 = f2dup(s_lin[2]), l5 = f2dup(s_lin[5]);
+            if (NODES) {
+                if (col0 + TC > ow) node_load_lx(min(lane, ow - 1 - col0), node_lx);
+                tile_node_coords<NG>(nt, p.pn, s_lin, s_yt, col0, node_lx, xt, node_xoff, node_yn, p.step_x, rows_ok, w_nodes, lane, XP, YP);
+            } else {
+                const float bx = fmaf(s_lin[1], xt, s_lin[0]), by = fmaf(s_lin[4], xt, s_lin[3]);
+                const float2 l2 = f2dup(s_lin[2]), l5 = f2dup(s_lin[5]);
 #pragma unroll
-            for (int j = 0; j < TR / 2; ++j) {
-                const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
-                XP[j] = __ffma2_rn(l2, ytp, f2dup(bx));
-                YP[j] = __ffma2_rn(l5, ytp, f2dup(by));
+                for (int j = 0; j < TR / 2; ++j) {
+                    const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
+                    XP[j] = __ffma2_rn(l2, ytp, f2dup(bx));
+                    YP[j] = __ffma2_rn(l5, ytp, f2dup(by));
+                }
+                tile_tps_basis(recs, pn4, xt, XP, YP);
             }
-            tile_tps_basis(recs, pn4, xt, XP, YP);
             const float2 wf = f2dup((float)W), hf = f2dup((float)H), half2 = f2dup(0.5f);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
@@ -642,18 +667,31 @@ static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
         if (rc) return rc;
     }
     const int pn8 = MODE == TMODE_TPS ? (p.pn + 7) & ~7 : 0;
-    const size_t smem = (size_t)TNW * 2 * TSTAGE_BYTES + (size_t)pn8 * sizeof(TpsRec) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float);
-    auto k = warp_bwd_tile_kernel<MODE>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<dim3((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B), TNT, smem, st>>>(p, maps);
+    const bool nodes = MODE == TMODE_TPS && p.nodes;
+    const size_t smem = (size_t)TNW * 2 * TSTAGE_BYTES + (size_t)pn8 * sizeof(TpsRec) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float) +
+                        (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) : 0);
+    auto go = [&](auto k) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<dim3((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B), TNT, smem, st>>>(p, maps);
+    };
+    if constexpr (MODE == TMODE_TPS) {
+        if (!nodes) go(warp_bwd_tile_kernel<MODE, 0>);
+        else if (p.pn == 16) go(warp_bwd_tile_kernel<MODE, 4>);
+        else if (p.pn == 25) go(warp_bwd_tile_kernel<MODE, 5>);
+        else if (p.pn == 256) go(warp_bwd_tile_kernel<MODE, 16>);
+        else go(warp_bwd_tile_kernel<MODE, 1>);
+    } else {
+        go(warp_bwd_tile_kernel<MODE, 0>);
+    }
     count_launch();
     return check_launch("warp_bwd_tile_kernel");
 }
 
 int bwd_tile_tps(const float* U, const float* coord, long long cstride, const float* T, const float* grad_out, const float* grad_x_in,
                  const float* grad_y_in, float* grad_U, float* grad_T, float* grad_xs, float* grad_ys, int B, int H, int W, int oh, int ow,
-                 int pn, cudaStream_t st) {
+                 int pn, int flags, cudaStream_t st) {
     BwdTileParams p = {};
+    p.nodes = tps_nodes_ok(H, W, 3, oh, ow, pn, flags) ? 1 : 0;
     p.src = U; p.grad_out = grad_out; p.grad_src = grad_U; p.grad_x = grad_xs; p.grad_y = grad_ys;
     p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow;
     p.coord = coord; p.coord_stride = cstride; p.T = T; p.pn = pn;

@@ -340,7 +340,8 @@ static float lin_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 // fast path (warp_fwd_tile.cu): warp-autonomous 32x8 tiles, TMA staging
 bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh, int ow, int pn_or_0);
 int tile_tps(const float* U, const float* coord, long long cstride, const float* T, float* out, float* x_out, float* y_out,
-             float* mask_out, int B, int H, int W, int oh, int ow, int pn, cudaStream_t st);
+             float* mask_out, int B, int H, int W, int oh, int ow, int pn, int flags, cudaStream_t st);
+bool tps_nodes_ok(int H, int W, int C, int oh, int ow, int pn, int flags);
 int tile_given(const float* im, const float* x, const float* y, float* out, int B, int H, int W, int oh, int ow, cudaStream_t st);
 int tile_flow(const float* im, const float* flow, float* out, int B, int H, int W, cudaStream_t st);
 int tile_homog(const float* im, const float* theta, int projective, float* out, float* x_out, float* y_out, int B, int H, int W,
@@ -388,6 +389,10 @@ extern "C" int dvsg_set_tile_tuning(int debug_mask, int target_ctas, int min_cta
     return DVSG_OK;
 }
 
+extern "C" int dvsg_tps_coords_mode(int H, int W, int C, int oh, int ow, int pn, int flags) {
+    return tps_nodes_ok(H, W, C, oh, ow, pn, flags) ? 1 : 0;
+}
+
 extern "C" int dvsg_tps_warp_fwd(const float* U, const float* coord, long long coord_batch_stride, const float* T,
                                  float* out, float* x_out, float* y_out, float* mask_out, int B, int H, int W, int C,
                                  int oh, int ow, int pn, int flags, void* stream) {
@@ -397,7 +402,7 @@ extern "C" int dvsg_tps_warp_fwd(const float* U, const float* coord, long long c
     DVSG_REQUIRE(coord_batch_stride == 0 || coord_batch_stride >= 2LL * pn, "tps_warp_fwd: coord stride %lld < 2*pn", coord_batch_stride);
     DVSG_REQUIRE((long long)H * W < (1LL << 31) / C && (long long)oh * ow < (1LL << 31) / C, "tps_warp_fwd: frame too large for int32 indexing");
     if (use_tile(flags, U, out, H, W, C, oh, ow, pn))
-        return B == 0 ? DVSG_OK : tile_tps(U, coord, coord_batch_stride, T, out, x_out, y_out, mask_out, B, H, W, oh, ow, pn, (cudaStream_t)stream);
+        return B == 0 ? DVSG_OK : tile_tps(U, coord, coord_batch_stride, T, out, x_out, y_out, mask_out, B, H, W, oh, ow, pn, flags, (cudaStream_t)stream);
     FwdParams p = {};
     p.src = U; p.out = out; p.x_out = x_out; p.y_out = y_out; p.mask_out = mask_out;
     p.B = B; p.H = H; p.W = W; p.C = C; p.oh = oh; p.ow = ow;

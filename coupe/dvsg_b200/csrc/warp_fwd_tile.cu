@@ -171,7 +171,9 @@ __device__ __forceinline__ void gather_tile(const float2 (&XC)[TR / 2], const fl
 }
 
 // G > 0: kernel specialised for G x G meshes; the compact separable-mesh tables are used when the frame's mesh is
-// separable (checked in the prologue), the generic records otherwise.
+// separable (checked in the prologue), the generic records otherwise.  G == 0: any mesh, generic records.  Both evaluate
+// every radial term per pixel (DVSG_FLAG_TPS_EXACT).  G < 0: tile-node evaluation (tile_common.cuh), the default: -1 any
+// mesh, -4 / -5 / -16 with the separable node pass for G x G meshes (checked per frame in the prologue).
 template <int MODE, bool MASK, int G>
 __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams p, const __grid_constant__ TileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -192,6 +194,11 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
     const unsigned char* recs = smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes);
     const uint32_t out_s = smem_u32(w_out), stage_s = smem_u32(w_stage), mbar = smem_u32(&s_mbar[warp]);
     const int pn8 = (p.pn + 7) & ~7;                 // table padded with zero-weight records to a multiple of 8
+    constexpr bool NODES = MODE == TMODE_TPS && G < 0;
+    constexpr int NG = G < -1 ? -G : 0;              // side of the separable mesh the node pass is specialised for
+    // node mode: [node tables][per-warp exchange buffers of 32 float2] follow the per-warp staging
+    const NodeTables nt = node_tables_at(smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes), p.pn);
+    float2* const w_nodes = reinterpret_cast<float2*>(smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + node_tables_bytes(p.pn)) + warp * 32;
 
     // ---- prologue: mbarriers, per-strip tables (the only CTA barrier of the kernel) -----------------
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
@@ -201,13 +208,21 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
         unsigned char* tab = smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes);
         const float* Tb = p.T + (size_t)b * 2 * (p.pn + 3);
         const float* cb = p.coord + (size_t)b * p.coord_stride;
-        if (G > 0) sep = tile_tps_tables_sep<(G > 0 ? G : 1)>(Tb, cb, pn8, row0, oh, p.step_y, tid, TNT, s_lin, tab);
+        if (NODES) tile_node_tables<NG>(Tb, cb, p.pn, row0, oh, p.step_x, p.step_y, tid, TNT, s_lin, nt);
+        else if (G > 0) sep = tile_tps_tables_sep<(G > 0 ? G : 1)>(Tb, cb, pn8, row0, oh, p.step_y, tid, TNT, s_lin, tab);
         else tile_tps_tables(Tb, cb, p.pn, pn8, row0, oh, p.step_y, tid, TNT, s_lin, reinterpret_cast<TpsRec*>(tab));
     } else if (MODE == TMODE_HOMOG) {
         const int nt = p.projective ? 8 : 6;
         if (tid < 9) s_lin[tid] = tid < nt ? __ldg(p.theta + (size_t)b * nt + tid) : (tid == 8 ? 1.0f : 0.0f);
     }
     __syncthreads();
+
+    // node mode: this lane's node (lanes past the last node repeat it; their values are never read)
+    const int node_l = min(lane, NNX * NNY - 1);
+    const float node_xoff = NODES ? NODE_XOFF[node_l % NNX] : 0.0f;
+    const float node_yn = NODES ? fmaf(p.step_y, (float)row0 + NODE_YOFF[node_l / NNX], -1.0f) : 0.0f;
+    float node_lx[NNX];                              // Lagrange weights of this lane's column; reloaded for a ragged last tile
+    if (NODES) node_load_lx(lane, node_lx);
 
     const float* srcb = p.src + (size_t)b * H * W * 3;
     const float2 one2 = f2dup(1.0f), onex = f2dup(p.one);
@@ -231,7 +246,10 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
         T.col = min(T.col0 + lane, ow - 1);          // columns / rows past the edge are duplicates of the edge pixel
         T.col_ok = T.col0 + lane < ow;
         xt = lin_coord(T.col, p.step_x);
-        if (MODE == TMODE_TPS) {
+        if (NODES) {
+            if (T.col0 + TC > ow) node_load_lx(min(lane, ow - 1 - T.col0), node_lx);      // the strip's last tile = this warp's last tile
+            tile_node_coords<NG>(nt, p.pn, s_lin, s_yt, T.col0, node_lx, xt, node_xoff, node_yn, p.step_x, rows_ok, w_nodes, lane, X, Y);
+        } else if (MODE == TMODE_TPS) {
             const float bx = fmaf(s_lin[1], xt, s_lin[0]), by = fmaf(s_lin[4], xt, s_lin[3]);
             const float2 l2 = f2dup(s_lin[2]), l5 = f2dup(s_lin[5]);
 #pragma unroll
@@ -474,7 +492,9 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     }
     const int rc = encode_frames(&maps.out, p.out, p.B, p.oh, p.ow, TC * 3, TR);
     if (rc) return rc;
-    const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) + (MODE == TMODE_TPS ? (size_t)((p.pn + 7) & ~7) * sizeof(TpsRec) : 0);
+    const bool nodes = MODE == TMODE_TPS && p.nodes;
+    const size_t smem = (size_t)TNW * (TOUT_BYTES + p.stage_bytes) +
+                        (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) : (MODE == TMODE_TPS ? (size_t)((p.pn + 7) & ~7) * sizeof(TpsRec) : 0));
     const dim3 grid((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B);
     auto go = [&](auto k) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -482,7 +502,11 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     };
     if constexpr (MODE == TMODE_TPS) {
         const bool m = p.mask_out != nullptr;
-        if (p.pn == 16) { if (m) go(warp_fwd_tile_kernel<MODE, true, 4>); else go(warp_fwd_tile_kernel<MODE, false, 4>); }
+        if (nodes && p.pn == 16) { if (m) go(warp_fwd_tile_kernel<MODE, true, -4>); else go(warp_fwd_tile_kernel<MODE, false, -4>); }
+        else if (nodes && p.pn == 25) { if (m) go(warp_fwd_tile_kernel<MODE, true, -5>); else go(warp_fwd_tile_kernel<MODE, false, -5>); }
+        else if (nodes && p.pn == 256) { if (m) go(warp_fwd_tile_kernel<MODE, true, -16>); else go(warp_fwd_tile_kernel<MODE, false, -16>); }
+        else if (nodes) { if (m) go(warp_fwd_tile_kernel<MODE, true, -1>); else go(warp_fwd_tile_kernel<MODE, false, -1>); }
+        else if (p.pn == 16) { if (m) go(warp_fwd_tile_kernel<MODE, true, 4>); else go(warp_fwd_tile_kernel<MODE, false, 4>); }
         else if (p.pn == 25) { if (m) go(warp_fwd_tile_kernel<MODE, true, 5>); else go(warp_fwd_tile_kernel<MODE, false, 5>); }
         else { if (m) go(warp_fwd_tile_kernel<MODE, true, 0>); else go(warp_fwd_tile_kernel<MODE, false, 0>); }
     } else {
@@ -492,9 +516,20 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     return check_launch("warp_fwd_tile_kernel");
 }
 
+// Shapes for which the tile kernels evaluate the TPS map on tile nodes (tile_common.cuh) unless DVSG_FLAG_TPS_EXACT asks
+// for the per-pixel evaluation: both tile kernels must be applicable (so that forward and backward see the same
+// coordinates), the mesh large enough for the node pass to pay (9 instructions per control point and tile + ~130 for the
+// interpolation, against 28 per control point), and a tile small against the frame (the error study covers >= 200 x 400).
+bool tps_nodes_ok(int H, int W, int C, int oh, int ow, int pn, int flags) {
+    static const bool env_exact = getenv("DVSG_TPS_EXACT") != nullptr;      // A/B experiments
+    (void)H;
+    return !(flags & DVSG_FLAG_TPS_EXACT) && !env_exact && C == 3 && W % 4 == 0 && ow % 4 == 0 && pn >= 8 && pn <= TKC && ow >= 400 && oh >= 200;
+}
+
 int tile_tps(const float* U, const float* coord, long long cstride, const float* T, float* out, float* x_out, float* y_out,
-             float* mask_out, int B, int H, int W, int oh, int ow, int pn, cudaStream_t st) {
+             float* mask_out, int B, int H, int W, int oh, int ow, int pn, int flags, cudaStream_t st) {
     TileParams p = {};
+    p.nodes = tps_nodes_ok(H, W, 3, oh, ow, pn, flags) ? 1 : 0;
     p.src = U; p.out = out; p.x_out = x_out; p.y_out = y_out; p.mask_out = mask_out;
     p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow;
     p.coord = coord; p.coord_stride = cstride; p.T = T; p.pn = pn;

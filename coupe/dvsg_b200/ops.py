@@ -172,7 +172,7 @@ def tps_warp_fwd(U, coord, T, out_size, want_grid=True, want_mask=False, flags=0
     return out, x, y, mask
 
 
-def tps_warp_bwd(U, coord, T, out_size, grad_out, grad_x=None, grad_y=None, need_grad_U=True, want_grid_grad=False, grad_U_out=None):
+def tps_warp_bwd(U, coord, T, out_size, grad_out, grad_x=None, grad_y=None, need_grad_U=True, want_grid_grad=False, grad_U_out=None, flags=0):
     lib = _lib.load()
     B, H, W, C = U.shape
     oh, ow = out_hw(out_size)
@@ -191,8 +191,9 @@ def tps_warp_bwd(U, coord, T, out_size, grad_out, grad_x=None, grad_y=None, need
     gxs = torch.empty(B * oh * ow, dtype=torch.float32, device=dev) if want_grid_grad else None
     gys = torch.empty(B * oh * ow, dtype=torch.float32, device=dev) if want_grid_grad else None
     with torch.cuda.device(dev):
-        rc = lib.dvsg_tps_warp_bwd(ptr(U), ptr(cbuf), cstride, ptr(T), ptr(grad_out), ptr(gx_in), ptr(gy_in), ptr(gU),
-                                   ptr(gT), ptr(gxs), ptr(gys), B, H, W, C, oh, ow, pn, stream_ptr(dev))
+        # `flags` must be the flags of the forward call (DVSG_FLAG_TPS_EXACT selects the same coordinates in both)
+        rc = lib.dvsg_tps_warp_bwd_ex(ptr(U), ptr(cbuf), cstride, ptr(T), ptr(grad_out), ptr(gx_in), ptr(gy_in), ptr(gU),
+                                      ptr(gT), ptr(gxs), ptr(gys), B, H, W, C, oh, ow, pn, flags & _lib.FLAG_TPS_EXACT, stream_ptr(dev))
     _lib.check(rc, 'dvsg_tps_warp_bwd')
     return gU, gT, gxs, gys
 

@@ -38,6 +38,14 @@ extern "C" {
 #define DVSG_FLAG_FORCE_DIRECT 1    /* use the direct-gather kernel even when the
                                        shared-memory-staged kernel is applicable          */
 
+#define DVSG_FLAG_TPS_EXACT    2    /* TPS kernels: evaluate every radial term per pixel.
+                                       Default (flag clear): the tile kernels evaluate the far
+                                       field of the spline on 6 x 5 Chebyshev nodes per 32 x 8
+                                       tile and interpolate (error <= 2e-7 normalised units, below
+                                       the fp32 noise of the reference's own sum); control points
+                                       near a tile are evaluated per pixel either way.  Pass the
+                                       SAME flag to the forward and the backward call.           */
+
 int         dvsg_version(void);
 const char* dvsg_last_error(void);
 /* number of kernels this library has launched on the calling thread (bench bookkeeping) */
@@ -97,6 +105,9 @@ int dvsg_tps_solve_bwd_prepared(const float* coord, long long coord_batch_stride
  *          the 2nd/3rd return values of ThinPlateSpline (:170);
  *   mask_out: optional [B,oh,ow] -- the warp of an all-ones image (model.py:82,85,121),
  *          i.e. the sum of the four bilinear weights in add_n order.                   */
+/* 1 when dvsg_tps_warp_fwd / _bwd would use the tile-node evaluation for these shapes and flags
+ * (assuming 16-byte aligned buffers), 0 when every radial term is evaluated per pixel.          */
+int dvsg_tps_coords_mode(int H, int W, int C, int oh, int ow, int pn, int flags);
 int dvsg_tps_warp_fwd(const float* U, const float* coord, long long coord_batch_stride,
                       const float* T, float* out, float* x_out, float* y_out, float* mask_out,
                       int B, int H, int W, int C, int oh, int ow, int pn, int flags,
@@ -127,6 +138,13 @@ int dvsg_tps_warp_bwd(const float* U, const float* coord, long long coord_batch_
                       const float* grad_y_in, float* grad_U, float* grad_T, float* grad_xs,
                       float* grad_ys, int B, int H, int W, int C, int oh, int ow, int pn,
                       void* stream);
+
+/* same with flags (DVSG_FLAG_TPS_EXACT: the flag the forward call was given)                   */
+int dvsg_tps_warp_bwd_ex(const float* U, const float* coord, long long coord_batch_stride,
+                         const float* T, const float* grad_out, const float* grad_x_in,
+                         const float* grad_y_in, float* grad_U, float* grad_T, float* grad_xs,
+                         float* grad_ys, int B, int H, int W, int C, int oh, int ow, int pn,
+                         int flags, void* stream);
 
 /* ---- K5: generic bilinear sampler -----------------------------------------------------
  * Replaces bilinear_interp (spatial_transformer.py:496-563): 1-px zero padding,

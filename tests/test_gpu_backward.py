@@ -250,7 +250,9 @@ def test_tile_and_generic_backward_kernels_agree_at_training_shape(amp):
     lib = _lib.load()
     try:
         lib.dvsg_set_bwd_tuning(1)
-        a = ops.tps_warp_bwd(U, coord, T, (H, W), g, gx_in, gy_in, need_grad_U=True, want_grid_grad=True)
+        # DVSG_FLAG_TPS_EXACT: the generic kernel evaluates every radial term per pixel; the tile kernel's default (tile
+        # nodes) yields coordinates ~1e-6 away, i.e. different corners on a few pixels
+        a = ops.tps_warp_bwd(U, coord, T, (H, W), g, gx_in, gy_in, need_grad_U=True, want_grid_grad=True, flags=2)
         lib.dvsg_set_bwd_tuning(1 | 2)      # force the generic kernel
         b = ops.tps_warp_bwd(U, coord, T, (H, W), g, gx_in, gy_in, need_grad_U=True, want_grid_grad=True)
     finally:
