@@ -41,6 +41,8 @@ WORKLOADS = {
     'cfg3': dict(kind='tps_train', B=32, H=288, W=512, mesh=4, bpp=32 + 56, desc='ThinPlateSpline fwd+bwd (grads wrt image and grid), batch 32 288x512, 4x4 mesh (BASELINE configs[2])'),
     'cfg3mask': dict(kind='tps_train', B=32, H=288, W=512, mesh=4, bpp=36 + 56, mask=True,
                      desc='ThinPlateSplineWithMask fwd+bwd (image + validity mask from one pass, model.py:81-85), batch 32 288x512, 4x4 mesh'),
+    'cfg3m5': dict(kind='tps_train', B=32, H=288, W=512, mesh=5, bpp=32 + 56,
+                   desc='ThinPlateSpline fwd+bwd, batch 32 288x512, 5x5 mesh (the training shape with the mesh model.py:18-19 really uses)'),
     'cfg4': dict(kind='flow', B=16, H=1080, W=1920, mesh=0, bpp=32, desc='tf_warp dense flow warp, batch 16 1080p + flow (BASELINE configs[3])'),
     'cfg5': dict(kind='tps', B=16, H=2160, W=3840, mesh=16, bpp=24, desc='ThinPlateSpline fwd, 4K frames, 16x16 mesh, ring of 16 resident frames (BASELINE configs[4])'),
 }

@@ -26,11 +26,12 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library next to this file."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """Compile every .cu under csrc/ into one shared library next to this file.  `out` / `defines`: an alternative build
+    of the same sources for A/B experiments (loaded with DVSG_LIB=...), never a different implementation."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-shared', '-o', LIB] + \
+    cmd = [_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-shared', '-o', out or LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -38,8 +39,10 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc failed building libdvsg_warp.so')
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':
-    print(build(force=True, verbose='-v' in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith('-o')]
+    print(build(force=True, verbose='-v' in sys.argv, out=outs[0] if outs else None, defines=defs))

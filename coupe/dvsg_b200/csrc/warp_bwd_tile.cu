@@ -33,6 +33,16 @@ namespace dvsg {
 
 bool tps_nodes_ok(int H, int W, int C, int oh, int ow, int pn, int flags);      // warp_fwd_tile.cu
 
+// Staging boxes of the backward kernel (floats x rows) and the CTAs per SM it is compiled for.  Every warp owns TWO buffers
+// of the largest box (source footprint + fixed-point accumulator), so the box size sets the occupancy:
+//   default          128 x 10, 128 x 13, 160 x 10 -> 6656 B, 4 CTAs (16 warps) per SM
+//   DVSG_BWD_SMALL   128 x 10, 128 x 10, 160 x 8  -> 5120 B, 5 CTAs (20 warps) per SM, registers capped at 102
+#ifdef DVSG_BWD_SMALL
+constexpr int BB_W0 = 128, BB_W2 = 160, BB_H0 = 10, BB_H1 = 10, BB_H2 = 8, BSTAGE = 5120, BWD_MINB = 5;
+#else
+constexpr int BB_W0 = BOX_W0, BB_W2 = BOX_W2, BB_H0 = BOX_H0, BB_H1 = BOX_H1, BB_H2 = BOX_H2, BSTAGE = TSTAGE_BYTES, BWD_MINB = 4;
+#endif
+
 struct BwdTileParams {
     const float* src;        // [B,H,W,3]
     const float* grad_out;   // [B,oh,ow,3]
@@ -129,7 +139,7 @@ __device__ __noinline__ void bwd_general_pixel(float xp, float yp, int W, int H,
 
 // ---- one pixel pair (rows 2j, 2j+1 of the lane's column) of a staged tile --------------------------------------------
 // Returns (d out/d x_pix of the two pixels, d out/d y_pix of the two pixels) and scatters w_k * grad_out.
-// The scatter accumulates in the warp's private buffer (= staging buffer + TSTAGE_BYTES, same layout) as 32-bit FIXED
+// The scatter accumulates in the warp's private buffer (= staging buffer + BSTAGE, same layout) as 32-bit FIXED
 // POINT with the native integer shared-memory atomic (ATOMS.ADD; float atomics on shared memory are CAS loops on sm_100
 // and lose to everything else that was tried): every scattered weight lies in [0, 1] (see CLAMP below for the frame
 // border), so |contribution| <= max |grad_out| of the tile.  Contributions are scaled by a power of two chosen per
@@ -200,8 +210,8 @@ __device__ __forceinline__ float4 bwd_pair_fixed(const float2 xp, const float2 y
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (CLAMP && !inside[h]) continue;      // clamped sample: its paired contributions cancel exactly (see above)
-                int* a0 = const_cast<int*>(reinterpret_cast<const int*>(p0[h])) + TSTAGE_BYTES / 4 + ch;
-                int* a1 = const_cast<int*>(reinterpret_cast<const int*>(p1[h])) + TSTAGE_BYTES / 4 + ch;
+                int* a0 = const_cast<int*>(reinterpret_cast<const int*>(p0[h])) + BSTAGE / 4 + ch;
+                int* a1 = const_cast<int*>(reinterpret_cast<const int*>(p1[h])) + BSTAGE / 4 + ch;
                 atomicAdd(a0, __float_as_int(h ? q00.y : q00.x) - 0x4B400000);
                 atomicAdd(a1, __float_as_int(h ? q10.y : q10.x) - 0x4B400000);
                 atomicAdd(a0 + 3, __float_as_int(h ? q01.y : q01.x) - 0x4B400000);
@@ -263,7 +273,7 @@ __device__ __forceinline__ float4 bwd_pair_padded(const float2 xp, const float2 
 
 // NM: 0 = every radial term per pixel; 1 = tile-node evaluation, any mesh; 4 / 5 / 16 = with the separable node pass
 template <int MODE, int NM>
-__global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTileParams p, const __grid_constant__ BwdTileMaps maps) {
+__global__ void __launch_bounds__(TNT, BWD_MINB) warp_bwd_tile_kernel(const BwdTileParams p, const __grid_constant__ BwdTileMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_mbar[TNW];
     __shared__ float s_lin[12];
@@ -280,28 +290,32 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
     const int pn4 = (p.pn + 3) & ~3, pn8 = (p.pn + 7) & ~7;
     const bool want_gT = MODE == TMODE_TPS && p.grad_T != nullptr;
 
-    unsigned char* w_stage = smem + (size_t)warp * (2 * TSTAGE_BYTES);
-    unsigned char* w_acc = w_stage + TSTAGE_BYTES;
-    const unsigned char* recs = smem + (size_t)TNW * (2 * TSTAGE_BYTES);
-    float* w_gt = reinterpret_cast<float*>(smem + (size_t)TNW * (2 * TSTAGE_BYTES) + (size_t)pn8 * sizeof(TpsRec)) + warp * (2 * pn8 + 16);
+    unsigned char* w_stage = smem + (size_t)warp * (2 * BSTAGE);
+    unsigned char* w_acc = w_stage + BSTAGE;
+    // after the per-warp buffers: [per-pixel tables (exact mode only)][per-warp grad_T accumulators]
+    //                             [node mode: node tables][per-warp node exchange buffers][Lagrange weights NODE_LX]
+    const size_t rec_bytes = NODES ? 0 : (size_t)pn8 * sizeof(TpsRec);
+    const unsigned char* recs = smem + (size_t)TNW * (2 * BSTAGE);
+    float* w_gt = reinterpret_cast<float*>(smem + (size_t)TNW * (2 * BSTAGE) + rec_bytes) + warp * (2 * pn8 + 16);
     const uint32_t stage_s = smem_u32(w_stage), acc_s = smem_u32(w_acc), mbar = smem_u32(&s_mbar[warp]);
-    // node mode: [node tables][per-warp exchange buffers] follow the grad_T accumulators
-    unsigned char* const node_base = smem + (size_t)TNW * (2 * TSTAGE_BYTES) + (size_t)pn8 * sizeof(TpsRec) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float);
+    unsigned char* const node_base = smem + (size_t)TNW * (2 * BSTAGE) + rec_bytes + (size_t)TNW * (2 * pn8 + 16) * sizeof(float);
     const NodeTables nt = node_tables_at(node_base, p.pn);
     float2* const w_nodes = reinterpret_cast<float2*>(node_base + node_tables_bytes(p.pn)) + warp * 32;
+    float* const s_lxt = reinterpret_cast<float*>(node_base + node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2));      // [TC][8]
 
     // ---- prologue -----------------------------------------------------------------------------------
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     if (tid < TR) s_yt[tid] = lin_coord(min(row0 + tid, oh - 1), p.step_y);
     if (MODE == TMODE_TPS) {
-        tile_tps_tables(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, pn8, row0, oh, p.step_y, tid, TNT,
-                        s_lin, reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (2 * TSTAGE_BYTES)));
-        if (want_gT) for (int i = lane; i < 2 * pn8 + 16; i += 32) w_gt[i] = 0.0f;
         if (NODES) {
-            __syncthreads();          // tile_tps_tables wrote s_lin: tile_node_tables rewrites it identically
             tile_node_tables<NG>(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, row0, oh, p.step_x, p.step_y, tid, TNT,
                                  s_lin, nt);
+            for (int i = tid; i < TC * 8; i += TNT) s_lxt[i] = NODE_LX[i >> 3][i & 7];
+        } else {
+            tile_tps_tables(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, pn8, row0, oh, p.step_y, tid, TNT,
+                            s_lin, reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (2 * BSTAGE)));
         }
+        if (want_gT) for (int i = lane; i < 2 * pn8 + 16; i += 32) w_gt[i] = 0.0f;
     }
     __syncthreads();
     const int node_l = min(lane, NNX * NNY - 1);
@@ -578,7 +592,133 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         }
 
         // ================= P2: grad_T = sum over pixels of grad(x_s, y_s) * (1, x_t, y_t, r_1..r_pn) =================
-        if (want_gT) {
+        if (want_gT && NODES) {
+            // ---- node mode: the adjoint of what tile_node_coords computes ------------------------------------------------
+            // coordinates = affine + sum_n L_n(pixel) F(n) + near field, F(n) = sum_{far k} c_k phi_k(node n):
+            //   A(n)      = sum_pixels L_n(pixel) g(pixel)              adjoint interpolation: rows first, then columns
+            //   grad c_k  = sum_n A(n) phi_k(n)                         far control points of this tile (lane = control point)
+            //   grad c_k  = sum_pixels g(pixel) phi_k(pixel)            its near control points, per pixel
+            // Scratch = the warp's staging buffer, idle between the gather of this tile and the TMA copy of the next.
+            __syncwarp();                                                          // every lane has finished reading the staged footprint
+            float* const hbuf = reinterpret_cast<float*>(w_stage);                 // [32 lanes][12]: (hx_b, hy_b), b = 0..4
+            float2* const abuf = reinterpret_cast<float2*>(w_stage + 32 * 48);     // [32 nodes]
+            const int n_row_near = nt.near_cnt[0];
+            unsigned near = 0;
+            if (n_row_near > 0) {
+                const float lo = (float)col0 - NODE_NEAR_X, hi = (float)(col0 + TC - 1) + NODE_NEAR_X;
+                for (int i = 0; i < n_row_near; ++i) {
+                    const float c = nt.near_col[i];
+                    if (c > lo && c < hi) near |= 1u << i;
+                }
+            }
+            if (n_row_near >= 0) {
+                // rows: h_b = sum_r My[b][r] g(r)
+                float hrow[2 * NNY];
+#pragma unroll
+                for (int bb = 0; bb < NNY; ++bb) {
+                    float2 ax = f2dup(0.0f), ay = f2dup(0.0f);
+#pragma unroll
+                    for (int j = 0; j < TR / 2; ++j) {
+                        const float2 m = f2(NODE_MY[bb][2 * j], NODE_MY[bb][2 * j + 1]);
+                        ax = __ffma2_rn(m, GX[j], ax);
+                        ay = __ffma2_rn(m, GY[j], ay);
+                    }
+                    hrow[2 * bb] = ax.x + ax.y; hrow[2 * bb + 1] = ay.x + ay.y;
+                }
+                float4* hb4 = reinterpret_cast<float4*>(hbuf + lane * 12);
+                hb4[0] = make_float4(hrow[0], hrow[1], hrow[2], hrow[3]);
+                hb4[1] = make_float4(hrow[4], hrow[5], hrow[6], hrow[7]);
+                hb4[2] = make_float4(hrow[8], hrow[9], 0.0f, 0.0f);
+                __syncwarp();
+                // columns: A(a, b) = sum_c Lx[a](c) h_b(c); lane = node (a, b)
+                {
+                    const int na = node_l % NNX, nb = node_l / NNX;
+                    const float* __restrict__ hp = hbuf + 2 * nb;
+                    const float* __restrict__ lp = s_lxt + na;
+                    float ax = 0.0f, ay = 0.0f;
+#pragma unroll 8
+                    for (int c = 0; c < TC; ++c) {
+                        const float2 h = *reinterpret_cast<const float2*>(hp + c * 12);
+                        const float w = lp[c * 8];
+                        ax = fmaf(w, h.x, ax);
+                        ay = fmaf(w, h.y, ay);
+                    }
+                    abuf[lane] = lane < NNX * NNY ? make_float2(ax, ay) : make_float2(0.0f, 0.0f);
+                }
+                __syncwarp();
+                // far control points: lane = control point, loop over the nodes
+                {
+                    float xnode[NNX], ynode[NNY];
+#pragma unroll
+                    for (int a = 0; a < NNX; ++a) xnode[a] = fmaf(p.step_x, (float)col0 + NODE_XOFF[a], -1.0f);
+#pragma unroll
+                    for (int bb = 0; bb < NNY; ++bb) ynode[bb] = fmaf(p.step_y, (float)row0 + NODE_YOFF[bb], -1.0f);
+                    for (int kk = lane; kk < p.pn; kk += 32) {
+                        bool is_near = false;
+                        for (unsigned m = near; m; m &= m - 1) is_near = is_near || nt.near_idx[__ffs(m) - 1] == kk;
+                        const float4 cp = nt.cp[kk];
+                        float dx2[NNX], dy2[NNY];
+#pragma unroll
+                        for (int a = 0; a < NNX; ++a) { const float d = xnode[a] - cp.x; dx2[a] = d * d; }
+#pragma unroll
+                        for (int bb = 0; bb < NNY; ++bb) { const float d = ynode[bb] - cp.y; dy2[bb] = fmaf(d, d, TPS_TINY); }
+                        float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+                        for (int n = 0; n < NNX * NNY; ++n) {
+                            const float2 a = abuf[n];
+                            const float d2 = dx2[n % NNX] + dy2[n / NNX];
+                            const float r = d2 * lg2_approx(d2);
+                            sx = fmaf(a.x, r, sx);
+                            sy = fmaf(a.y, r, sy);
+                        }
+                        if (!is_near) { w_gt[2 * kk] += sx; w_gt[2 * kk + 1] += sy; }
+                    }
+                }
+                __syncwarp();
+            }
+            // near control points (all of them in a degenerate strip): per pixel, the forward's own radial term
+            {
+                const int n_loop = n_row_near < 0 ? p.pn : n_row_near;
+                for (int i = 0; i < n_loop; ++i) {
+                    if (n_row_near >= 0 && !((near >> i) & 1u)) continue;
+                    const int kk = n_row_near < 0 ? i : nt.near_idx[i];
+                    const float4 cp = nt.cp[kk];
+                    const float dx = xt - cp.x;
+                    const float2 dxx = f2dup(dx * dx), npy = f2dup(-cp.y);
+                    float2 sx = f2dup(0.0f), sy = f2dup(0.0f);
+#pragma unroll
+                    for (int j = 0; j < TR / 2; ++j) {
+                        const float2 dy = __fadd2_rn(*reinterpret_cast<const float2*>(s_yt + 2 * j), npy);
+                        const float2 d2 = __ffma2_rn(dy, dy, dxx);
+                        const float2 t = __fadd2_rn(d2, f2dup(TPS_EPS));
+                        const float2 r = __ffma2_rn(d2, f2(lg2_approx(t.x), lg2_approx(t.y)), f2dup(-TPS_EPS_LG2));
+                        sx = __ffma2_rn(GX[j], r, sx);
+                        sy = __ffma2_rn(GY[j], r, sy);
+                    }
+                    float vx = sx.x + sx.y, vy = sy.x + sy.y;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) { vx += __shfl_xor_sync(0xffffffffu, vx, o); vy += __shfl_xor_sync(0xffffffffu, vy, o); }
+                    if (lane == 0) { w_gt[2 * kk] += vx; w_gt[2 * kk + 1] += vy; }
+                }
+            }
+            {   // affine part: (1, x_t, y_t)
+                float v[16];
+                float2 sx = f2dup(0.0f), sy = f2dup(0.0f), sxy = f2dup(0.0f), syy = f2dup(0.0f);
+#pragma unroll
+                for (int j = 0; j < TR / 2; ++j) {
+                    const float2 ytp = *reinterpret_cast<const float2*>(s_yt + 2 * j);
+                    sx = __fadd2_rn(sx, GX[j]); sy = __fadd2_rn(sy, GY[j]);
+                    sxy = __ffma2_rn(GX[j], ytp, sxy); syy = __ffma2_rn(GY[j], ytp, syy);
+                }
+                const float ax = sx.x + sx.y, ay = sy.x + sy.y;
+                v[0] = ax; v[1] = ax * xt; v[2] = sxy.x + sxy.y; v[3] = ay; v[4] = ay * xt; v[5] = syy.x + syy.y;
+#pragma unroll
+                for (int i = 6; i < 16; ++i) v[i] = 0.0f;
+                const float tot = reduce16(v, lane);
+                if ((lane & 1) == 0) w_gt[2 * pn8 + (lane >> 1)] += tot;
+            }
+            __syncwarp();
+        } else if (want_gT) {
             const unsigned char* rp = recs;
             for (int k = 0; k < pn8; k += 8) {
                 float v[16];
@@ -632,7 +772,8 @@ __global__ void __launch_bounds__(TNT, 4) warp_bwd_tile_kernel(const BwdTilePara
         float* gTb = p.grad_T + (size_t)b * 2 * N;
         for (int i = lane; i < 2 * pn8; i += 32) {
             const int k = i >> 1, xy = i & 1;               // entry 2*k + xy
-            if (k < p.pn) atomicAdd(gTb + xy * N + 3 + k, w_gt[i] * TLN2);
+            // + 1e-6 * sum_pixels g: every c_k also enters the affine constant through the folded epsilon (tps_affine0)
+            if (k < p.pn) atomicAdd(gTb + xy * N + 3 + k, fmaf(w_gt[i], TLN2, TPS_EPS * w_gt[2 * pn8 + 3 * xy]));
         }
         if (lane < 6) atomicAdd(gTb + (lane / 3) * N + lane % 3, w_gt[2 * pn8 + lane]);
     }
@@ -654,13 +795,13 @@ static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
     const long long strips = (long long)p.B * p.n_ty;
     // the TPS prologue builds the per-strip tables; the field samplers have none and prefer short CTAs (tf_warp backward,
     // 32 x 288 x 512: 16 / 8 / 4 tiles per CTA 156 / 144 / 138 us; 16 x 720p: 40 / 20 / 4 tiles 220 / 199 / 189 us)
-    p.seg_len = tile_pick_seg_len(strips, p.n_tx, 148 * 4, MODE == TMODE_TPS ? 0.5 : 0.05, "DVSG_BWD_SEGLEN");
+    p.seg_len = tile_pick_seg_len(strips, p.n_tx, 148 * BWD_MINB, MODE == TMODE_TPS ? 0.5 : 0.05, "DVSG_BWD_SEGLEN");
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "bwd tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
     BwdTileMaps maps;
     for (int i = 0; i < NBOX; ++i) {
-        p.bw[i] = min(box_w(i), 3 * p.W);
-        p.bh[i] = min(box_h(i), p.H);
+        p.bw[i] = min(i == 2 ? BB_W2 : BB_W0, 3 * p.W);
+        p.bh[i] = min(i == 0 ? BB_H0 : (i == 1 ? BB_H1 : BB_H2), p.H);
         int rc = encode_frames(&maps.src[i], p.src, p.B, p.H, p.W, p.bw[i], p.bh[i]);
         if (rc) return rc;
         rc = encode_frames(&maps.gsrc[i], p.grad_src ? p.grad_src : p.src, p.B, p.H, p.W, p.bw[i], p.bh[i]);
@@ -668,8 +809,8 @@ static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
     }
     const int pn8 = MODE == TMODE_TPS ? (p.pn + 7) & ~7 : 0;
     const bool nodes = MODE == TMODE_TPS && p.nodes;
-    const size_t smem = (size_t)TNW * 2 * TSTAGE_BYTES + (size_t)pn8 * sizeof(TpsRec) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float) +
-                        (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) : 0);
+    const size_t smem = (size_t)TNW * 2 * BSTAGE + (nodes ? 0 : (size_t)pn8 * sizeof(TpsRec)) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float) +
+                        (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) + TC * 8 * sizeof(float) : 0);
     auto go = [&](auto k) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<dim3((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B), TNT, smem, st>>>(p, maps);
