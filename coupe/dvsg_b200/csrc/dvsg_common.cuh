@@ -91,14 +91,14 @@ constexpr float TPS_EPS = 1e-6f;
 // warp-collective: sum of pn coefficients in a fixed order (lane-strided partial sums, xor tree: same value on every lane)
 __device__ __forceinline__ float tps_coef_sum(const float* __restrict__ c, int pn, int lane) {
     float s = 0.0f;
-    for (int k = lane; k < pn; k += 32) s = __fadd_rn(s, __ldg(c + k));
+    for (int k = lane; k < pn; k += 32) s = __fadd_rn(s, c[k]);      // plain loads: the coefficients may live in shared memory
 #pragma unroll
     for (int o = 16; o; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
     return s;
 }
 // affine constant of one output row of T with the folded epsilon term (called by one whole warp)
 __device__ __forceinline__ float tps_affine0(const float* __restrict__ Trow, int pn, int lane) {
-    return __fmaf_rn(TPS_EPS, tps_coef_sum(Trow + 3, pn, lane), __ldg(Trow));
+    return __fmaf_rn(TPS_EPS, tps_coef_sum(Trow + 3, pn, lane), Trow[0]);
 }
 // (y_t - p_y)^2 as stored in the tables
 __device__ __forceinline__ float tps_dy2(float yt, float py) {

@@ -45,7 +45,27 @@ struct TileParams {
     int segs, seg_len;    // CTAs per strip, tiles per CTA
     float one;            // 1.0f, opaque to ptxas: add2x() below
     int nodes;            // TPS: tile-node evaluation of the map (default) instead of the per-pixel one
+    // fused prepared solve (online loop, pn + 3 <= 32): when winv != nullptr every CTA first forms its frame's coefficients
+    // T = (W^-1 (coord + vector))^T exactly as tps_apply_kernel does (fp64 accumulation over j = 0..pn-1, rounded once), CTA
+    // (0, 0) of each frame also stores them to T_out
+    const double* winv;   // [N][2N] workspace of dvsg_tps_prepare: W^-1 is its right half
+    const float* vec;     // [B, pn, 2] regressed offsets
+    float* T_out;         // [B, 2, pn+3]
 };
+constexpr int TFUSE_N = 32;   // largest system (pn + 3) whose solve is fused into the warp kernel's prologue
+
+// the prepared solve of one frame by the first 2N threads of a CTA: s_T[c*N + i] = float(sum_j Winv[i][j] * double(coord_j + vec_j)[c])
+__device__ __forceinline__ void tile_fused_solve(const double* __restrict__ winv, const float* __restrict__ cb, const float* __restrict__ vb, int pn,
+                                                 int tid, float* s_T) {
+    const int N = pn + 3, M = 2 * N;
+    if (tid < 2 * N) {
+        const int c = tid / N, i = tid - c * N;
+        const double* __restrict__ w = winv + (size_t)i * M + N;
+        double a = 0.0;
+        for (int j = 0; j < pn; ++j) a += w[j] * (double)__fadd_rn(__ldg(cb + 2 * j + c), __ldg(vb + 2 * j + c));      // ThinPlateSpline.py:161-163
+        s_T[c * N + i] = (float)a;
+    }
+}
 
 // staging boxes (floats wide x rows): pitch = 512 or 640 B keeps the row pitch a multiple of 128 B, so the
 // bank of a corner depends on its column only (3*x mod 32), whatever row each lane reads
@@ -134,12 +154,12 @@ __device__ __forceinline__ void tile_tps_tables(const float* __restrict__ Tb, co
     if (warp < 2) {
         const float c0 = tps_affine0(Tb + warp * N, pn, lane);
         if (lane == 0) s_lin[3 * warp] = c0;
-        else if (lane < 3) s_lin[3 * warp + lane] = __ldg(Tb + warp * N + lane);
+        else if (lane < 3) s_lin[3 * warp + lane] = Tb[warp * N + lane];
     }
     for (int k = tid; k < pn8; k += nthreads) {
         const bool real = k < pn;
         const float px = real ? __ldg(cb + 2 * k) : 0.0f, py = real ? __ldg(cb + 2 * k + 1) : 0.0f;
-        const float cx = real ? __ldg(Tb + 3 + k) * TLN2 : 0.0f, cy = real ? __ldg(Tb + N + 3 + k) * TLN2 : 0.0f;
+        const float cx = real ? Tb[3 + k] * TLN2 : 0.0f, cy = real ? Tb[N + 3 + k] * TLN2 : 0.0f;
         float d[TR];
 #pragma unroll
         for (int r = 0; r < TR; ++r)
@@ -207,14 +227,14 @@ __device__ __forceinline__ bool tile_tps_tables_sep(const float* __restrict__ Tb
     if (warp < 2) {
         const float c0 = tps_affine0(Tb + warp * N, PN, lane);
         if (lane == 0) s_lin[3 * warp] = c0;
-        else if (lane < 3) s_lin[3 * warp + lane] = __ldg(Tb + warp * N + lane);
+        else if (lane < 3) s_lin[3 * warp + lane] = Tb[warp * N + lane];
     }
     float* dyt = reinterpret_cast<float*>(recs + SepLayout<G>::DY);
     float2* cf = reinterpret_cast<float2*>(recs + SepLayout<G>::CF);
     float* npx = reinterpret_cast<float*>(recs + SepLayout<G>::NPX);
     for (int i = tid; i < G * TR; i += nthreads)
         dyt[i] = tps_dy2(lin_coord(min(row0 + i % TR, oh - 1), step_y), __ldg(cb + 2 * (i / TR * G) + 1));
-    for (int k = tid; k < PN; k += nthreads) cf[k] = make_float2(__ldg(Tb + 3 + k) * TLN2, __ldg(Tb + N + 3 + k) * TLN2);
+    for (int k = tid; k < PN; k += nthreads) cf[k] = make_float2(Tb[3 + k] * TLN2, Tb[N + 3 + k] * TLN2);
     if (tid < G) npx[tid] = -__ldg(cb + 2 * tid);
     return true;
 }
@@ -306,11 +326,11 @@ __device__ __forceinline__ void tile_node_tables(const float* __restrict__ Tb, c
     if (warp < 2) {
         const float c0 = tps_affine0(Tb + warp * N, pn, lane);      // constant + 1e-6 * sum_k c_k (the far field's folded epsilon)
         if (lane == 0) s_lin[3 * warp] = c0;
-        else if (lane < 3) s_lin[3 * warp + lane] = __ldg(Tb + warp * N + lane);
+        else if (lane < 3) s_lin[3 * warp + lane] = Tb[warp * N + lane];
     }
     for (int k = tid; k < pn4; k += nthreads) {
         const bool real = k < pn;
-        nt.cp[k] = real ? make_float4(__ldg(cb + 2 * k), __ldg(cb + 2 * k + 1), __ldg(Tb + 3 + k) * TLN2, __ldg(Tb + N + 3 + k) * TLN2)
+        nt.cp[k] = real ? make_float4(__ldg(cb + 2 * k), __ldg(cb + 2 * k + 1), Tb[3 + k] * TLN2, Tb[N + 3 + k] * TLN2)
                         : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     if (warp == nthreads / 32 - 1) {
@@ -513,7 +533,26 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // [B][rows][3*cols] fp32 tensor, box = bw floats x bh rows x 1 frame, zero fill outside the tensor
+inline int encode_frames_uncached(CUtensorMap* m, const float* base, int B, int rows, int cols, int bw, int bh);
 inline int encode_frames(CUtensorMap* m, const float* base, int B, int rows, int cols, int bw, int bh) {
+    // the online loop (one frame per call, the same buffers call after call) re-encodes identical maps: keep the last few
+    struct Slot { const float* base; int B, rows, cols, bw, bh; CUtensorMap map; };
+    constexpr int NSLOT = 16;
+    static thread_local Slot cache[NSLOT];
+    static thread_local int next_slot = 0;
+    for (int i = 0; i < NSLOT; ++i) {
+        const Slot& c = cache[i];
+        if (c.base == base && c.B == B && c.rows == rows && c.cols == cols && c.bw == bw && c.bh == bh && base != nullptr) { *m = c.map; return DVSG_OK; }
+    }
+    const int rc = encode_frames_uncached(m, base, B, rows, cols, bw, bh);
+    if (rc == DVSG_OK) {
+        Slot& c = cache[next_slot];
+        next_slot = (next_slot + 1) % NSLOT;
+        c.base = base; c.B = B; c.rows = rows; c.cols = cols; c.bw = bw; c.bh = bh; c.map = *m;
+    }
+    return rc;
+}
+inline int encode_frames_uncached(CUtensorMap* m, const float* base, int B, int rows, int cols, int bw, int bh) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("tile kernel: cuTensorMapEncodeTiled is not available from this driver"); return DVSG_ERR_CUDA; }
     const cuuint64_t dims[3] = {(cuuint64_t)cols * 3, (cuuint64_t)rows, (cuuint64_t)B};

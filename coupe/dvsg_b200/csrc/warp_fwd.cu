@@ -342,6 +342,9 @@ bool tile_path_ok(const void* src, const void* out, int H, int W, int C, int oh,
 int tile_tps(const float* U, const float* coord, long long cstride, const float* T, float* out, float* x_out, float* y_out,
              float* mask_out, int B, int H, int W, int oh, int ow, int pn, int flags, cudaStream_t st);
 bool tps_nodes_ok(int H, int W, int C, int oh, int ow, int pn, int flags);
+int tile_tps_fused(const float* U, const float* coord, const float* vector, const double* winv, float* T_out, float* out, float* x_out,
+                   float* y_out, float* mask_out, int B, int H, int W, int oh, int ow, int pn, int flags, cudaStream_t st);
+constexpr int FUSE_N = 32;      // == TFUSE_N of tile_common.cuh
 int tile_given(const float* im, const float* x, const float* y, float* out, int B, int H, int W, int oh, int ow, cudaStream_t st);
 int tile_flow(const float* im, const float* flow, float* out, int B, int H, int W, cudaStream_t st);
 int tile_homog(const float* im, const float* theta, int projective, float* out, float* x_out, float* y_out, int B, int H, int W,
@@ -479,6 +482,12 @@ extern "C" int dvsg_tps_warp_frames(const float* U, const float* coord, const fl
 extern "C" int dvsg_tps_warp_frames_offsets(const float* U, const float* coord, const float* vector, void* prepared, size_t prepared_bytes,
                                             float* T, float* out, float* x_out, float* y_out, float* mask_out, int B, int H, int W, int C,
                                             int oh, int ow, int pn, void* stream) {
+    if (pn + 3 <= FUSE_N && B > 0 && H > 0 && W > 0 && oh > 0 && ow > 0 && U && coord && vector && T && out && prepared &&
+        prepared_bytes >= dvsg_tps_prepare_workspace_bytes(B, pn, 0) && (x_out == nullptr) == (y_out == nullptr) &&
+        use_tile(0, U, out, H, W, C, oh, ow, pn))
+        // ONE launch: the prepared solve runs in the warp kernel's prologue (same arithmetic, same bits)
+        return tile_tps_fused(U, coord, vector, reinterpret_cast<const double*>(prepared), T, out, x_out, y_out, mask_out, B, H, W, oh, ow, pn, 0,
+                              (cudaStream_t)stream);
     const int rc = dvsg_tps_solve_offsets_prepared(coord, 0, vector, T, B, pn, prepared, prepared_bytes, stream);
     if (rc) return rc;
     return dvsg_tps_warp_fwd(U, coord, 0, T, out, x_out, y_out, mask_out, B, H, W, C, oh, ow, pn, 0, stream);

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
     __shared__ __align__(8) unsigned long long s_mbar[TNW];
     __shared__ float s_lin[12];
     __shared__ __align__(16) float s_yt[TR];
+    __shared__ float s_T[MODE == TMODE_TPS ? 2 * TFUSE_N : 1];      // coefficients of this frame when the solve is fused (online loop)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler: tile bookkeeping lives in uniform registers
@@ -206,8 +207,14 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
     bool sep = false;
     if (MODE == TMODE_TPS) {
         unsigned char* tab = smem + (size_t)TNW * (TOUT_BYTES + p.stage_bytes);
-        const float* Tb = p.T + (size_t)b * 2 * (p.pn + 3);
         const float* cb = p.coord + (size_t)b * p.coord_stride;
+        const float* Tb = p.T + (size_t)b * 2 * (p.pn + 3);
+        if (p.winv != nullptr) {      // fused prepared solve: one launch per call of the online loop
+            tile_fused_solve(p.winv, cb, p.vec + (size_t)b * p.pn * 2, p.pn, tid, s_T);
+            __syncthreads();
+            if (blockIdx.x == 0 && blockIdx.y == 0 && tid < 2 * (p.pn + 3)) p.T_out[(size_t)b * 2 * (p.pn + 3) + tid] = s_T[tid];
+            Tb = s_T;
+        }
         if (NODES) tile_node_tables<NG>(Tb, cb, p.pn, row0, oh, p.step_x, p.step_y, tid, TNT, s_lin, nt);
         else if (G > 0) sep = tile_tps_tables_sep<(G > 0 ? G : 1)>(Tb, cb, pn8, row0, oh, p.step_y, tid, TNT, s_lin, tab);
         else tile_tps_tables(Tb, cb, p.pn, pn8, row0, oh, p.step_y, tid, TNT, s_lin, reinterpret_cast<TpsRec*>(tab));
@@ -497,7 +504,8 @@ static int launch_tile(TileParams p, cudaStream_t st) {
                         (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) : (MODE == TMODE_TPS ? (size_t)((p.pn + 7) & ~7) * sizeof(TpsRec) : 0));
     const dim3 grid((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B);
     auto go = [&](auto k) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static int smem_set = 0;      // per kernel instantiation: raise the dynamic shared-memory limit only when it grows
+        if ((int)smem > smem_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = (int)smem; }
         k<<<grid, TNT, smem, st>>>(p, maps);
     };
     if constexpr (MODE == TMODE_TPS) {
@@ -536,6 +544,21 @@ int tile_tps(const float* U, const float* coord, long long cstride, const float*
     p.src = U; p.out = out; p.x_out = x_out; p.y_out = y_out; p.mask_out = mask_out;
     p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow;
     p.coord = coord; p.coord_stride = cstride; p.T = T; p.pn = pn;
+    p.step_x = tile_lin_step(ow); p.step_y = tile_lin_step(oh);
+    return launch_tile<TMODE_TPS>(p, st);
+}
+
+// ThinPlateSpline of the online loop in ONE launch: the prepared solve (coord + vector, W^-1 from dvsg_tps_prepare) runs in the
+// prologue of every CTA -- 2N threads x pn fp64 multiply-adds, the arithmetic of tps_apply_kernel, so T and the frames are
+// bit-identical to dvsg_tps_solve_offsets_prepared followed by dvsg_tps_warp_fwd
+int tile_tps_fused(const float* U, const float* coord, const float* vector, const double* winv, float* T_out, float* out, float* x_out,
+                   float* y_out, float* mask_out, int B, int H, int W, int oh, int ow, int pn, int flags, cudaStream_t st) {
+    TileParams p = {};
+    p.nodes = tps_nodes_ok(H, W, 3, oh, ow, pn, flags) ? 1 : 0;
+    p.src = U; p.out = out; p.x_out = x_out; p.y_out = y_out; p.mask_out = mask_out;
+    p.B = B; p.H = H; p.W = W; p.oh = oh; p.ow = ow;
+    p.coord = coord; p.coord_stride = 0; p.T = T_out; p.pn = pn;
+    p.winv = winv; p.vec = vector; p.T_out = T_out;
     p.step_x = tile_lin_step(ow); p.step_y = tile_lin_step(oh);
     return launch_tile<TMODE_TPS>(p, st);
 }

@@ -405,17 +405,29 @@ class OnlineWarper(object):
         self._mesh_ptr = ptr(self.mesh)
         self._args = (ptr(self.ws), self.nbytes, ptr(self.T), ptr(self.out), None, None, None,
                       self.B, self.H, self.W, self.C, self.H, self.W, self.pn)
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._U_shape = (self.B, self.H, self.W, self.C)
+        self._v_shape = (self.B, self.pn, 2)
+        # raw handle of the current stream without constructing a torch.cuda.Stream per frame (the per-frame host cost of
+        # the online loop is what bounds it: the kernel itself lasts ~6 us)
+        self._raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
 
     def warp(self, U, vector):
         """U [B,H,W,C] and vector [B,pn,2]: contiguous fp32 CUDA tensors.  Returns the warped frames (a buffer owned by this
-        object, overwritten by the next call)."""
-        if U.shape != self.out.shape or U.dtype != torch.float32 or not U.is_cuda or not U.is_contiguous():
-            raise ValueError('U must be a contiguous fp32 CUDA tensor of shape %r' % (tuple(self.out.shape),))
-        if tuple(vector.shape) != (self.B, self.pn, 2) or vector.dtype != torch.float32 or not vector.is_cuda or not vector.is_contiguous():
-            raise ValueError('vector must be a contiguous fp32 CUDA tensor of shape %r' % ((self.B, self.pn, 2),))
-        # coord + vector (ThinPlateSpline.py:161) is formed inside the prepared solve
-        with torch.cuda.device(self.out.device):
-            rc = self._fn(U.data_ptr(), self._mesh_ptr, vector.data_ptr(), *self._args, torch.cuda.current_stream(U.device).cuda_stream)
+        object, overwritten by the next call).  One C-ABI call = one kernel launch per call for meshes up to 29 points."""
+        if U.shape != self._U_shape or U.dtype is not torch.float32 or not U.is_cuda or not U.is_contiguous():
+            raise ValueError('U must be a contiguous fp32 CUDA tensor of shape %r' % (self._U_shape,))
+        if vector.shape != self._v_shape or vector.dtype is not torch.float32 or not vector.is_cuda or not vector.is_contiguous():
+            raise ValueError('vector must be a contiguous fp32 CUDA tensor of shape %r' % (self._v_shape,))
+        # coord + vector (ThinPlateSpline.py:161) is formed inside the prepared solve, which runs in the warp kernel's prologue
+        if torch.cuda.current_device() != self._dev_index:
+            with torch.cuda.device(self._dev_index):
+                return self._call(U, vector)
+        return self._call(U, vector)
+
+    def _call(self, U, vector):
+        st = self._raw_stream(self._dev_index) if self._raw_stream is not None else torch.cuda.current_stream(self.out.device).cuda_stream
+        rc = self._fn(U.data_ptr(), self._mesh_ptr, vector.data_ptr(), *self._args, st)
         if rc:
             _lib.check(rc, 'dvsg_tps_warp_frames_offsets')
         return self.out

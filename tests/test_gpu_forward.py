@@ -771,3 +771,42 @@ def test_node_evaluation_vs_exact_evaluation_and_fp64_oracle(case):
     print('   pixels nodes vs exact kernel on same corners: %.2e (allowance %.2e), corner flips %.4f%%' % (d_px, allow, 100.0 * (1.0 - same.mean())))
     assert d_px <= allow
     assert (1.0 - same.mean()) <= 5e-3 + 2e3 * e_o.max()
+
+
+@pytest.mark.parametrize('shape', [(1, 288, 512, 4), (3, 288, 512, 5), (2, 720, 1280, 4), (1, 96, 160, 5), (2, 40, 50, 4), (1, 288, 512, 6)],
+                         ids=lambda s: 'B%d_%dx%d_m%d' % s)
+def test_online_call_is_one_launch_and_bit_identical_to_solve_then_warp(shape):
+    """dvsg_tps_warp_frames_offsets (the per-frame call of eval.py:101-124): for pn + 3 <= 32 on the tile path the prepared
+    solve runs in the prologue of the warp kernel -- ONE launch -- with the arithmetic of tps_apply_kernel; coefficients,
+    frames, grid and mask are bit-identical to dvsg_tps_solve_offsets_prepared followed by dvsg_tps_warp_fwd.  Larger
+    systems (6x6: N = 39) and shapes off the tile path (40 x 50) keep the two launches."""
+    from coupe.dvsg_b200 import _lib
+    lib = _lib.load()
+    B, H, W, m = shape
+    pn = m * m
+    rng = np.random.default_rng(sum(shape))
+    U = cu(smooth_image(rng, B, H, W, 3))
+    mesh = cu(tiled_mesh(m, m, 1)[0])
+    vec = cu(rng.uniform(-0.1, 0.1, (B, pn, 2)).astype(np.float32))
+    nbytes = lib.dvsg_tps_prepare_workspace_bytes(B, pn, 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    assert lib.dvsg_tps_prepare(mesh.data_ptr(), 0, B, pn, ws.data_ptr(), nbytes, 0) == 0
+
+    def bufs():
+        return (torch.empty((B, 2, pn + 3), device=DEV), torch.empty((B, H, W, 3), device=DEV), torch.empty(B * H * W, device=DEV),
+                torch.empty(B * H * W, device=DEV), torch.empty((B, H, W), device=DEV))
+    T1, o1, x1, y1, m1 = bufs()
+    n0 = _lib.launch_count()
+    rc = lib.dvsg_tps_warp_frames_offsets(U.data_ptr(), mesh.data_ptr(), vec.data_ptr(), ws.data_ptr(), nbytes, T1.data_ptr(), o1.data_ptr(),
+                                          x1.data_ptr(), y1.data_ptr(), m1.data_ptr(), B, H, W, 3, H, W, pn, 0)
+    assert rc == 0
+    launches = _lib.launch_count() - n0
+    fused = pn + 3 <= 32 and W % 4 == 0 and W >= 32 and H >= 8
+    assert launches == (1 if fused else 2)
+    T2, o2, x2, y2, m2 = bufs()
+    assert lib.dvsg_tps_solve_offsets_prepared(mesh.data_ptr(), 0, vec.data_ptr(), T2.data_ptr(), B, pn, ws.data_ptr(), nbytes, 0) == 0
+    assert lib.dvsg_tps_warp_fwd(U.data_ptr(), mesh.data_ptr(), 0, T2.data_ptr(), o2.data_ptr(), x2.data_ptr(), y2.data_ptr(), m2.data_ptr(),
+                                 B, H, W, 3, H, W, pn, 0, 0) == 0
+    torch.cuda.synchronize()
+    for a, b_ in ((T1, T2), (o1, o2), (x1, x2), (y1, y2), (m1, m2)):
+        assert torch.equal(a, b_)
