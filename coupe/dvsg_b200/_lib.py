@@ -49,6 +49,13 @@ PROTOTYPES = {
     'dvsg_frames_u8_to_f32': (c_int, [_P, _P, c_longlong, c_int, _P]),
     'dvsg_frames_f32_to_u8': (c_int, [_P, _P, c_longlong, c_int, _P]),
     'dvsg_frames_u8_resize_to_f32': (c_int, [_P, _P] + [c_int] * 6 + [_P]),
+    'dvsg_flow_resize_scale': (c_int, [_P, _P] + [c_int] * 5 + [_P]),
+    'dvsg_elastic_workspace_bytes': (c_size_t, [c_int]),
+    'dvsg_elastic_prepare': (c_int, [_P, c_int, _P, c_size_t, _P]),
+    'dvsg_elastic_solve': (c_int, [_P, _P, c_int, c_int, _P, c_size_t, _P]),
+    'dvsg_elastic_solve_bwd': (c_int, [_P, _P, c_int, c_int, _P, c_size_t, _P]),
+    'dvsg_elastic_grid': (c_int, [_P, _P, _P, _P] + [c_int] * 4 + [_P]),
+    'dvsg_elastic_grid_bwd': (c_int, [_P, _P, _P, _P] + [c_int] * 4 + [_P]),
     'dvsg_host_tps_warp_u8': (c_int, [_P, _P, _P, _P, _P, c_int, c_int]),
     'dvsg_tps_eval_points': (c_int, [_P, c_longlong, _P, _P, _P, _P] + [c_int] * 5 + [_P]),
     'dvsg_tps_eval_points_bwd': (c_int, [_P, c_longlong, _P, _P, _P, _P] + [c_int] * 5 + [_P]),

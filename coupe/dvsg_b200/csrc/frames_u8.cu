@@ -124,6 +124,35 @@ __global__ void __launch_bounds__(256) u8_resize_to_f32_kernel(const unsigned ch
     }
 }
 
+// Flow ingest (data_loader.py:239): cv2.resize(np.load(flow), (w, h)) * [w, h] for a float32 [Hs, Ws, 2] field.  cv2's
+// INTER_LINEAR on float32 input, restated from its observable behaviour: coordinates (dx + 0.5) * scale - 0.5 in double,
+// cast to float; taps and sums in float with separately rounded products (no FMA) -- bit-identical to cv2 4.13 on every case
+// tested (tests compare with cv2 itself); then the float64 product with (w, h), rounded once by the float32 feed, which is
+// the correctly rounded float product.
+__global__ void __launch_bounds__(256) flow_resize_scale_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int Hs, int Ws, int h,
+                                                                int w, double scale_x, double scale_y) {
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, b = blockIdx.z;
+    if (dx >= w) return;
+    float fx = (float)__dadd_rn(__dmul_rn((double)dx + 0.5, scale_x), -0.5);
+    int sx = (int)floorf(fx);
+    fx = __fsub_rn(fx, (float)sx);
+    if (sx < 0) { sx = 0; fx = 0.0f; }
+    if (sx >= Ws - 1) { sx = Ws - 1; fx = 0.0f; }
+    const int sx1 = min(sx + 1, Ws - 1);
+    float fy = (float)__dadd_rn(__dmul_rn((double)dy + 0.5, scale_y), -0.5);
+    const int sy = (int)floorf(fy);
+    fy = __fsub_rn(fy, (float)sy);
+    const int sy0 = min(max(sy, 0), Hs - 1), sy1 = min(max(sy + 1, 0), Hs - 1);
+    const float a0 = __fsub_rn(1.0f, fx), a1 = fx, b0 = __fsub_rn(1.0f, fy), b1 = fy;
+    const float2* f = src + (size_t)b * Hs * Ws;
+    const float2 s00 = __ldg(f + (size_t)sy0 * Ws + sx), s01 = __ldg(f + (size_t)sy0 * Ws + sx1);
+    const float2 s10 = __ldg(f + (size_t)sy1 * Ws + sx), s11 = __ldg(f + (size_t)sy1 * Ws + sx1);
+    const float r0x = __fadd_rn(__fmul_rn(s00.x, a0), __fmul_rn(s01.x, a1)), r1x = __fadd_rn(__fmul_rn(s10.x, a0), __fmul_rn(s11.x, a1));
+    const float r0y = __fadd_rn(__fmul_rn(s00.y, a0), __fmul_rn(s01.y, a1)), r1y = __fadd_rn(__fmul_rn(s10.y, a0), __fmul_rn(s11.y, a1));
+    const float vx = __fadd_rn(__fmul_rn(r0x, b0), __fmul_rn(r1x, b1)), vy = __fadd_rn(__fmul_rn(r0y, b0), __fmul_rn(r1y, b1));
+    dst[((size_t)b * h + dy) * w + dx] = make_float2(__fmul_rn(vx, (float)w), __fmul_rn(vy, (float)h));
+}
+
 static int grid_for(long long n) {
     const long long blocks = (n + 255) / 256;
     return (int)(blocks < 148 * 16 ? (blocks > 0 ? blocks : 1) : 148 * 16);     // grid-stride: 8 CTAs of 256 threads per SM, two rounds
@@ -167,4 +196,17 @@ extern "C" int dvsg_frames_u8_resize_to_f32(const unsigned char* src, float* dst
         src, dst, Hs, Ws, h, w, scale_x, scale_y, swap_rb);
     count_launch();
     return check_launch("u8_resize_to_f32_kernel");
+}
+
+extern "C" int dvsg_flow_resize_scale(const float* src, float* dst, int B, int Hs, int Ws, int h, int w, void* stream) {
+    DVSG_REQUIRE(B >= 0 && Hs >= 1 && Ws >= 1 && h > 0 && w > 0, "flow_resize_scale: bad shape");
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(src && dst, "flow_resize_scale: null pointer");
+    DVSG_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0, "flow_resize_scale: buffers must be 8-byte aligned");
+    DVSG_REQUIRE(B <= 65535 && h <= 65535 && w < (1 << 24) && h < (1 << 24), "flow_resize_scale: batch %d / size %d x %d exceed the limits", B, h, w);
+    const double scale_x = 1.0 / ((double)w / (double)Ws), scale_y = 1.0 / ((double)h / (double)Hs);
+    flow_resize_scale_kernel<<<dim3((unsigned)((w + 255) / 256), (unsigned)h, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(src), reinterpret_cast<float2*>(dst), Hs, Ws, h, w, scale_x, scale_y);
+    count_launch();
+    return check_launch("flow_resize_scale_kernel");
 }

@@ -44,6 +44,22 @@ __device__ __forceinline__ float tps_w_entry(const float* __restrict__ c, int pn
     return r == 0 ? 1.0f : c[2 * k + (r - 1)];
 }
 
+// L_ij of ElasticTransformer._initialize_tps (spatial_transformer.py:324-349), fp32, as written there:
+//   rows 0, 1 : [0 0 0 | x_1..x_pn], [0 0 0 | y_1..y_pn]      (L_top)
+//   row  2    : [0 0 1 | 1 .. 1]                               (L_mid: ones([1, pn+1]) starts at the constant column)
+//   rows 3+i  : [x_i y_i 1 | U(|p_i - p_k|^2)],  U(r2) = r2 * log(r2) with log(0) -> 0   (U_func :300-310)
+// Unknowns are ordered (a_x, a_y, a_1, w_1..w_pn) -- the rows of right_mat (:288).  c = control points [pn,2] (x, y).
+__device__ __forceinline__ float elastic_l_entry(const float* __restrict__ c, int pn, int i, int j) {
+    if (i < 2) return j < 3 ? 0.0f : c[2 * (j - 3) + i];
+    if (i == 2) return j < 2 ? 0.0f : 1.0f;
+    const int r = i - 3;
+    if (j < 2) return c[2 * r + j];
+    if (j == 2) return 1.0f;
+    const int k = j - 3;
+    const float d2 = tps_d2(c[2 * r], c[2 * r + 1], c[2 * k], c[2 * k + 1]);
+    return d2 > 0.0f ? DVSG_MUL(d2, logf(d2)) : 0.0f;
+}
+
 // rhs layout: TRANSPOSED == false : forward,  A = W,   rhs = pad(target)   -> T[b][c][i]
 //             TRANSPOSED == true  : backward, A = W^T, rhs = grad_T^T      -> grad_target[b][i][c], i < pn
 template <bool TRANSPOSED>
@@ -229,7 +245,8 @@ __global__ void __launch_bounds__(SH_THREADS) tps_solve_shared_kernel(const floa
 constexpr int INV_THREADS = 1024;
 
 __global__ void __launch_bounds__(INV_THREADS) tps_inverse_kernel(const float* __restrict__ coord, long long coord_stride, int pn,
-                                                                  double* __restrict__ work /* [nsys][N][2N] */, int* __restrict__ status) {
+                                                                  double* __restrict__ work /* [nsys][N][2N] */, int* __restrict__ status,
+                                                                  int elastic = 0) {
     extern __shared__ double s_buf[];   // pivot row (2N) + factor column (N)
     __shared__ double s_red[32];
     __shared__ int s_redi[32];
@@ -242,7 +259,7 @@ __global__ void __launch_bounds__(INV_THREADS) tps_inverse_kernel(const float* _
     double* s_col = s_buf + M;
     for (int e = tid; e < N * M; e += INV_THREADS) {
         const int i = e / M, j = e % M;
-        a[e] = j < N ? (double)tps_w_entry(c, pn, i, j) : (j - N == i ? 1.0 : 0.0);
+        a[e] = j < N ? (double)(elastic ? elastic_l_entry(c, pn, i, j) : tps_w_entry(c, pn, i, j)) : (j - N == i ? 1.0 : 0.0);
     }
     __syncthreads();
     for (int k = 0; k < N; ++k) {
@@ -331,6 +348,24 @@ __global__ void tps_apply_kernel(const double* __restrict__ work, int shared_sys
         out[((size_t)b * 2 + 0) * N + o] = (float)a0;
         out[((size_t)b * 2 + 1) * N + o] = (float)a1;
     }
+}
+
+// ElasticTransformer._transform (spatial_transformer.py:283-285): coefficients[b][c][o] = sum_i theta[b][c][i] * L_inv[o][3 + i]
+// with theta [B,2,pn] the absolute target coordinates (all x, then all y: :161); TRANSPOSED: the gradient w.r.t. theta,
+// grad_theta[b][c][i] = sum_o grad_coef[b][c][o] * L_inv[o][3 + i].  fp64 accumulation, rounded once.
+template <bool TRANSPOSED>
+__global__ void elastic_apply_kernel(const double* __restrict__ work, const float* __restrict__ in, float* __restrict__ out, int B, int pn) {
+    const int N = pn + 3, M = 2 * N;
+    const int n_out = TRANSPOSED ? pn : N;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * 2 * n_out) return;
+    const int o = (int)(gid % n_out);
+    const long long bc = gid / n_out;
+    const double* linv = work + N;      // right half of [I | L^-1]
+    double a = 0.0;
+    if (TRANSPOSED) { for (int q = 0; q < N; ++q) a += linv[(size_t)q * M + 3 + o] * (double)in[bc * N + q]; }
+    else { for (int i = 0; i < pn; ++i) a += linv[(size_t)o * M + 3 + i] * (double)in[bc * pn + i]; }
+    out[bc * n_out + o] = (float)a;
 }
 
 static size_t big_workspace_bytes(int B, int pn, long long stride) {
@@ -454,4 +489,43 @@ extern "C" int dvsg_tps_solve_bwd(const float* coord, long long coord_batch_stri
                                   int B, int pn, void* workspace, size_t workspace_bytes, void* stream) {
     return solve_impl<true>(coord, coord_batch_stride, grad_T, grad_target, B, pn, workspace, workspace_bytes, (cudaStream_t)stream,
                             "tps_solve_bwd");
+}
+
+// ---- ElasticTransformer (spatial_transformer.py:93-362): the second TPS formulation of the reference ------------------
+// One system for the layer's constant regular mesh, inverted once (dvsg_elastic_prepare = _initialize_tps), applied per call.
+extern "C" size_t dvsg_elastic_workspace_bytes(int pn) { return pn >= 1 ? big_workspace_bytes(1, pn, 0) : 0; }
+
+extern "C" int dvsg_elastic_prepare(const float* source_points, int pn, void* workspace, size_t workspace_bytes, void* stream) {
+    DVSG_REQUIRE(source_points && workspace && pn >= 3 && pn + 3 <= 2048, "elastic_prepare: bad argument");
+    const size_t need = big_workspace_bytes(1, pn, 0);
+    DVSG_REQUIRE(workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "elastic_prepare: workspace of %zu bytes (8-byte aligned) required", need);
+    const int N = pn + 3;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* status = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + need - 256);
+    if (cudaMemsetAsync(status, 0, sizeof(int), st) != cudaSuccess) return check_launch("elastic_prepare status reset");
+    cudaFuncSetAttribute(tps_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * (int)sizeof(double));
+    tps_inverse_kernel<<<1, INV_THREADS, (size_t)3 * N * sizeof(double), st>>>(source_points, 0, pn, reinterpret_cast<double*>(workspace), status, 1);
+    count_launch();
+    return check_launch("tps_inverse_kernel (elastic)");
+}
+
+extern "C" int dvsg_elastic_solve(const float* theta_abs, float* coef, int B, int pn, const void* workspace, size_t workspace_bytes, void* stream) {
+    DVSG_REQUIRE(B >= 0 && pn >= 3, "elastic_solve: bad shape");
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(theta_abs && coef && workspace && workspace_bytes >= big_workspace_bytes(1, pn, 0), "elastic_solve: bad argument");
+    const long long n = (long long)B * 2 * (pn + 3);
+    elastic_apply_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(workspace), theta_abs, coef, B, pn);
+    count_launch();
+    return check_launch("elastic_apply_kernel");
+}
+
+extern "C" int dvsg_elastic_solve_bwd(const float* grad_coef, float* grad_theta, int B, int pn, const void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+    DVSG_REQUIRE(B >= 0 && pn >= 3, "elastic_solve_bwd: bad shape");
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(grad_coef && grad_theta && workspace && workspace_bytes >= big_workspace_bytes(1, pn, 0), "elastic_solve_bwd: bad argument");
+    const long long n = (long long)B * 2 * pn;
+    elastic_apply_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(workspace), grad_coef, grad_theta, B, pn);
+    count_launch();
+    return check_launch("elastic_apply_kernel (bwd)");
 }

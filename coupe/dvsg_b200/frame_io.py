@@ -3,7 +3,8 @@
 The reference's inference loop converts every frame on the CPU (eval.py:76-81: BGR uint8 -> RGB, / 255.) and converts
 the stabilised frame back (eval.py:112-113: np.uint8(x * 255.), RGB -> BGR).  These are the same two conversions as
 CUDA kernels behind the C ABI (dvsg_frames_u8_to_f32 / dvsg_frames_f32_to_u8), so frames can cross PCIe as uint8.
-read_frames() also performs the resize of eval.py:80 (cv2.resize of the float64 frame, INTER_LINEAR) on the device.
+read_frames() also performs the resize of eval.py:80 (cv2.resize of the float64 frame, INTER_LINEAR) on the device;
+read_flow() is the optical-flow ingest of data_loader.py:239.
 """
 import torch
 
@@ -56,3 +57,22 @@ def read_frames(frames_u8, out_size, swap_rb=True):
         rc = _lib.load().dvsg_frames_u8_resize_to_f32(f.data_ptr(), out.data_ptr(), B, Hs, Ws, h, w, 1 if swap_rb else 0, stream_ptr(f.device))
     _lib.check(rc, 'dvsg_frames_u8_resize_to_f32')
     return out
+
+
+def read_flow(flow, out_size):
+    """The optical-flow ingest of data_loader.py:239, `cv2.resize(np.load(of_file), (w, h)) * [w, h]`, on the device: flow is
+    the stored float32 field of normalised displacements, [Hs, Ws, 2] or a batch [B, Hs, Ws, 2]; the result is in pixels at
+    the working size out_size = (h, w) -- the `of` argument of tf_warp (channel 0 = dx, 1 = dy)."""
+    if not isinstance(flow, torch.Tensor) or not flow.is_cuda:
+        raise ValueError('flow: expected a CUDA torch tensor (no CPU fallback on this path)')
+    if flow.dtype != torch.float32 or flow.shape[-1] != 2 or flow.dim() not in (3, 4):
+        raise ValueError('flow: expected a float32 [Hs, Ws, 2] or [B, Hs, Ws, 2] tensor, got %s %r' % (flow.dtype, tuple(flow.shape)))
+    single = flow.dim() == 3
+    f = (flow.unsqueeze(0) if single else flow).contiguous()
+    h, w = int(out_size[0]), int(out_size[1])
+    B, Hs, Ws = f.shape[0], f.shape[1], f.shape[2]
+    out = torch.empty((B, h, w, 2), dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        rc = _lib.load().dvsg_flow_resize_scale(f.data_ptr(), out.data_ptr(), B, Hs, Ws, h, w, stream_ptr(f.device))
+    _lib.check(rc, 'dvsg_flow_resize_scale')
+    return out[0] if single else out

@@ -176,6 +176,28 @@ int dvsg_homography_warp_fwd(const float* im, const float* theta, int projective
                              float* x_out, float* y_out, int B, int H, int W, int C,
                              int oh, int ow, void* stream);
 
+/* ---- ElasticTransformer (spatial_transformer.py:93-362) ---------------
+ * The reference's second TPS formulation: regular mesh fixed at construction, U(r2) = r2 log r2
+ * without epsilon, coefficients ordered (x, y, 1, w_1..w_pn), one L^-1 shared by every call.
+ *   dvsg_elastic_prepare   = _initialize_tps (:324-362): L formed in fp32 as written (including the
+ *                            L_mid quirk), inverted in fp64 into `workspace`;
+ *   dvsg_elastic_solve     = theta @ L_inv (:283-285): theta_abs [B,2,pn] = source + offsets (all x,
+ *                            then all y, :161) -> coef [B,2,pn+3]; _bwd: gradient w.r.t. theta_abs;
+ *   dvsg_elastic_grid      = coefficients @ right_mat (:286-296) -> x_s, y_s flat [B*oh*ow]; the
+ *                            sampling itself is dvsg_bilinear_fwd; _bwd: grad_coef [B,2,pn+3].
+ * source_points [pn,2] (x, y) is the mesh of get_meshgrid(g, g) (:313-322).                        */
+size_t dvsg_elastic_workspace_bytes(int pn);
+int dvsg_elastic_prepare(const float* source_points, int pn, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int dvsg_elastic_solve(const float* theta_abs, float* coef, int B, int pn, const void* workspace,
+                       size_t workspace_bytes, void* stream);
+int dvsg_elastic_solve_bwd(const float* grad_coef, float* grad_theta, int B, int pn,
+                           const void* workspace, size_t workspace_bytes, void* stream);
+int dvsg_elastic_grid(const float* source_points, const float* coef, float* x_out, float* y_out,
+                      int B, int oh, int ow, int pn, void* stream);
+int dvsg_elastic_grid_bwd(const float* source_points, const float* grad_x, const float* grad_y,
+                          float* grad_coef, int B, int oh, int ow, int pn, void* stream);
+
 /* ---- host-buffer pipeline (end-to-end path: H2D, solve, warp, D2H) ----------------------
  * The call a host-side user of ThinPlateSpline(U, coord, vector, out_size) makes when the
  * frames live in host memory (eval.py:106-110 feeds numpy through feed_dict every frame).
@@ -208,6 +230,11 @@ int dvsg_frames_f32_to_u8(const float* src, unsigned char* dst, long long n_pixe
  * restated in double; equal to the cv2 result after the fp32 cast (tests compare against cv2).   */
 int dvsg_frames_u8_resize_to_f32(const unsigned char* src, float* dst, int B, int Hs, int Ws, int h,
                                  int w, int swap_rb, void* stream);
+/* Flow ingest (data_loader.py:239): `cv2.resize(np.load(flow_file), (w, h)) * [w, h]` -- a float32 [B,Hs,Ws,2] field of
+ * normalised displacements -> [B,h,w,2] in pixels.  cv2's INTER_LINEAR on float32 restated in float (compared with cv2
+ * itself in the tests: bit-identical), then the product with (w, h) rounded once.  Device pointers, 8-byte aligned.  */
+int dvsg_flow_resize_scale(const float* src, float* dst, int B, int Hs, int Ws, int h, int w,
+                           void* stream);
 /* Host pipeline with uint8 frames on the host side: U_host, out_host [B,H,W,3] uint8; ingest and
  * egress run on the device, so a frame crosses PCIe as 3 B/pixel each way.  C must be 3.     */
 int  dvsg_host_tps_warp_u8(dvsg_host_pipeline* p, const unsigned char* U_host,

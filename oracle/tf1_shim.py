@@ -5,7 +5,7 @@ reference's hot-path files cannot be imported as they are.  This module provides
 enough of the `tensorflow` 1.x module surface for the UNMODIFIED reference files
 
     /root/reference/ThinPlateSpline.py, ThinPlateSpline2.py,
-    /root/reference/spatial_transformer.py, /root/reference/warp_with_optical_flow.py
+    /root/reference/spatial_transformer.py (incl. ElasticTransformer), /root/reference/warp_with_optical_flow.py
     (+ the methods masked_MSE, temporal_loss, get_surf_loss of /root/reference/trainer.py)
 
 to execute eagerly (each tf.* call computes immediately on torch CPU fp32/int32 tensors).
@@ -143,8 +143,17 @@ def reshape(x, shp):
     return _t(x).reshape(_ints(shp))
 
 
-def transpose(x, perm):
-    return _t(x).permute(*perm)
+def transpose(x, perm=None):
+    x = _t(x)
+    return x.permute(*reversed(builtins.range(x.dim()))) if perm is None else x.permute(*perm)
+
+
+def where(cond, a, b):
+    return torch.where(cond, _t(a), _t(b))
+
+
+def is_inf(x):
+    return torch.isinf(_t(x))
 
 
 def expand_dims(x, axis):

@@ -200,12 +200,34 @@ def loss_cases():
     return cases
 
 
+def elastic_cases():
+    """N4: ElasticTransformer (spatial_transformer.py:93-362) executed unmodified, with autograd
+    gradients w.r.t. the input and theta.  Own generator: the older fixtures stay bit-identical."""
+    rng = np.random.default_rng(20261020)
+    st = tf.load_reference(os.path.join(REF, 'spatial_transformer.py'), 'ref_spatial_transformer_elastic')
+    cases = {}
+    for name, b, h, w, c, g, osz, amp in [('elastic_4x4', 2, 14, 18, 3, 4, (14, 18), 0.12), ('elastic_3x3_resize', 1, 12, 16, 18, 3, (10, 12), 0.2)]:
+        im = smooth_image(rng, b, h, w, c)
+        theta = rng.uniform(-amp, amp, (b, 2 * g * g)).astype(np.float32)
+        g_out = rng.standard_normal((b, osz[0], osz[1], c)).astype(np.float32)
+        et = st.ElasticTransformer(list(osz), param_dim=2 * g * g, param_dim_per_side=g)
+        im_t, th_t = tt(im).requires_grad_(True), tt(theta).requires_grad_(True)
+        out, x_s, y_s = et.transform(im_t, th_t)
+        (out * tt(g_out)).sum().backward()
+        cases[name] = dict(im=im, theta=theta, grid_size=np.array(g), out_size=np.array(osz), g_out=g_out, out=out.detach().numpy(),
+                           x=x_s.detach().numpy(), y=y_s.detach().numpy(), grad_im=im_t.grad.numpy(), grad_theta=th_t.grad.numpy(),
+                           l_inv=et.L_inv.detach().numpy(), abs_theta=et.get_abs_theta(tt(theta)).numpy(),
+                           abs_src=et.get_abs_src_points(b).numpy())
+    return cases
+
+
 def main():
     rng = np.random.default_rng(20261018)
     allc = {}
     allc.update(tps_cases(rng))
     allc.update(sampler_cases(rng))
     allc.update(loss_cases())
+    allc.update(elastic_cases())
     for name, arrays in allc.items():
         path = os.path.join(OUT, name + '.npz')
         np.savez_compressed(path, **arrays)

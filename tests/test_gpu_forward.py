@@ -810,3 +810,78 @@ def test_online_call_is_one_launch_and_bit_identical_to_solve_then_warp(shape):
     torch.cuda.synchronize()
     for a, b_ in ((T1, T2), (o1, o2), (x1, x2), (y1, y2), (m1, m2)):
         assert torch.equal(a, b_)
+
+
+# ---- N4: flow ingest and ElasticTransformer ------------------------------------------------------------------
+@pytest.mark.parametrize('sizes', [(72, 128, 288, 512), (288, 512, 288, 512), (180, 320, 288, 512), (360, 640, 288, 512), (100, 150, 61, 19), (1, 1, 5, 7)])
+def test_read_flow_matches_cv2(sizes):
+    """data_loader.py:239 on the device: bit-identical to `cv2.resize(flow, (w, h)) * [w, h]` (cast by the float32 feed) and to
+    the oracle's restatement, single fields and batches."""
+    cv2 = pytest.importorskip('cv2')
+    from coupe.dvsg_b200 import frame_io
+    hs, ws, h, w = sizes
+    rng = np.random.default_rng(hs + w)
+    flows = rng.uniform(-0.05, 0.05, (3, hs, ws, 2)).astype(np.float32)
+    got = frame_io.read_flow(cu(flows), (h, w)).cpu().numpy()
+    for i in range(3):
+        ref = (cv2.resize(flows[i], (w, h)).reshape(h, w, 2) * [w, h]).astype(np.float32)
+        np.testing.assert_array_equal(got[i], ref)
+        np.testing.assert_array_equal(got[i], O.flow_ingest(flows[i], w, h))
+    np.testing.assert_array_equal(frame_io.read_flow(cu(flows[1]), (h, w)).cpu().numpy(), got[1])
+    # the ingested field is what tf_warp takes (warp_with_optical_flow.py:117-120): channel 0 = dx, 1 = dy, pixels
+    if h >= 8 and w >= 8:
+        from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+        im = rng.random((3, h, w, 3), dtype=np.float32)
+        out = tf_warp(cu(im), cu(got), h, w).cpu().numpy()
+        np.testing.assert_array_equal(out, O.tf_warp(im, got, h, w))
+
+
+@pytest.mark.parametrize('name', ['elastic_4x4', 'elastic_3x3_resize'])
+def test_elastic_transformer_vs_reference_golden(name):
+    """ElasticTransformer(out_size, 2*g*g, g).transform(inp, theta) against spatial_transformer.py:93-362 run unmodified
+    (make_golden.elastic_cases): coordinates <= 2e-5, pixels <= 1e-4, sampler bit-exact on the kernel's coordinates,
+    gradients w.r.t. the input and theta rel <= 1e-4 (corner flips removed exactly would need the TPS helper: the frames
+    are small and no corner flips at this noise level; asserted)."""
+    from coupe.dvsg_b200.spatial_transformer import ElasticTransformer
+    g = load_golden(name)
+    gs, osz = int(g['grid_size']), [int(v) for v in g['out_size']]
+    et = ElasticTransformer(osz, param_dim=2 * gs * gs, param_dim_per_side=gs)
+    im = cu(g['im']).requires_grad_(True)
+    theta = cu(g['theta']).requires_grad_(True)
+    out, x, y = et.transform(im, theta)
+    assert out.shape == tuple(g['out'].shape)
+    xn, yn = x.detach().cpu().numpy(), y.detach().cpu().numpy()
+    ex = max(np.abs(xn - g['x']).max(), np.abs(yn - g['y']).max())
+    eo = np.abs(out.detach().cpu().numpy() - g['out']).max()
+    print('%s: coord err %.2e pixel err %.2e' % (name, ex, eo))
+    assert ex <= 2e-5 and eo <= 1e-4
+    np.testing.assert_array_equal(out.detach().cpu().numpy().reshape(-1, g['im'].shape[3]), O.bilinear_interp(g['im'], xn, yn, osz))
+    (out * cu(g['g_out'])).sum().backward()
+    H, W = g['im'].shape[1:3]
+    same = np.array_equal(np.floor((xn + 1) / 2 * (W - 1)), np.floor((g['x'] + 1) / 2 * (W - 1))) and \
+        np.array_equal(np.floor((yn + 1) / 2 * (H - 1)), np.floor((g['y'] + 1) / 2 * (H - 1)))
+    assert same, 'a sampling corner flipped: compare stage-wise instead'
+    gi, gt = im.grad.cpu().numpy(), theta.grad.cpu().numpy()
+    assert np.abs(gi - g['grad_im']).max() <= 1e-4 * np.abs(g['grad_im']).max()
+    assert np.abs(gt - g['grad_theta']).max() <= 1e-4 * np.abs(g['grad_theta']).max()
+    np.testing.assert_allclose(et.get_abs_theta(cu(g['theta'])).cpu().numpy(), g['abs_theta'], atol=1e-6)
+    np.testing.assert_allclose(et.get_abs_src_points(g['im'].shape[0]).cpu().numpy(), g['abs_src'], atol=1e-6)
+
+
+def test_elastic_transformer_vs_oracle_at_the_training_shape():
+    """288 x 512, 4x4 control mesh (the constructor defaults), offsets +-0.1: coordinates vs the oracle's restatement of
+    _initialize_tps / _transform <= 2e-5, sampler bit-exact; identity theta reproduces the identity grid."""
+    from coupe.dvsg_b200.spatial_transformer import ElasticTransformer
+    b, h, w = 2, 288, 512
+    rng = np.random.default_rng(93)
+    im = smooth_image(rng, b, h, w, 3)
+    theta = rng.uniform(-0.1, 0.1, (b, 32)).astype(np.float32)
+    et = ElasticTransformer([h, w])
+    out, x, y = et.transform(cu(im), cu(theta))
+    xn, yn = x.cpu().numpy(), y.cpu().numpy()
+    r_out, r_x, r_y = O.elastic_transform(im, theta, 4, (h, w))
+    assert max(np.abs(xn - r_x).max(), np.abs(yn - r_y).max()) <= 2e-5
+    np.testing.assert_array_equal(out.cpu().numpy().reshape(-1, 3), O.bilinear_interp(im, xn, yn, (h, w)))
+    _, x0, y0 = et.transform(cu(im), cu(np.zeros((b, 32), np.float32)))
+    gx = np.tile(O.tf_linspace(-1.0, 1.0, w)[None], (h, 1)).reshape(-1)
+    assert np.abs(x0.cpu().numpy()[:h * w] - gx).max() <= 2e-5

@@ -116,3 +116,17 @@ def test_surf_loss_vs_reference_golden():
     loss, idx = O.surf_loss(g['surf'], g['x'], g['y'], g['max_dim'], b, w, h)
     assert abs(loss - float(g['loss'])) <= 1e-6 * abs(float(g['loss']))
     assert idx.max() == h * w                        # padded features hit the appended -1 entry (trainer.py:364-365)
+
+
+# ---- N4: ElasticTransformer (spatial_transformer.py:93-362 executed unmodified over the shim) ----
+@pytest.mark.parametrize('name', ['elastic_4x4', 'elastic_3x3_resize'])
+def test_elastic_transformer_vs_reference_golden(name):
+    g = load_golden(name)
+    gs, osz = int(g['grid_size']), tuple(int(v) for v in g['out_size'])
+    out, x, y = O.elastic_transform(g['im'], g['theta'], gs, osz)
+    assert max(np.abs(x - g['x']).max(), np.abs(y - g['y']).max()) <= 2e-5
+    assert np.abs(out - g['out']).max() <= 1e-4
+    _, _, _, l_inv = O.elastic_initialize(gs, osz)
+    assert np.abs(l_inv - g['l_inv']).max() <= 1e-5 * np.abs(g['l_inv']).max()
+    # the sampler on the golden's own coordinates is bit-exact (bilinear_interp, B2)
+    np.testing.assert_array_equal(O.bilinear_interp(g['im'], g['x'], g['y'], osz).reshape(g['out'].shape), g['out'])

@@ -216,3 +216,15 @@ def test_resize_restatement_matches_cv2():
     imp = np.zeros((2, 9, 1))
     imp[:, 4, 0] = 1.0
     np.testing.assert_allclose(O.resize_linear_f64(imp, 7, 2)[..., 0], cv2.resize(imp, (7, 2)), atol=1e-15)
+
+
+@pytest.mark.parametrize('sizes', [(72, 128, 288, 512), (288, 512, 288, 512), (180, 320, 288, 512), (360, 640, 288, 512), (100, 150, 61, 19), (1, 1, 5, 7)])
+def test_flow_ingest_restatement_matches_cv2(sizes):
+    """data_loader.py:239 is plain cv2 + NumPy: the oracle's restatement of cv2.resize on a float32 field is compared with
+    cv2 itself (bit-identical with cv2 4.13), then `* [w, h]` and the float32 feed."""
+    cv2 = pytest.importorskip('cv2')
+    hs, ws, h, w = sizes
+    rng = np.random.default_rng(hs + w)
+    flow = rng.uniform(-0.05, 0.05, (hs, ws, 2)).astype(np.float32)
+    ref = (cv2.resize(flow, (w, h)).reshape(h, w, 2) * [w, h]).astype(np.float32)
+    np.testing.assert_array_equal(O.flow_ingest(flow, w, h), ref)
