@@ -482,33 +482,73 @@ def run_ours(args, wl):
         mesh_h, vec_h = p.mesh.cpu().contiguous(), p.vec[:Be].cpu().contiguous()
 
         def time_pipe(fn):
+            """(streaming Mpix/s, blocking Mpix/s): e2e_steps batches submitted back to back with one wait at the end (a clip is a
+            stream of batches: the upload of batch k+1 overlaps the download of batch k), and one blocking call per batch."""
+            res = []
+            for streaming in (True, False):
+                pipe.set_async(streaming)
+                for _ in range(2):
+                    fn()
+                pipe.sync()
+                barrier()
+                ts = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    fn()   # every call uploads its batch from pinned host memory and downloads the warped frames
+                pipe.sync()
+                te = time.perf_counter() - ts
+                if world > 1:
+                    t = torch.tensor([te], device=dev, dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    te = float(t.item())
+                res.append(world * Be * H * W * args.e2e_steps / te / 1e6)
+            pipe.set_async(False)
+            return res
+        v, vb = time_pipe(lambda: pipe.thin_plate_spline(U_h, mesh_h, vec_h, out_h))
+        e2e = {'value': v, 'unit': 'Mpix/s', 'blocking_value': vb,
+               'h2d_bytes_per_step': int(U_h.numel() * 4 + vec_h.numel() * 4 + mesh_h.numel() * 4),
+               'd2h_bytes_per_step': int(out_h.numel() * 4), 'frames_per_step': Be, 'pcie_gbs': v * 24e-3,
+               'api': 'dvsg_host_tps_warp (coupe.dvsg_b200.ops.HostPipeline.thin_plate_spline), pinned host buffers; value = batches streamed '
+                      'through the pipeline (dvsg_host_pipeline_set_async + one sync per %d batches), blocking_value = one blocking call per batch' % args.e2e_steps}
+        # same call with uint8 frames on the host side (N4: ingest u/255 and egress uint8(x*255) on the device)
+        U8_h = (U_h * 255.0).to(torch.uint8).pin_memory()
+        out8_h = torch.empty_like(U8_h).pin_memory()
+        v8, v8b = time_pipe(lambda: pipe.thin_plate_spline_u8(U8_h, mesh_h, vec_h, out8_h))
+        e2e_u8 = {'value': v8, 'unit': 'Mpix/s', 'blocking_value': v8b,
+                  'h2d_bytes_per_step': int(U8_h.numel() + vec_h.numel() * 4 + mesh_h.numel() * 4),
+                  'd2h_bytes_per_step': int(out8_h.numel()), 'frames_per_step': Be, 'pcie_gbs': v8 * 6e-3,
+                  'api': 'dvsg_host_tps_warp_u8 (HostPipeline.thin_plate_spline_u8): uint8 BGR frames in and out, eval.py:76-81,112-113 on the device'}
+        pipe.close()
+        del U_h, out_h, U8_h, out8_h
+    if kind == 'flow' and not args.no_e2e:
+        Be = min(B, args.e2e_frames)
+        pipe = ops.HostPipeline(H, W, 3, 16, frames_per_chunk=max(1, min(args.e2e_chunk, Be)), n_slots=args.e2e_slots, device=local)
+        im_h = torch.empty((Be, H, W, 3), dtype=torch.float32).pin_memory()
+        im_h.copy_(p.U[:Be])
+        fl_h = torch.empty((Be, H, W, 2), dtype=torch.float32).pin_memory()
+        fl_h.copy_(p.flow[:Be])
+        out_h = torch.empty_like(im_h).pin_memory()
+        res = []
+        for streaming in (True, False):
+            pipe.set_async(streaming)
             for _ in range(2):
-                fn()
+                pipe.tf_warp(im_h, fl_h, out_h)
+            pipe.sync()
             barrier()
             ts = time.perf_counter()
             for _ in range(args.e2e_steps):
-                fn()   # blocking: returns when the output is complete in host memory
+                pipe.tf_warp(im_h, fl_h, out_h)
+            pipe.sync()
             te = time.perf_counter() - ts
             if world > 1:
                 t = torch.tensor([te], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 te = float(t.item())
-            return world * Be * H * W * args.e2e_steps / te / 1e6
-        v = time_pipe(lambda: pipe.thin_plate_spline(U_h, mesh_h, vec_h, out_h))
-        e2e = {'value': v, 'unit': 'Mpix/s',
-               'h2d_bytes_per_step': int(U_h.numel() * 4 + vec_h.numel() * 4 + mesh_h.numel() * 4),
-               'd2h_bytes_per_step': int(out_h.numel() * 4), 'frames_per_step': Be,
-               'api': 'dvsg_host_tps_warp (coupe.dvsg_b200.ops.HostPipeline.thin_plate_spline), pinned host buffers'}
-        # same call with uint8 frames on the host side (N4: ingest u/255 and egress uint8(x*255) on the device)
-        U8_h = (U_h * 255.0).to(torch.uint8).pin_memory()
-        out8_h = torch.empty_like(U8_h).pin_memory()
-        v8 = time_pipe(lambda: pipe.thin_plate_spline_u8(U8_h, mesh_h, vec_h, out8_h))
-        e2e_u8 = {'value': v8, 'unit': 'Mpix/s',
-                  'h2d_bytes_per_step': int(U8_h.numel() + vec_h.numel() * 4 + mesh_h.numel() * 4),
-                  'd2h_bytes_per_step': int(out8_h.numel()), 'frames_per_step': Be,
-                  'api': 'dvsg_host_tps_warp_u8 (HostPipeline.thin_plate_spline_u8): uint8 BGR frames in and out, eval.py:76-81,112-113 on the device'}
+            res.append(world * Be * H * W * args.e2e_steps / te / 1e6)
+        e2e = {'value': res[0], 'unit': 'Mpix/s', 'blocking_value': res[1], 'h2d_bytes_per_step': int(im_h.numel() * 4 + fl_h.numel() * 4),
+               'd2h_bytes_per_step': int(out_h.numel() * 4), 'frames_per_step': Be, 'pcie_gbs': res[0] * 32e-3,
+               'api': 'dvsg_host_flow_warp (HostPipeline.tf_warp), pinned host buffers; value = batches streamed, blocking_value = one blocking call per batch'}
         pipe.close()
-        del U_h, out_h, U8_h, out8_h
+        del im_h, fl_h, out_h
     del p
     torch.cuda.empty_cache()
 
@@ -631,7 +671,7 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--e2e-frames', type=int, default=64)
-    ap.add_argument('--e2e-chunk', type=int, default=4, help='frames per staging chunk of the host pipeline')
+    ap.add_argument('--e2e-chunk', type=int, default=8, help='frames per staging chunk of the host pipeline')
     ap.add_argument('--e2e-slots', type=int, default=4, help='device staging slots (streams) of the host pipeline')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')

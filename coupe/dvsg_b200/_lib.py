@@ -46,6 +46,9 @@ PROTOTYPES = {
     'dvsg_host_pipeline_create': (c_int, [ctypes.POINTER(c_void_p)] + [c_int] * 7),
     'dvsg_host_pipeline_destroy': (None, [_P]),
     'dvsg_host_tps_warp': (c_int, [_P, _P, _P, _P, _P, c_int]),
+    'dvsg_host_flow_warp': (c_int, [_P, _P, _P, _P, c_int]),
+    'dvsg_host_pipeline_set_async': (c_int, [_P, c_int]),
+    'dvsg_host_pipeline_sync': (c_int, [_P]),
     'dvsg_frames_u8_to_f32': (c_int, [_P, _P, c_longlong, c_int, _P]),
     'dvsg_frames_f32_to_u8': (c_int, [_P, _P, c_longlong, c_int, _P]),
     'dvsg_frames_u8_resize_to_f32': (c_int, [_P, _P] + [c_int] * 6 + [_P]),

@@ -52,6 +52,10 @@ struct dvsg_host_pipeline {
     std::vector<cudaStream_t> streams;
     std::vector<float*> d_in, d_out, d_vec, d_T;
     std::vector<unsigned char*> d_in8, d_out8;     // uint8 staging of the frames (allocated by the first u8 call)
+    std::vector<float*> d_flow;                    // flow staging (allocated by the first tf_warp call)
+    std::vector<float> h_coord;                    // mesh whose inverse d_winv holds (re-prepared only when the caller's mesh changes)
+    int async;                                     // 1: calls return once their work is enqueued (dvsg_host_pipeline_sync waits)
+    int next_chunk;                                // slots rotate across calls, so consecutive calls overlap in async mode
 };
 
 #define DVSG_CUDA(call)                                                   \
@@ -73,6 +77,8 @@ extern "C" int dvsg_host_pipeline_create(dvsg_host_pipeline** out, int device, i
     p->frame_elems = (size_t)H * W * C;
     p->d_coord = nullptr;
     p->d_winv = nullptr;
+    p->async = 0;
+    p->next_chunk = 0;
     p->winv_bytes = dvsg_tps_prepare_workspace_bytes(1, pn, 0);
     *out = p;
     DVSG_CUDA(cudaMalloc(&p->d_coord, (size_t)pn * 2 * sizeof(float)));
@@ -104,14 +110,43 @@ extern "C" void dvsg_host_pipeline_destroy(dvsg_host_pipeline* p) {
     for (auto q : p->d_T) cudaFree(q);
     for (auto q : p->d_in8) cudaFree(q);
     for (auto q : p->d_out8) cudaFree(q);
+    for (auto q : p->d_flow) cudaFree(q);
     cudaFree(p->d_coord);
     cudaFree(p->d_winv);
     delete p;
 }
 
-__global__ void add_mesh_kernel(const float* __restrict__ coord, float* __restrict__ vec, int n, int per_frame) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) vec[i] = __fadd_rn(coord[i % per_frame], vec[i]);   // coord + vector, ThinPlateSpline.py:161
+// Upload the mesh and invert its system -- only when it differs from the one the pipeline already holds (a clip's mesh is a
+// constant, model.py:62-68): later calls skip the upload, the inversion and the synchronisation they need.
+static int host_prepare_mesh(dvsg_host_pipeline* p, const float* coord_host) {
+    const size_t n = (size_t)p->pn * 2;
+    if (p->h_coord.size() == n && memcmp(p->h_coord.data(), coord_host, n * sizeof(float)) == 0) return DVSG_OK;
+    for (auto st : p->streams) DVSG_CUDA(cudaStreamSynchronize(st));      // chunks in flight still read the old inverse
+    DVSG_CUDA(cudaMemcpyAsync(p->d_coord, coord_host, n * sizeof(float), cudaMemcpyHostToDevice, p->streams[0]));
+    const int rc0 = dvsg_tps_prepare(p->d_coord, 0, 1, p->pn, p->d_winv, p->winv_bytes, p->streams[0]);
+    if (rc0) return rc0;
+    DVSG_CUDA(cudaStreamSynchronize(p->streams[0]));
+    p->h_coord.assign(coord_host, coord_host + n);
+    return DVSG_OK;
+}
+
+static int host_finish(dvsg_host_pipeline* p) {
+    if (p->async) return DVSG_OK;
+    for (auto st : p->streams) DVSG_CUDA(cudaStreamSynchronize(st));
+    return DVSG_OK;
+}
+
+extern "C" int dvsg_host_pipeline_set_async(dvsg_host_pipeline* p, int async) {
+    DVSG_REQUIRE(p, "host_pipeline_set_async: null pipeline");
+    p->async = async ? 1 : 0;
+    return DVSG_OK;
+}
+
+extern "C" int dvsg_host_pipeline_sync(dvsg_host_pipeline* p) {
+    DVSG_REQUIRE(p, "host_pipeline_sync: null pipeline");
+    DVSG_CUDA(cudaSetDevice(p->device));
+    for (auto st : p->streams) DVSG_CUDA(cudaStreamSynchronize(st));
+    return DVSG_OK;
 }
 
 extern "C" int dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, const float* coord_host,
@@ -122,13 +157,11 @@ extern "C" int dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, co
     DVSG_CUDA(cudaSetDevice(p->device));
     const size_t fe = p->frame_elems;
     const int pn = p->pn;
-    DVSG_CUDA(cudaMemcpyAsync(p->d_coord, coord_host, (size_t)pn * 2 * sizeof(float), cudaMemcpyHostToDevice, p->streams[0]));
-    {   // one inversion of the mesh's system per call; every chunk then only applies it
-        const int rc0 = dvsg_tps_prepare(p->d_coord, 0, 1, pn, p->d_winv, p->winv_bytes, p->streams[0]);
+    {   // the inverse of the mesh's system is computed when the mesh changes; every chunk only applies it
+        const int rc0 = host_prepare_mesh(p, coord_host);
         if (rc0) return rc0;
     }
-    DVSG_CUDA(cudaStreamSynchronize(p->streams[0]));
-    int chunk = 0;
+    int& chunk = p->next_chunk;
     for (int f0 = 0; f0 < B; f0 += p->fpc, ++chunk) {
         const int s = chunk % p->n_slots;
         const int nf = B - f0 < p->fpc ? B - f0 : p->fpc;
@@ -136,20 +169,13 @@ extern "C" int dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, co
         DVSG_CUDA(cudaMemcpyAsync(p->d_in[s], U_host + (size_t)f0 * fe, fe * nf * sizeof(float), cudaMemcpyHostToDevice, st));
         DVSG_CUDA(cudaMemcpyAsync(p->d_vec[s], vector_host + (size_t)f0 * pn * 2, (size_t)nf * pn * 2 * sizeof(float),
                                   cudaMemcpyHostToDevice, st));
-        const int n = nf * pn * 2;
-        add_mesh_kernel<<<(n + 255) / 256, 256, 0, st>>>(p->d_coord, p->d_vec[s], n, pn * 2);
-        count_launch();
-        int rc = check_launch("add_mesh_kernel");
-        if (rc) return rc;
-        rc = dvsg_tps_solve_prepared(p->d_coord, 0, p->d_vec[s], p->d_T[s], nf, pn, p->d_winv, p->winv_bytes, st);
-        if (rc) return rc;
-        rc = dvsg_tps_warp_fwd(p->d_in[s], p->d_coord, 0, p->d_T[s], p->d_out[s], nullptr, nullptr, nullptr, nf, p->H, p->W,
-                               p->C, p->H, p->W, pn, 0, st);
+        // coord + vector, the prepared solve and the fused warp: one launch for meshes up to 29 points, two otherwise
+        const int rc = dvsg_tps_warp_frames_offsets(p->d_in[s], p->d_coord, p->d_vec[s], p->d_winv, p->winv_bytes, p->d_T[s], p->d_out[s], nullptr,
+                                                    nullptr, nullptr, nf, p->H, p->W, p->C, p->H, p->W, pn, st);
         if (rc) return rc;
         DVSG_CUDA(cudaMemcpyAsync(out_host + (size_t)f0 * fe, p->d_out[s], fe * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    for (auto st : p->streams) DVSG_CUDA(cudaStreamSynchronize(st));
-    return DVSG_OK;
+    return host_finish(p);
 }
 
 // Same pipeline with uint8 frames on the host side: the ingest u/255 (+ optional BGR->RGB) and the
@@ -171,13 +197,11 @@ extern "C" int dvsg_host_tps_warp_u8(dvsg_host_pipeline* p, const unsigned char*
         DVSG_CUDA(cudaMalloc(&b, fe * p->fpc));
         p->d_out8.push_back(b);
     }
-    DVSG_CUDA(cudaMemcpyAsync(p->d_coord, coord_host, (size_t)pn * 2 * sizeof(float), cudaMemcpyHostToDevice, p->streams[0]));
-    {   // one inversion of the mesh's system per call; every chunk then only applies it
-        const int rc0 = dvsg_tps_prepare(p->d_coord, 0, 1, pn, p->d_winv, p->winv_bytes, p->streams[0]);
+    {
+        const int rc0 = host_prepare_mesh(p, coord_host);
         if (rc0) return rc0;
     }
-    DVSG_CUDA(cudaStreamSynchronize(p->streams[0]));
-    int chunk = 0;
+    int& chunk = p->next_chunk;
     for (int f0 = 0; f0 < B; f0 += p->fpc, ++chunk) {
         const int s = chunk % p->n_slots;
         const int nf = B - f0 < p->fpc ? B - f0 : p->fpc;
@@ -187,20 +211,39 @@ extern "C" int dvsg_host_tps_warp_u8(dvsg_host_pipeline* p, const unsigned char*
                                   cudaMemcpyHostToDevice, st));
         int rc = dvsg_frames_u8_to_f32(p->d_in8[s], p->d_in[s], (long long)nf * p->H * p->W, swap_rb, st);
         if (rc) return rc;
-        const int n = nf * pn * 2;
-        add_mesh_kernel<<<(n + 255) / 256, 256, 0, st>>>(p->d_coord, p->d_vec[s], n, pn * 2);
-        count_launch();
-        rc = check_launch("add_mesh_kernel");
-        if (rc) return rc;
-        rc = dvsg_tps_solve_prepared(p->d_coord, 0, p->d_vec[s], p->d_T[s], nf, pn, p->d_winv, p->winv_bytes, st);
-        if (rc) return rc;
-        rc = dvsg_tps_warp_fwd(p->d_in[s], p->d_coord, 0, p->d_T[s], p->d_out[s], nullptr, nullptr, nullptr, nf, p->H, p->W,
-                               p->C, p->H, p->W, pn, 0, st);
+        rc = dvsg_tps_warp_frames_offsets(p->d_in[s], p->d_coord, p->d_vec[s], p->d_winv, p->winv_bytes, p->d_T[s], p->d_out[s], nullptr, nullptr,
+                                          nullptr, nf, p->H, p->W, p->C, p->H, p->W, pn, st);
         if (rc) return rc;
         rc = dvsg_frames_f32_to_u8(p->d_out[s], p->d_out8[s], (long long)nf * p->H * p->W, swap_rb, st);
         if (rc) return rc;
         DVSG_CUDA(cudaMemcpyAsync(out_host + (size_t)f0 * fe, p->d_out8[s], fe * nf, cudaMemcpyDeviceToHost, st));
     }
-    for (auto st : p->streams) DVSG_CUDA(cudaStreamSynchronize(st));
-    return DVSG_OK;
+    return host_finish(p);
+}
+
+// tf_warp(im, flow, H, W) on HOST buffers (warp_with_optical_flow.py:96-176 as trainer.py:246-247 / model.py:87-88 call it):
+// frames and flow fields go up (12 + 8 bytes per pixel), warped frames come back (12).  Same chunked, multi-stream pipeline.
+extern "C" int dvsg_host_flow_warp(dvsg_host_pipeline* p, const float* im_host, const float* flow_host, float* out_host, int B) {
+    DVSG_REQUIRE(p && B >= 0, "host_flow_warp: bad argument");
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(im_host && flow_host && out_host, "host_flow_warp: null pointer");
+    DVSG_CUDA(cudaSetDevice(p->device));
+    const size_t fe = p->frame_elems, ff = (size_t)p->H * p->W * 2;
+    while ((int)p->d_flow.size() < p->n_slots) {
+        float* a = nullptr;
+        DVSG_CUDA(cudaMalloc(&a, ff * p->fpc * sizeof(float)));
+        p->d_flow.push_back(a);
+    }
+    int& chunk = p->next_chunk;
+    for (int f0 = 0; f0 < B; f0 += p->fpc, ++chunk) {
+        const int s = chunk % p->n_slots;
+        const int nf = B - f0 < p->fpc ? B - f0 : p->fpc;
+        cudaStream_t st = p->streams[s];
+        DVSG_CUDA(cudaMemcpyAsync(p->d_in[s], im_host + (size_t)f0 * fe, fe * nf * sizeof(float), cudaMemcpyHostToDevice, st));
+        DVSG_CUDA(cudaMemcpyAsync(p->d_flow[s], flow_host + (size_t)f0 * ff, ff * nf * sizeof(float), cudaMemcpyHostToDevice, st));
+        const int rc = dvsg_flow_warp_fwd(p->d_in[s], p->d_flow[s], p->d_out[s], nf, p->H, p->W, p->C, 0, st);
+        if (rc) return rc;
+        DVSG_CUDA(cudaMemcpyAsync(out_host + (size_t)f0 * fe, p->d_out[s], fe * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    return host_finish(p);
 }

@@ -489,6 +489,30 @@ class HostPipeline(object):
         _lib.check(rc, 'dvsg_host_tps_warp_u8')
         return out_host
 
+    def tf_warp(self, im_host, flow_host, out_host=None):
+        """tf_warp(im, flow, H, W) on HOST buffers: im_host [B,H,W,C], flow_host [B,H,W,2] CPU fp32 contiguous (pinned for full
+        PCIe bandwidth).  Returns out_host."""
+        lib = _lib.load()
+        for name, t in (('im', im_host), ('flow', flow_host)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError('%s must be a contiguous fp32 CPU tensor' % name)
+        B = im_host.shape[0]
+        if tuple(im_host.shape[1:]) != self.shape or tuple(flow_host.shape) != (B, self.shape[0], self.shape[1], 2):
+            raise ValueError('shape mismatch with the pipeline configuration')
+        if out_host is None:
+            out_host = torch.empty_like(im_host, pin_memory=im_host.is_pinned())
+        rc = lib.dvsg_host_flow_warp(self._h, im_host.data_ptr(), flow_host.data_ptr(), out_host.data_ptr(), B)
+        _lib.check(rc, 'dvsg_host_flow_warp')
+        return out_host
+
+    def set_async(self, flag=True):
+        """Streaming mode: calls return once enqueued, so consecutive batches overlap (upload of batch k+1 with the download of
+        batch k); sync() waits.  Host buffers of a call must stay valid, and its outputs unread, until sync()."""
+        _lib.check(_lib.load().dvsg_host_pipeline_set_async(self._h, 1 if flag else 0), 'dvsg_host_pipeline_set_async')
+
+    def sync(self):
+        _lib.check(_lib.load().dvsg_host_pipeline_sync(self._h), 'dvsg_host_pipeline_sync')
+
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
             _lib.load().dvsg_host_pipeline_destroy(self._h)

@@ -208,9 +208,19 @@ int  dvsg_host_pipeline_create(dvsg_host_pipeline** out, int device, int H, int 
                                int pn, int frames_per_chunk, int n_slots);
 void dvsg_host_pipeline_destroy(dvsg_host_pipeline* p);
 /* U_host [B,H,W,C], coord_host [pn,2] (shared mesh) , vector_host [B,pn,2],
- * out_host [B,H,W,C]; blocks until out_host is complete.                               */
+ * out_host [B,H,W,C]; blocks until out_host is complete (unless the pipeline is asynchronous).
+ * The mesh's system is inverted when coord_host differs from the previous call's mesh.   */
 int  dvsg_host_tps_warp(dvsg_host_pipeline* p, const float* U_host, const float* coord_host,
                         const float* vector_host, float* out_host, int B);
+/* tf_warp on host buffers: im_host [B,H,W,C], flow_host [B,H,W,2] -> out_host [B,H,W,C]  */
+int  dvsg_host_flow_warp(dvsg_host_pipeline* p, const float* im_host, const float* flow_host,
+                         float* out_host, int B);
+/* Streaming use (a clip is a long sequence of batches): with async != 0 the dvsg_host_* calls
+ * return as soon as their copies and kernels are enqueued, so the upload of batch k+1 overlaps
+ * the download of batch k; dvsg_host_pipeline_sync waits for everything submitted so far.  The
+ * host buffers of a call must stay valid (and its outputs unread) until the sync.         */
+int  dvsg_host_pipeline_set_async(dvsg_host_pipeline* p, int async);
+int  dvsg_host_pipeline_sync(dvsg_host_pipeline* p);
 
 
 /* ---- N4: frame ingest / egress (the steps on either side of the warp in eval.py) -------------

@@ -885,3 +885,40 @@ def test_elastic_transformer_vs_oracle_at_the_training_shape():
     _, x0, y0 = et.transform(cu(im), cu(np.zeros((b, 32), np.float32)))
     gx = np.tile(O.tf_linspace(-1.0, 1.0, w)[None], (h, 1)).reshape(-1)
     assert np.abs(x0.cpu().numpy()[:h * w] - gx).max() <= 2e-5
+
+
+def test_host_pipeline_streaming_mesh_change_and_tf_warp():
+    """HostPipeline: (1) asynchronous (streaming) submission gives the same frames as blocking calls; (2) a second mesh makes
+    the pipeline invert the new system (the inverse is cached per mesh, not per call); (3) tf_warp on host buffers equals the
+    device tf_warp bit for bit; (4) a 6x6 mesh (N = 39 > 32: two launches per chunk) works through the same pipeline."""
+    from coupe.dvsg_b200 import ops
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline
+    from coupe.dvsg_b200.warp_with_optical_flow import tf_warp
+    rng = np.random.default_rng(77)
+    B, H, W = 7, 96, 160
+    u = smooth_image(rng, B, H, W, 3)
+    U_h = torch.from_numpy(u).pin_memory()
+    for m in (4, 6):
+        pn = m * m
+        pipe = ops.HostPipeline(H, W, 3, pn, frames_per_chunk=2, n_slots=3)
+        for trial in range(2):      # two different meshes through the same pipeline
+            mesh = tiled_mesh(m, m, 1)[0] + (rng.uniform(-0.02, 0.02, (pn, 2)).astype(np.float32) if trial else 0)
+            vec = rng.uniform(-0.1, 0.1, (B, pn, 2)).astype(np.float32)
+            ref, _, _ = ThinPlateSpline(cu(u), cu(mesh), cu(vec), [H, W], return_grid=False)
+            out_b = pipe.thin_plate_spline(U_h, torch.from_numpy(mesh), torch.from_numpy(vec))
+            assert torch.equal(out_b, ref.cpu())
+            pipe.set_async(True)
+            outs = [torch.empty_like(U_h).pin_memory() for _ in range(3)]
+            for o in outs:
+                pipe.thin_plate_spline(U_h, torch.from_numpy(mesh), torch.from_numpy(vec), o)
+            pipe.sync()
+            pipe.set_async(False)
+            for o in outs:
+                assert torch.equal(o, ref.cpu())
+        pipe.close()
+    flow = smooth_flow(rng, B, H, W).astype(np.float32)
+    pipe = ops.HostPipeline(H, W, 3, 16, frames_per_chunk=3, n_slots=2)
+    got = pipe.tf_warp(U_h, torch.from_numpy(flow).pin_memory())
+    assert torch.equal(got, tf_warp(cu(u), cu(flow), H, W).cpu())
+    np.testing.assert_array_equal(got.numpy(), O.tf_warp(u, flow, H, W))
+    pipe.close()
