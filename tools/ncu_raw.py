@@ -17,6 +17,19 @@ for k in keys:
     if k in hdr:
         i = hdr.index(k)
         print('%-78s %-10s %s' % (k, units[i], data[0][i]))
+# sectors per request of the LSU global accesses (derived: the ratio metric itself is not part of --set full); the frames
+# themselves move through TMA (no LSU requests), so these are the few per-lane accesses that remain (flow / grad_out loads,
+# grid stores, the per-pixel fallback path)
+col = {h: i for i, h in enumerate(hdr)}
+for op in ('ld', 'st', 'red'):
+    rq, sc = 'l1tex__t_requests_pipe_lsu_mem_global_op_%s.sum' % op, 'l1tex__t_sectors_pipe_lsu_mem_global_op_%s.sum' % op
+    if rq in col and sc in col:
+        try:
+            r, t = float(data[0][col[rq]]), float(data[0][col[sc]])
+            if r > 0:
+                print('%-78s %-10s %.2f  (%d requests, %d sectors)' % ('sectors per request, LSU global %s (derived)' % op, 'ratio', t / r, r, t))
+        except ValueError:
+            pass
 print('--- warp stall breakdown (per warp active, %)')
 st = []
 for i, h in enumerate(hdr):
