@@ -14,6 +14,9 @@
 //
 // HBM traffic (algorithmic): 4C B read + 4C B written per output pixel (+8 B if x, y are
 // materialised, +8 B flow read for MODE_FLOW, +8 B x,y read for MODE_GIVEN).
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <stdlib.h>
+
 #include "dvsg_common.cuh"
 #include "sampler_math.cuh"
 
@@ -324,6 +327,142 @@ __global__ void __launch_bounds__(WIDE_NT) warp_fwd_wide_kernel(const FwdParams 
     }
 }
 
+// ---- wide pixels, TMA-staged (round 2) ----------------------------------------------------------------------------
+// The kernel above gathers its four corners straight from global memory and spends 78 instructions per (pixel, channel
+// pair): it is ISSUE-bound (80 % issue-slot utilisation) at 0.60 of the HBM roofline.  Here the CTA (128 threads, a
+// 16 x 8-pixel output tile) stages the tile's source FOOTPRINT in shared memory with two side-by-side 3-D TMA tensor
+// copies ([B][H][W*C] floats; a box is at most 256 elements wide = 14 pixels of 18 channels), zero-filled outside the
+// frame -- the zero padding of bilinear_interp / tf_warp -- and every thread then owns ONE pixel:
+//   1  sampling coordinate, padded corners and weights (same operations, same order as everywhere else);
+//   2  CTA bounding box of the corners (REDUX per warp, 4 x 4 words of shared memory), origin aligned to 16 bytes;
+//   3  thread 0 issues the two TMA copies; every thread turns its corners into shared-memory offsets (registers, no records);
+//   4  per channel pair: four LDS.64 (lanes 72 bytes apart: conflict-free per half-warp at C = 18), the blend in add_n order
+//      in packed fp32x2, one STS.64 into the output tile; 15 instructions per pair;
+//   5  the output tile leaves with two TMA tensor stores (8 pixels x 8 rows each), clipped at the frame edge by the hardware.
+// A tile whose footprint does not fit 2 boxes x 12 rows gathers from global memory instead (same arithmetic).
+// Tried on the way (C = 18, 32 x 288 x 512): (pixel, channel pair) work items with per-pixel records in shared memory and
+// direct STG.64 -- 0.58 of HBM as first written, 0.68 with 32-bit indexing and a packed blend; three pairs per item 0.64.
+constexpr int WS_PX = 16, WS_ROWS = 8, WS_NT = WS_PX * WS_ROWS, WS_BOX_ROWS = 12, WS_OBOX_PX = 8;
+
+__device__ __forceinline__ void ws_tma_load_3d(uint32_t dst_smem, const void* tmap, int x, int y, int z, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst_smem), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void ws_tma_store_3d(const void* tmap, int x, int y, int z, uint32_t src_smem) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tmap), "r"(x), "r"(y), "r"(z), "r"(src_smem) : "memory");
+}
+struct alignas(64) WideMaps { CUtensorMap src, out; };
+
+template <int MODE>
+__global__ void __launch_bounds__(WS_NT) warp_fwd_wide_staged_kernel(const FwdParams p, const __grid_constant__ WideMaps maps, const int pxb,
+                                                                     const int pal_shift, const int stage_bytes, const float one) {
+    extern __shared__ __align__(128) unsigned char ws_smem[];      // [2 boxes][WS_BOX_ROWS][pxb * C] floats, then the output tile
+    __shared__ int s_bb[4][4];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const int H = p.H, W = p.W, C = p.C, oh = p.oh, ow = p.ow, cv = C >> 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = blockIdx.x * WS_PX, row0 = blockIdx.y * WS_ROWS, b = blockIdx.z;
+    const uint32_t mbar = smem_u32(&s_mbar);
+    if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    // ---- 1: coordinate, corners, weights of this thread's pixel (pixels past the frame edge repeat the edge pixel) -------
+    const int pr = tid / WS_PX, pc = tid % WS_PX;
+    const int col = min(col0 + pc, ow - 1), row = min(row0 + pr, oh - 1);
+    const bool live = col0 + pc < ow && row0 + pr < oh;
+    Corners c;
+    {
+        const size_t pix = ((size_t)b * oh + row) * ow + col;
+        float xq, yq;      // pixel-space coordinate before the clip
+        if (MODE == MODE_GIVEN) {
+            xq = zp_pix_from_norm(__ldg(p.x_in + pix), W);
+            yq = zp_pix_from_norm(__ldg(p.y_in + pix), H);
+        } else if (MODE == MODE_FLOW) {
+            const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + pix);
+            xq = DVSG_ADD((float)col, f.x);   // warp_with_optical_flow.py:107-120
+            yq = DVSG_ADD((float)row, f.y);
+        } else {
+            const int nt = p.projective ? 8 : 6;
+            const float* th = p.theta + (size_t)b * nt;
+            const float xt = lin_coord(col, p.step_x), yt = lin_coord(row, p.step_y);
+            float xn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 0), xt), DVSG_MUL(__ldg(th + 1), yt)), __ldg(th + 2));
+            float yn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 3), xt), DVSG_MUL(__ldg(th + 4), yt)), __ldg(th + 5));
+            if (p.projective) {
+                const float zn = DVSG_ADD(DVSG_ADD(DVSG_MUL(__ldg(th + 6), xt), DVSG_MUL(__ldg(th + 7), yt)), 1.0f);
+                xn = zn != 0.0f ? DVSG_DIV(xn, zn) : 0.0f;   // tf.div_no_nan, :446-447
+                yn = zn != 0.0f ? DVSG_DIV(yn, zn) : 0.0f;
+            }
+            if (p.x_out && live) { p.x_out[pix] = xn; p.y_out[pix] = yn; }
+            xq = zp_pix_from_norm(xn, W);
+            yq = zp_pix_from_norm(yn, H);
+        }
+        c = zp_corners(xq, yq, W, H);      // padded corners in [0, W+1] x [0, H+1]; frame index = padded index - 1
+    }
+    // ---- 2: bounding box of the tile's corners (frame coordinates; the padding ring is part of it) ----------------
+    {
+        const int xl = __reduce_min_sync(0xffffffffu, c.x0 - 1), xh = __reduce_max_sync(0xffffffffu, c.x1 - 1);
+        const int yl = __reduce_min_sync(0xffffffffu, c.y0 - 1), yh = __reduce_max_sync(0xffffffffu, c.y1 - 1);
+        if (lane == 0) { s_bb[warp][0] = xl; s_bb[warp][1] = xh; s_bb[warp][2] = yl; s_bb[warp][3] = yh; }
+    }
+    __syncthreads();
+    const int x_lo = min(min(s_bb[0][0], s_bb[1][0]), min(s_bb[2][0], s_bb[3][0])), x_hi = max(max(s_bb[0][1], s_bb[1][1]), max(s_bb[2][1], s_bb[3][1]));
+    const int y_lo = min(min(s_bb[0][2], s_bb[1][2]), min(s_bb[2][2], s_bb[3][2])), y_hi = max(max(s_bb[0][3], s_bb[1][3]), max(s_bb[2][3], s_bb[3][3]));
+    // origin aligned down to 2^pal_shift pixels (that many pixels of C floats are a multiple of 16 bytes: TMA box origins must be 16-byte aligned)
+    const int fx0 = (x_lo >> pal_shift) << pal_shift;      // arithmetic shift: rounds toward -infinity
+    const bool staged = x_hi - fx0 + 1 <= 2 * pxb && y_hi - y_lo + 1 <= WS_BOX_ROWS;
+    const int box_f2 = WS_BOX_ROWS * pxb * cv;      // float2 elements per box
+    const int box1_f2 = (box_f2 + 15) & ~15;        // the second box starts at the next multiple of 128 bytes (TMA destination alignment)
+    // ---- 3: TMA copies of the footprint; corner offsets ---------------------------------------------------------------
+    if (staged && tid == 0) {
+        mbar_arrive_expect_tx(mbar, (unsigned)(2 * box_f2 * 8));
+        ws_tma_load_3d(smem_u32(ws_smem), &maps.src, fx0 * C, y_lo, b, mbar);
+        ws_tma_load_3d(smem_u32(ws_smem) + (unsigned)(box1_f2 * 8), &maps.src, (fx0 + pxb) * C, y_lo, b, mbar);
+    }
+    const float2 w00 = make_float2(DVSG_MUL(c.ax1, c.ay1), DVSG_MUL(c.ax1, c.ay1)), w01 = make_float2(DVSG_MUL(c.ax0, c.ay1), DVSG_MUL(c.ax0, c.ay1));
+    const float2 w10 = make_float2(DVSG_MUL(c.ax1, c.ay0), DVSG_MUL(c.ax1, c.ay0)), w11 = make_float2(DVSG_MUL(c.ax0, c.ay0), DVSG_MUL(c.ax0, c.ay0));
+    const float2 one2 = make_float2(one, one);      // 1.0f from the kernel arguments: a + b as fma(a, 1, b), rounded once, not contracted
+    // this thread's pixel in the output tile: two boxes of 8 pixels x 8 rows, each dense [row][8 * C floats]
+    float2* const otile = reinterpret_cast<float2*>(ws_smem + stage_bytes);
+    float2* const o = otile + (pc / WS_OBOX_PX) * (WS_ROWS * WS_OBOX_PX * cv) + (pr * WS_OBOX_PX + pc % WS_OBOX_PX) * cv;
+    // ---- 4: per channel pair: gather, blend, stage -------------------------------------------------------------------
+    if (staged) {
+        // offsets in float2 units inside the staging buffer; corners in the padding ring read the TMA's zero fill
+        const int xa = c.x0 - 1 - fx0, xb = c.x1 - 1 - fx0, ya = c.y0 - 1 - y_lo, yb = c.y1 - 1 - y_lo;
+        const int oa = xa >= pxb ? box1_f2 + (xa - pxb) * cv : xa * cv, ob = xb >= pxb ? box1_f2 + (xb - pxb) * cv : xb * cv;
+        const float2* __restrict__ stage = reinterpret_cast<const float2*>(ws_smem);
+        const float2 *__restrict__ p00 = stage + ya * pxb * cv + oa, *__restrict__ p01 = stage + ya * pxb * cv + ob;
+        const float2 *__restrict__ p10 = stage + yb * pxb * cv + oa, *__restrict__ p11 = stage + yb * pxb * cv + ob;
+        mbar_wait(mbar, 0);
+#pragma unroll 3
+        for (int k = 0; k < cv; ++k) {
+            // add_n([w00*I00, w01*I01, w10*I10, w11*I11]) left to right (spatial_transformer.py:557-562), both channels of the pair at once
+            const float2 t00 = __fmul2_rn(w00, p00[k]), t01 = __fmul2_rn(w01, p01[k]), t10 = __fmul2_rn(w10, p10[k]), t11 = __fmul2_rn(w11, p11[k]);
+            o[k] = __ffma2_rn(__ffma2_rn(__ffma2_rn(t00, one2, t01), one2, t10), one2, t11);
+        }
+    } else {
+        const bool vx0 = zp_valid(c.x0, W), vx1 = zp_valid(c.x1, W), vy0 = zp_valid(c.y0, H), vy1 = zp_valid(c.y1, H);
+        const float2* __restrict__ srcb = reinterpret_cast<const float2*>(p.src + (size_t)b * H * W * C);
+        const float2 z = make_float2(0.0f, 0.0f);
+        const bool v00 = vx0 && vy0, v01 = vx1 && vy0, v10 = vx0 && vy1, v11 = vx1 && vy1;
+        const float2 *p00 = srcb + (v00 ? ((c.y0 - 1) * W + (c.x0 - 1)) * cv : 0), *p01 = srcb + (v01 ? ((c.y0 - 1) * W + (c.x1 - 1)) * cv : 0);
+        const float2 *p10 = srcb + (v10 ? ((c.y1 - 1) * W + (c.x0 - 1)) * cv : 0), *p11 = srcb + (v11 ? ((c.y1 - 1) * W + (c.x1 - 1)) * cv : 0);
+        for (int k = 0; k < cv; ++k) {
+            const float2 t00 = __fmul2_rn(w00, v00 ? __ldg(p00 + k) : z), t01 = __fmul2_rn(w01, v01 ? __ldg(p01 + k) : z);
+            const float2 t10 = __fmul2_rn(w10, v10 ? __ldg(p10 + k) : z), t11 = __fmul2_rn(w11, v11 ? __ldg(p11 + k) : z);
+            o[k] = __ffma2_rn(__ffma2_rn(__ffma2_rn(t00, one2, t01), one2, t10), one2, t11);
+        }
+    }
+    // ---- 5: output tile -> global with two TMA tensor stores (clipped at the frame edge) --------------------------------
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t os = smem_u32(otile);
+        ws_tma_store_3d(&maps.out, col0 * C, row0, b, os);
+        if (col0 + WS_OBOX_PX < ow) ws_tma_store_3d(&maps.out, (col0 + WS_OBOX_PX) * C, row0, b, os + (unsigned)(WS_ROWS * WS_OBOX_PX * C * 4));
+        bulk_commit();
+        bulk_wait_read0();      // shared memory must outlive the stores' reads
+    }
+}
+
 // ---- spatial_transformer._meshgrid (spatial_transformer.py:460-482) --------------------------
 __global__ void st_meshgrid_kernel(float* __restrict__ grid, int oh, int ow, float step_x, float step_y) {
     const int n = oh * ow;
@@ -373,10 +512,58 @@ static bool wide_path_ok(int flags, const void* src, const void* out, int C, int
            (reinterpret_cast<uintptr_t>(out) & 7u) == 0 && (oh + WIDE_ROWS - 1) / WIDE_ROWS <= 65535;
 }
 
+// largest box width in pixels (<= 256 elements) whose byte width is a multiple of 16; 0 when two boxes cannot hold a tile
+static int ws_box_px(int C) {
+    for (int pxb = 256 / C; pxb >= (WS_PX + 6 + 1) / 2; --pxb)
+        if ((pxb * C) % 4 == 0) return pxb;
+    return 0;
+}
+
 template <int MODE>
 static int launch_fwd_wide(FwdParams p, cudaStream_t st) {
     if (p.B == 0 || p.oh == 0 || p.ow == 0) return DVSG_OK;
     DVSG_REQUIRE(p.B <= 65535, "batch %d exceeds the grid z limit 65535: split the call", p.B);
+    // TMA-staged variant: rows of W*C and ow*C floats at 16-byte multiples, 16-byte aligned bases, boxes wide enough for a tile
+    static const bool no_staged = getenv("DVSG_WIDE_DIRECT") != nullptr;      // A/B experiments
+    const int pxb = ws_box_px(p.C);
+    if (!no_staged && pxb > 0 && WS_OBOX_PX * p.C <= 256 && ((long long)p.W * p.C) % 4 == 0 && ((long long)p.ow * p.C) % 4 == 0 && aligned16(p.src) &&
+        aligned16(p.out) && (p.oh + WS_ROWS - 1) / WS_ROWS <= 65535 && (long long)(p.W + 2 * pxb + 2) * p.C < (1LL << 31) &&
+        (long long)(p.ow + WS_PX) * p.C < (1LL << 31)) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn enc = []() -> EncodeFn {
+            void* f = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+            return reinterpret_cast<EncodeFn>(f);
+        }();
+        if (enc) {
+            WideMaps maps;
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const cuuint64_t sdims[3] = {(cuuint64_t)p.W * p.C, (cuuint64_t)p.H, (cuuint64_t)p.B};
+            const cuuint64_t sstr[2] = {(cuuint64_t)p.W * p.C * 4, (cuuint64_t)p.H * p.W * p.C * 4};
+            const cuuint32_t sbox[3] = {(cuuint32_t)(pxb * p.C), (cuuint32_t)WS_BOX_ROWS, 1};
+            const cuuint64_t odims[3] = {(cuuint64_t)p.ow * p.C, (cuuint64_t)p.oh, (cuuint64_t)p.B};
+            const cuuint64_t ostr[2] = {(cuuint64_t)p.ow * p.C * 4, (cuuint64_t)p.oh * p.ow * p.C * 4};
+            const cuuint32_t obox[3] = {(cuuint32_t)(WS_OBOX_PX * p.C), (cuuint32_t)WS_ROWS, 1};
+            if (enc(&maps.src, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.src), sdims, sstr, sbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, odims, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                const int pal_shift = (p.C % 4 == 0) ? 0 : 1;      // 2^pal_shift pixels of C floats are a multiple of 16 bytes
+                const size_t box_bytes = (size_t)WS_BOX_ROWS * pxb * p.C * sizeof(float);
+                const size_t stage_bytes = (((box_bytes + 127) & ~(size_t)127) + box_bytes + 127) & ~(size_t)127;
+                const size_t smem = stage_bytes + (size_t)WS_NT * p.C * sizeof(float);
+                const dim3 grid((unsigned)((p.ow + WS_PX - 1) / WS_PX), (unsigned)((p.oh + WS_ROWS - 1) / WS_ROWS), (unsigned)p.B);
+                auto k = warp_fwd_wide_staged_kernel<MODE>;
+                static int smem_set = 0;
+                if ((int)smem > smem_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = (int)smem; }
+                k<<<grid, WS_NT, smem, st>>>(p, maps, pxb, pal_shift, (int)stage_bytes, 1.0f);
+                count_launch();
+                return check_launch("warp_fwd_wide_staged_kernel");
+            }
+        }
+    }
     const dim3 grid((unsigned)((p.ow + WIDE_PX - 1) / WIDE_PX), (unsigned)((p.oh + WIDE_ROWS - 1) / WIDE_ROWS), (unsigned)p.B);
     warp_fwd_wide_kernel<MODE><<<grid, WIDE_NT, 0, st>>>(p);
     count_launch();
