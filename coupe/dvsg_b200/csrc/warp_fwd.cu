@@ -354,32 +354,50 @@ __device__ __forceinline__ void ws_tma_store_3d(const void* tmap, int x, int y, 
 }
 struct alignas(64) WideMaps { CUtensorMap src, out; };
 
+// The CTA walks `seg_len` tiles of a strip as a software pipeline (the chain coordinates -> footprint -> TMA copy -> gather ->
+// TMA store of ONE tile is ~4 us of mostly latency: one tile per CTA reached 0.66 of HBM): while tile t is gathered, the
+// copy of tile t+1's footprint is in flight into the other staging buffer and the coordinates of tile t+2 are being loaded.
 template <int MODE>
 __global__ void __launch_bounds__(WS_NT) warp_fwd_wide_staged_kernel(const FwdParams p, const __grid_constant__ WideMaps maps, const int pxb,
-                                                                     const int pal_shift, const int stage_bytes, const float one) {
-    extern __shared__ __align__(128) unsigned char ws_smem[];      // [2 boxes][WS_BOX_ROWS][pxb * C] floats, then the output tile
-    __shared__ int s_bb[4][4];
-    __shared__ __align__(8) unsigned long long s_mbar;
+                                                                     const int pal_shift, const int stage_bytes, const int seg_len, const int box_rows, const float one) {
+    extern __shared__ __align__(128) unsigned char ws_smem[];      // 2 x [2 boxes][WS_BOX_ROWS][pxb * C] floats, then the output tile
+    __shared__ int s_bb[2][4][4];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
     const int H = p.H, W = p.W, C = p.C, oh = p.oh, ow = p.ow, cv = C >> 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col0 = blockIdx.x * WS_PX, row0 = blockIdx.y * WS_ROWS, b = blockIdx.z;
-    const uint32_t mbar = smem_u32(&s_mbar);
-    if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-    // ---- 1: coordinate, corners, weights of this thread's pixel (pixels past the frame edge repeat the edge pixel) -------
+    const int row0 = blockIdx.y * WS_ROWS, b = blockIdx.z;
+    const int n_tx = (ow + WS_PX - 1) / WS_PX, t_begin = blockIdx.x * seg_len, t_end = min(t_begin + seg_len, n_tx);
+    if (tid == 0) { mbar_init(smem_u32(&s_mbar[0]), 1); mbar_init(smem_u32(&s_mbar[1]), 1); fence_mbar_init(); }
     const int pr = tid / WS_PX, pc = tid % WS_PX;
-    const int col = min(col0 + pc, ow - 1), row = min(row0 + pr, oh - 1);
-    const bool live = col0 + pc < ow && row0 + pr < oh;
-    Corners c;
-    {
-        const size_t pix = ((size_t)b * oh + row) * ow + col;
+    const int row = min(row0 + pr, oh - 1);
+    const bool row_live = row0 + pr < oh;
+    const int box_f2 = box_rows * pxb * cv;         // float2 elements per box
+    const int box1_f2 = (box_f2 + 15) & ~15;        // the second box starts at the next multiple of 128 bytes (TMA destination alignment)
+    const float2 one2 = make_float2(one, one);      // 1.0f from the kernel arguments: a + b as fma(a, 1, b), rounded once, not contracted
+    // this thread's pixel in the output tile: two boxes of 8 pixels x 8 rows, each dense [row][8 * C floats]
+    float2* const otile = reinterpret_cast<float2*>(ws_smem + 2 * stage_bytes);
+    float2* const o = otile + (pc / WS_OBOX_PX) * (WS_ROWS * WS_OBOX_PX * cv) + (pr * WS_OBOX_PX + pc % WS_OBOX_PX) * cv;
+    const float2* __restrict__ srcb = reinterpret_cast<const float2*>(p.src + (size_t)b * H * W * C);
+
+    // raw per-pixel inputs of a tile (GIVEN: x, y; FLOW: dx, dy): issued two tiles ahead of their use
+    auto load_raw = [&](const int t, float& rx, float& ry) {
+        if (MODE == MODE_GIVEN || MODE == MODE_FLOW) {
+            const int col = min(t * WS_PX + pc, ow - 1);
+            const size_t pix = ((size_t)b * oh + row) * ow + col;
+            if (MODE == MODE_GIVEN) { rx = __ldg(p.x_in + pix); ry = __ldg(p.y_in + pix); }
+            else { const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + pix); rx = f.x; ry = f.y; }
+        }
+    };
+    // 1: coordinate, padded corners and weights of this thread's pixel of tile t (pixels past the frame edge repeat the edge pixel)
+    auto corners_of_tile = [&](const int t, const float rx, const float ry) -> Corners {
+        const int col = min(t * WS_PX + pc, ow - 1);
         float xq, yq;      // pixel-space coordinate before the clip
         if (MODE == MODE_GIVEN) {
-            xq = zp_pix_from_norm(__ldg(p.x_in + pix), W);
-            yq = zp_pix_from_norm(__ldg(p.y_in + pix), H);
+            xq = zp_pix_from_norm(rx, W);
+            yq = zp_pix_from_norm(ry, H);
         } else if (MODE == MODE_FLOW) {
-            const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow) + pix);
-            xq = DVSG_ADD((float)col, f.x);   // warp_with_optical_flow.py:107-120
-            yq = DVSG_ADD((float)row, f.y);
+            xq = DVSG_ADD((float)col, rx);   // warp_with_optical_flow.py:107-120
+            yq = DVSG_ADD((float)row, ry);
         } else {
             const int nt = p.projective ? 8 : 6;
             const float* th = p.theta + (size_t)b * nt;
@@ -391,76 +409,109 @@ __global__ void __launch_bounds__(WS_NT) warp_fwd_wide_staged_kernel(const FwdPa
                 xn = zn != 0.0f ? DVSG_DIV(xn, zn) : 0.0f;   // tf.div_no_nan, :446-447
                 yn = zn != 0.0f ? DVSG_DIV(yn, zn) : 0.0f;
             }
-            if (p.x_out && live) { p.x_out[pix] = xn; p.y_out[pix] = yn; }
+            if (p.x_out && row_live && t * WS_PX + pc < ow) {
+                const size_t pix = ((size_t)b * oh + row) * ow + col;
+                p.x_out[pix] = xn; p.y_out[pix] = yn;
+            }
             xq = zp_pix_from_norm(xn, W);
             yq = zp_pix_from_norm(yn, H);
         }
-        c = zp_corners(xq, yq, W, H);      // padded corners in [0, W+1] x [0, H+1]; frame index = padded index - 1
-    }
-    // ---- 2: bounding box of the tile's corners (frame coordinates; the padding ring is part of it) ----------------
-    {
+        return zp_corners(xq, yq, W, H);      // padded corners in [0, W+1] x [0, H+1]; frame index = padded index - 1
+    };
+    // 2a: per-warp bounding box of the tile's corners (frame coordinates; the padding ring is part of it) -> s_bb[sel]
+    auto bbox_post = [&](const Corners& c, const int sel) {
         const int xl = __reduce_min_sync(0xffffffffu, c.x0 - 1), xh = __reduce_max_sync(0xffffffffu, c.x1 - 1);
         const int yl = __reduce_min_sync(0xffffffffu, c.y0 - 1), yh = __reduce_max_sync(0xffffffffu, c.y1 - 1);
-        if (lane == 0) { s_bb[warp][0] = xl; s_bb[warp][1] = xh; s_bb[warp][2] = yl; s_bb[warp][3] = yh; }
+        if (lane == 0) { s_bb[sel][warp][0] = xl; s_bb[sel][warp][1] = xh; s_bb[sel][warp][2] = yl; s_bb[sel][warp][3] = yh; }
+    };
+    // 2b + 3 (after a CTA barrier): footprint origin, does it fit, thread 0 issues the two TMA copies into staging buffer `sel`
+    auto footprint_issue = [&](const int sel, int& fx0, int& y_lo) -> bool {
+        const int x_lo = min(min(s_bb[sel][0][0], s_bb[sel][1][0]), min(s_bb[sel][2][0], s_bb[sel][3][0]));
+        const int x_hi = max(max(s_bb[sel][0][1], s_bb[sel][1][1]), max(s_bb[sel][2][1], s_bb[sel][3][1]));
+        y_lo = min(min(s_bb[sel][0][2], s_bb[sel][1][2]), min(s_bb[sel][2][2], s_bb[sel][3][2]));
+        const int y_hi = max(max(s_bb[sel][0][3], s_bb[sel][1][3]), max(s_bb[sel][2][3], s_bb[sel][3][3]));
+        // origin aligned down to 2^pal_shift pixels (that many pixels of C floats are a multiple of 16 bytes: TMA box origins must be 16-byte aligned)
+        fx0 = (x_lo >> pal_shift) << pal_shift;      // arithmetic shift: rounds toward -infinity
+        const bool staged = x_hi - fx0 + 1 <= 2 * pxb && y_hi - y_lo + 1 <= box_rows;
+        if (staged && tid == 0) {
+            const uint32_t mb = smem_u32(&s_mbar[sel]), dst = smem_u32(ws_smem) + (unsigned)(sel * stage_bytes);
+            mbar_arrive_expect_tx(mb, (unsigned)(2 * box_f2 * 8));
+            ws_tma_load_3d(dst, &maps.src, fx0 * C, y_lo, b, mb);
+            ws_tma_load_3d(dst + (unsigned)(box1_f2 * 8), &maps.src, (fx0 + pxb) * C, y_lo, b, mb);
+        }
+        return staged;
+    };
+
+    if (t_begin >= t_end) return;
+    float rx1 = 0.0f, ry1 = 0.0f, rx2 = 0.0f, ry2 = 0.0f;      // raw inputs of tiles t+1, t+2
+    Corners cur, nxt = {};
+    bool cur_staged, nxt_staged = false;
+    int cur_fx0, cur_ylo, nxt_fx0 = 0, nxt_ylo = 0;
+    unsigned ph0 = 0u, ph1 = 0u;      // mbarrier parities of the two staging buffers
+    {   // prologue: tile t_begin's footprint on its way, tile t_begin + 1's raw inputs loading
+        float rx0 = 0.0f, ry0 = 0.0f;
+        load_raw(t_begin, rx0, ry0);
+        if (t_begin + 1 < t_end) load_raw(t_begin + 1, rx1, ry1);
+        cur = corners_of_tile(t_begin, rx0, ry0);
+        bbox_post(cur, t_begin & 1);
+        __syncthreads();
+        cur_staged = footprint_issue(t_begin & 1, cur_fx0, cur_ylo);
     }
-    __syncthreads();
-    const int x_lo = min(min(s_bb[0][0], s_bb[1][0]), min(s_bb[2][0], s_bb[3][0])), x_hi = max(max(s_bb[0][1], s_bb[1][1]), max(s_bb[2][1], s_bb[3][1]));
-    const int y_lo = min(min(s_bb[0][2], s_bb[1][2]), min(s_bb[2][2], s_bb[3][2])), y_hi = max(max(s_bb[0][3], s_bb[1][3]), max(s_bb[2][3], s_bb[3][3]));
-    // origin aligned down to 2^pal_shift pixels (that many pixels of C floats are a multiple of 16 bytes: TMA box origins must be 16-byte aligned)
-    const int fx0 = (x_lo >> pal_shift) << pal_shift;      // arithmetic shift: rounds toward -infinity
-    const bool staged = x_hi - fx0 + 1 <= 2 * pxb && y_hi - y_lo + 1 <= WS_BOX_ROWS;
-    const int box_f2 = WS_BOX_ROWS * pxb * cv;      // float2 elements per box
-    const int box1_f2 = (box_f2 + 15) & ~15;        // the second box starts at the next multiple of 128 bytes (TMA destination alignment)
-    // ---- 3: TMA copies of the footprint; corner offsets ---------------------------------------------------------------
-    if (staged && tid == 0) {
-        mbar_arrive_expect_tx(mbar, (unsigned)(2 * box_f2 * 8));
-        ws_tma_load_3d(smem_u32(ws_smem), &maps.src, fx0 * C, y_lo, b, mbar);
-        ws_tma_load_3d(smem_u32(ws_smem) + (unsigned)(box1_f2 * 8), &maps.src, (fx0 + pxb) * C, y_lo, b, mbar);
-    }
-    const float2 w00 = make_float2(DVSG_MUL(c.ax1, c.ay1), DVSG_MUL(c.ax1, c.ay1)), w01 = make_float2(DVSG_MUL(c.ax0, c.ay1), DVSG_MUL(c.ax0, c.ay1));
-    const float2 w10 = make_float2(DVSG_MUL(c.ax1, c.ay0), DVSG_MUL(c.ax1, c.ay0)), w11 = make_float2(DVSG_MUL(c.ax0, c.ay0), DVSG_MUL(c.ax0, c.ay0));
-    const float2 one2 = make_float2(one, one);      // 1.0f from the kernel arguments: a + b as fma(a, 1, b), rounded once, not contracted
-    // this thread's pixel in the output tile: two boxes of 8 pixels x 8 rows, each dense [row][8 * C floats]
-    float2* const otile = reinterpret_cast<float2*>(ws_smem + stage_bytes);
-    float2* const o = otile + (pc / WS_OBOX_PX) * (WS_ROWS * WS_OBOX_PX * cv) + (pr * WS_OBOX_PX + pc % WS_OBOX_PX) * cv;
-    // ---- 4: per channel pair: gather, blend, stage -------------------------------------------------------------------
-    if (staged) {
-        // offsets in float2 units inside the staging buffer; corners in the padding ring read the TMA's zero fill
-        const int xa = c.x0 - 1 - fx0, xb = c.x1 - 1 - fx0, ya = c.y0 - 1 - y_lo, yb = c.y1 - 1 - y_lo;
-        const int oa = xa >= pxb ? box1_f2 + (xa - pxb) * cv : xa * cv, ob = xb >= pxb ? box1_f2 + (xb - pxb) * cv : xb * cv;
-        const float2* __restrict__ stage = reinterpret_cast<const float2*>(ws_smem);
-        const float2 *__restrict__ p00 = stage + ya * pxb * cv + oa, *__restrict__ p01 = stage + ya * pxb * cv + ob;
-        const float2 *__restrict__ p10 = stage + yb * pxb * cv + oa, *__restrict__ p11 = stage + yb * pxb * cv + ob;
-        mbar_wait(mbar, 0);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int sel = t & 1;
+        const bool has_next = t + 1 < t_end;
+        if (t + 2 < t_end) load_raw(t + 2, rx2, ry2);
+        if (has_next) {
+            nxt = corners_of_tile(t + 1, rx1, ry1);
+            bbox_post(nxt, sel ^ 1);
+        }
+        if (tid == 0 && t > t_begin) bulk_wait_read0();      // the previous tile's stores have read the output tile
+        __syncthreads();                                     // s_bb of tile t+1 visible; output tile and the other staging buffer free
+        if (has_next) nxt_staged = footprint_issue(sel ^ 1, nxt_fx0, nxt_ylo);
+        // ---- 4: per channel pair: gather, blend, stage --------------------------------------------------------------
+        const float2 w00 = make_float2(DVSG_MUL(cur.ax1, cur.ay1), DVSG_MUL(cur.ax1, cur.ay1)), w01 = make_float2(DVSG_MUL(cur.ax0, cur.ay1), DVSG_MUL(cur.ax0, cur.ay1));
+        const float2 w10 = make_float2(DVSG_MUL(cur.ax1, cur.ay0), DVSG_MUL(cur.ax1, cur.ay0)), w11 = make_float2(DVSG_MUL(cur.ax0, cur.ay0), DVSG_MUL(cur.ax0, cur.ay0));
+        if (cur_staged) {
+            // offsets in float2 units inside the staging buffer; corners in the padding ring read the TMA's zero fill
+            const int xa = cur.x0 - 1 - cur_fx0, xb = cur.x1 - 1 - cur_fx0, ya = cur.y0 - 1 - cur_ylo, yb = cur.y1 - 1 - cur_ylo;
+            const int oa = xa >= pxb ? box1_f2 + (xa - pxb) * cv : xa * cv, ob = xb >= pxb ? box1_f2 + (xb - pxb) * cv : xb * cv;
+            const float2* __restrict__ stage = reinterpret_cast<const float2*>(ws_smem + sel * stage_bytes);
+            const float2 *__restrict__ p00 = stage + ya * pxb * cv + oa, *__restrict__ p01 = stage + ya * pxb * cv + ob;
+            const float2 *__restrict__ p10 = stage + yb * pxb * cv + oa, *__restrict__ p11 = stage + yb * pxb * cv + ob;
+            mbar_wait(smem_u32(&s_mbar[sel]), sel ? ph1 : ph0);
+            if (sel) ph1 ^= 1u; else ph0 ^= 1u;
 #pragma unroll 3
-        for (int k = 0; k < cv; ++k) {
-            // add_n([w00*I00, w01*I01, w10*I10, w11*I11]) left to right (spatial_transformer.py:557-562), both channels of the pair at once
-            const float2 t00 = __fmul2_rn(w00, p00[k]), t01 = __fmul2_rn(w01, p01[k]), t10 = __fmul2_rn(w10, p10[k]), t11 = __fmul2_rn(w11, p11[k]);
-            o[k] = __ffma2_rn(__ffma2_rn(__ffma2_rn(t00, one2, t01), one2, t10), one2, t11);
+            for (int k = 0; k < cv; ++k) {
+                // add_n([w00*I00, w01*I01, w10*I10, w11*I11]) left to right (spatial_transformer.py:557-562), both channels of the pair at once
+                const float2 t00 = __fmul2_rn(w00, p00[k]), t01 = __fmul2_rn(w01, p01[k]), t10 = __fmul2_rn(w10, p10[k]), t11 = __fmul2_rn(w11, p11[k]);
+                o[k] = __ffma2_rn(__ffma2_rn(__ffma2_rn(t00, one2, t01), one2, t10), one2, t11);
+            }
+        } else {
+            const bool vx0 = zp_valid(cur.x0, W), vx1 = zp_valid(cur.x1, W), vy0 = zp_valid(cur.y0, H), vy1 = zp_valid(cur.y1, H);
+            const float2 z = make_float2(0.0f, 0.0f);
+            const bool v00 = vx0 && vy0, v01 = vx1 && vy0, v10 = vx0 && vy1, v11 = vx1 && vy1;
+            const float2 *p00 = srcb + (v00 ? ((cur.y0 - 1) * W + (cur.x0 - 1)) * cv : 0), *p01 = srcb + (v01 ? ((cur.y0 - 1) * W + (cur.x1 - 1)) * cv : 0);
+            const float2 *p10 = srcb + (v10 ? ((cur.y1 - 1) * W + (cur.x0 - 1)) * cv : 0), *p11 = srcb + (v11 ? ((cur.y1 - 1) * W + (cur.x1 - 1)) * cv : 0);
+            for (int k = 0; k < cv; ++k) {
+                const float2 t00 = __fmul2_rn(w00, v00 ? __ldg(p00 + k) : z), t01 = __fmul2_rn(w01, v01 ? __ldg(p01 + k) : z);
+                const float2 t10 = __fmul2_rn(w10, v10 ? __ldg(p10 + k) : z), t11 = __fmul2_rn(w11, v11 ? __ldg(p11 + k) : z);
+                o[k] = __ffma2_rn(__ffma2_rn(__ffma2_rn(t00, one2, t01), one2, t10), one2, t11);
+            }
         }
-    } else {
-        const bool vx0 = zp_valid(c.x0, W), vx1 = zp_valid(c.x1, W), vy0 = zp_valid(c.y0, H), vy1 = zp_valid(c.y1, H);
-        const float2* __restrict__ srcb = reinterpret_cast<const float2*>(p.src + (size_t)b * H * W * C);
-        const float2 z = make_float2(0.0f, 0.0f);
-        const bool v00 = vx0 && vy0, v01 = vx1 && vy0, v10 = vx0 && vy1, v11 = vx1 && vy1;
-        const float2 *p00 = srcb + (v00 ? ((c.y0 - 1) * W + (c.x0 - 1)) * cv : 0), *p01 = srcb + (v01 ? ((c.y0 - 1) * W + (c.x1 - 1)) * cv : 0);
-        const float2 *p10 = srcb + (v10 ? ((c.y1 - 1) * W + (c.x0 - 1)) * cv : 0), *p11 = srcb + (v11 ? ((c.y1 - 1) * W + (c.x1 - 1)) * cv : 0);
-        for (int k = 0; k < cv; ++k) {
-            const float2 t00 = __fmul2_rn(w00, v00 ? __ldg(p00 + k) : z), t01 = __fmul2_rn(w01, v01 ? __ldg(p01 + k) : z);
-            const float2 t10 = __fmul2_rn(w10, v10 ? __ldg(p10 + k) : z), t11 = __fmul2_rn(w11, v11 ? __ldg(p11 + k) : z);
-            o[k] = __ffma2_rn(__ffma2_rn(__ffma2_rn(t00, one2, t01), one2, t10), one2, t11);
+        // ---- 5: output tile -> global with two TMA tensor stores (clipped at the frame edge) ------------------------------
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t os = smem_u32(otile);
+            const int col0 = t * WS_PX;
+            ws_tma_store_3d(&maps.out, col0 * C, row0, b, os);
+            if (col0 + WS_OBOX_PX < ow) ws_tma_store_3d(&maps.out, (col0 + WS_OBOX_PX) * C, row0, b, os + (unsigned)(WS_ROWS * WS_OBOX_PX * C * 4));
+            bulk_commit();
         }
+        cur = nxt; cur_staged = nxt_staged; cur_fx0 = nxt_fx0; cur_ylo = nxt_ylo;
+        rx1 = rx2; ry1 = ry2;
     }
-    // ---- 5: output tile -> global with two TMA tensor stores (clipped at the frame edge) --------------------------------
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t os = smem_u32(otile);
-        ws_tma_store_3d(&maps.out, col0 * C, row0, b, os);
-        if (col0 + WS_OBOX_PX < ow) ws_tma_store_3d(&maps.out, (col0 + WS_OBOX_PX) * C, row0, b, os + (unsigned)(WS_ROWS * WS_OBOX_PX * C * 4));
-        bulk_commit();
-        bulk_wait_read0();      // shared memory must outlive the stores' reads
-    }
+    if (tid == 0) bulk_wait_read0();      // shared memory must outlive the stores' reads
 }
 
 // ---- spatial_transformer._meshgrid (spatial_transformer.py:460-482) --------------------------
@@ -512,12 +563,12 @@ static bool wide_path_ok(int flags, const void* src, const void* out, int C, int
            (reinterpret_cast<uintptr_t>(out) & 7u) == 0 && (oh + WIDE_ROWS - 1) / WIDE_ROWS <= 65535;
 }
 
-// largest box width in pixels (<= 256 elements) whose byte width is a multiple of 16; 0 when two boxes cannot hold a tile
-static int ws_box_px(int C) {
-    for (int pxb = 256 / C; pxb >= (WS_PX + 6 + 1) / 2; --pxb)
-        if ((pxb * C) % 4 == 0) return pxb;
-    return 0;
-}
+// Staging box: 10 pixels x 12 rows, two side by side = 20 x 12 source pixels for a 16 x 8 output tile.  The box size is the
+// first-order knob of this kernel: every staged byte crosses L2 -> shared memory through the TMA unit, and with the widest
+// box that 256 elements allow (14 px at C = 18, 28 x 12 pixels staged per tile = 2.6x the output) the kernel sat at 0.62-0.68
+// of HBM whatever else was done to it; 10 x 12: 0.74 at 288 x 512, 0.81 at 1080p (10 x 10 is no faster and sends sheared
+// grids to the global-memory path).  0 when ten pixels exceed a box (C > 25).
+static int ws_box_px(int C) { return (10 * C <= 256 && (10 * C) % 4 == 0) ? 10 : 0; }
 
 template <int MODE>
 static int launch_fwd_wide(FwdParams p, cudaStream_t st) {
@@ -525,7 +576,11 @@ static int launch_fwd_wide(FwdParams p, cudaStream_t st) {
     DVSG_REQUIRE(p.B <= 65535, "batch %d exceeds the grid z limit 65535: split the call", p.B);
     // TMA-staged variant: rows of W*C and ow*C floats at 16-byte multiples, 16-byte aligned bases, boxes wide enough for a tile
     static const bool no_staged = getenv("DVSG_WIDE_DIRECT") != nullptr;      // A/B experiments
-    const int pxb = ws_box_px(p.C);
+    int pxb = ws_box_px(p.C), box_rows = WS_BOX_ROWS;
+    if (const char* e = getenv("DVSG_WIDE_BOX")) {      // experiments only: "pixels per box,rows"
+        int a = 0, r = 0;
+        if (sscanf(e, "%d,%d", &a, &r) == 2 && a >= 9 && a * p.C <= 256 && (a * p.C) % 4 == 0 && r >= 9 && r <= 16) { pxb = a; box_rows = r; }
+    }
     if (!no_staged && pxb > 0 && WS_OBOX_PX * p.C <= 256 && ((long long)p.W * p.C) % 4 == 0 && ((long long)p.ow * p.C) % 4 == 0 && aligned16(p.src) &&
         aligned16(p.out) && (p.oh + WS_ROWS - 1) / WS_ROWS <= 65535 && (long long)(p.W + 2 * pxb + 2) * p.C < (1LL << 31) &&
         (long long)(p.ow + WS_PX) * p.C < (1LL << 31)) {
@@ -542,7 +597,7 @@ static int launch_fwd_wide(FwdParams p, cudaStream_t st) {
             const cuuint32_t estr[3] = {1, 1, 1};
             const cuuint64_t sdims[3] = {(cuuint64_t)p.W * p.C, (cuuint64_t)p.H, (cuuint64_t)p.B};
             const cuuint64_t sstr[2] = {(cuuint64_t)p.W * p.C * 4, (cuuint64_t)p.H * p.W * p.C * 4};
-            const cuuint32_t sbox[3] = {(cuuint32_t)(pxb * p.C), (cuuint32_t)WS_BOX_ROWS, 1};
+            const cuuint32_t sbox[3] = {(cuuint32_t)(pxb * p.C), (cuuint32_t)box_rows, 1};
             const cuuint64_t odims[3] = {(cuuint64_t)p.ow * p.C, (cuuint64_t)p.oh, (cuuint64_t)p.B};
             const cuuint64_t ostr[2] = {(cuuint64_t)p.ow * p.C * 4, (cuuint64_t)p.oh * p.ow * p.C * 4};
             const cuuint32_t obox[3] = {(cuuint32_t)(WS_OBOX_PX * p.C), (cuuint32_t)WS_ROWS, 1};
@@ -551,14 +606,21 @@ static int launch_fwd_wide(FwdParams p, cudaStream_t st) {
                 enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, odims, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
                 const int pal_shift = (p.C % 4 == 0) ? 0 : 1;      // 2^pal_shift pixels of C floats are a multiple of 16 bytes
-                const size_t box_bytes = (size_t)WS_BOX_ROWS * pxb * p.C * sizeof(float);
+                const size_t box_bytes = (size_t)box_rows * pxb * p.C * sizeof(float);
                 const size_t stage_bytes = (((box_bytes + 127) & ~(size_t)127) + box_bytes + 127) & ~(size_t)127;
-                const size_t smem = stage_bytes + (size_t)WS_NT * p.C * sizeof(float);
-                const dim3 grid((unsigned)((p.ow + WS_PX - 1) / WS_PX), (unsigned)((p.oh + WS_ROWS - 1) / WS_ROWS), (unsigned)p.B);
+                const size_t smem = 2 * stage_bytes + (size_t)WS_NT * p.C * sizeof(float);
+                // tiles per CTA: long enough to amortise the pipeline's fill (8), short enough for >= 4 waves of CTAs
+                const int n_tx = (p.ow + WS_PX - 1) / WS_PX;
+                const long long strips = (long long)p.B * ((p.oh + WS_ROWS - 1) / WS_ROWS);
+                int seg_len = 8;
+                if (const char* e = getenv("DVSG_WIDE_SEGLEN")) seg_len = max(atoi(e), 1);      // experiments only
+                while (seg_len > 2 && strips * ((n_tx + seg_len - 1) / seg_len) < 4LL * 148 * 3) seg_len /= 2;
+                seg_len = min(seg_len, n_tx);
+                const dim3 grid((unsigned)((n_tx + seg_len - 1) / seg_len), (unsigned)((p.oh + WS_ROWS - 1) / WS_ROWS), (unsigned)p.B);
                 auto k = warp_fwd_wide_staged_kernel<MODE>;
                 static int smem_set = 0;
                 if ((int)smem > smem_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = (int)smem; }
-                k<<<grid, WS_NT, smem, st>>>(p, maps, pxb, pal_shift, (int)stage_bytes, 1.0f);
+                k<<<grid, WS_NT, smem, st>>>(p, maps, pxb, pal_shift, (int)stage_bytes, seg_len, box_rows, 1.0f);
                 count_launch();
                 return check_launch("warp_fwd_wide_staged_kernel");
             }
