@@ -24,6 +24,24 @@ int check_launch(const char* what);   // cudaGetLastError -> DVSG_ERR_CUDA
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Raise a kernel's dynamic shared-memory limit only when it has to grow (cudaFuncSetAttribute costs ~1 us per call, which the
+// online loop pays per frame otherwise).  Keyed by the kernel's ADDRESS: template instantiations share one function-pointer
+// type, so a `static` inside a generic lambda would be shared by all of them.
+inline void ensure_dynamic_smem(const void* kernel, int bytes) {
+    struct Entry { const void* k; int dev, bytes; };      // the attribute belongs to (kernel, device)
+    static thread_local Entry seen[96];
+    static thread_local int n_seen = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i].k == kernel && seen[i].dev == dev) {
+            if (bytes > seen[i].bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); seen[i].bytes = bytes; }
+            return;
+        }
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (n_seen < 96) { seen[n_seen].k = kernel; seen[n_seen].dev = dev; seen[n_seen].bytes = bytes; ++n_seen; }
+}
+
 #if defined(__CUDACC__)
 // ---- device-side PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

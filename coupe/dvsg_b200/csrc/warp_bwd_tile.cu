@@ -812,8 +812,7 @@ static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
     const size_t smem = (size_t)TNW * 2 * BSTAGE + (nodes ? 0 : (size_t)pn8 * sizeof(TpsRec)) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float) +
                         (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) + TC * 8 * sizeof(float) : 0);
     auto go = [&](auto k) {
-        static int smem_set = 0;
-        if ((int)smem > smem_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = (int)smem; }
+        ensure_dynamic_smem(reinterpret_cast<const void*>(k), (int)smem);
         k<<<dim3((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B), TNT, smem, st>>>(p, maps);
     };
     if constexpr (MODE == TMODE_TPS) {

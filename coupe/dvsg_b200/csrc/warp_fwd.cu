@@ -618,8 +618,7 @@ static int launch_fwd_wide(FwdParams p, cudaStream_t st) {
                 seg_len = min(seg_len, n_tx);
                 const dim3 grid((unsigned)((n_tx + seg_len - 1) / seg_len), (unsigned)((p.oh + WS_ROWS - 1) / WS_ROWS), (unsigned)p.B);
                 auto k = warp_fwd_wide_staged_kernel<MODE>;
-                static int smem_set = 0;
-                if ((int)smem > smem_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = (int)smem; }
+                ensure_dynamic_smem(reinterpret_cast<const void*>(k), (int)smem);
                 k<<<grid, WS_NT, smem, st>>>(p, maps, pxb, pal_shift, (int)stage_bytes, seg_len, box_rows, 1.0f);
                 count_launch();
                 return check_launch("warp_fwd_wide_staged_kernel");

@@ -504,8 +504,7 @@ static int launch_tile(TileParams p, cudaStream_t st) {
                         (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) : (MODE == TMODE_TPS ? (size_t)((p.pn + 7) & ~7) * sizeof(TpsRec) : 0));
     const dim3 grid((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B);
     auto go = [&](auto k) {
-        static int smem_set = 0;      // per kernel instantiation: raise the dynamic shared-memory limit only when it grows
-        if ((int)smem > smem_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = (int)smem; }
+        ensure_dynamic_smem(reinterpret_cast<const void*>(k), (int)smem);
         k<<<grid, TNT, smem, st>>>(p, maps);
     };
     if constexpr (MODE == TMODE_TPS) {
