@@ -1,6 +1,5 @@
 // sampler_math.cuh -- the per-pixel arithmetic of the two bilinear samplers on the DVSG
-// warp path, written once for device code (and compilable as plain C++ by the host-side
-// logic check under tests/hostcheck/, which is test infrastructure, not a fallback).
+// warp path, written once for all device kernels (it also compiles as plain host C++).
 //
 // Everything that feeds an integer sample index is spelled with explicitly rounded
 // single operations (no FMA contraction) in exactly the reference's op order, so that the
