@@ -314,12 +314,13 @@ __device__ __forceinline__ void tile_node_tables(const float* __restrict__ Tb, c
                                                  float step_x, float step_y, int tid, int nthreads, float* s_lin, const NodeTables& nt) {
     const int N = pn + 3, pn4 = (pn + 3) & ~3, lane = tid & 31, warp = tid >> 5;
     if (G > 0) {
+        constexpr int GS = G > 0 ? G : 1;
         bool ok = true;
-        for (int k = tid; k < G * G; k += nthreads)
-            ok = ok && __ldg(cb + 2 * k) == __ldg(cb + 2 * (k % G)) && __ldg(cb + 2 * k + 1) == __ldg(cb + 2 * (k / G * G) + 1);
+        for (int k = tid; k < GS * GS; k += nthreads)
+            ok = ok && __ldg(cb + 2 * k) == __ldg(cb + 2 * (k % GS)) && __ldg(cb + 2 * k + 1) == __ldg(cb + 2 * (k / GS * GS) + 1);
         const int sep = __syncthreads_and(ok);
         if (tid == 0) nt.near_cnt[1] = sep;
-        if (tid < G) { nt.gxy[tid] = __ldg(cb + 2 * tid); nt.gxy[TKS + tid] = __ldg(cb + 2 * (tid * G) + 1); }
+        if (tid < GS) { nt.gxy[tid] = __ldg(cb + 2 * tid); nt.gxy[TKS + tid] = __ldg(cb + 2 * (tid * GS) + 1); }
     } else if (tid == 0) {
         nt.near_cnt[1] = 0;
     }
@@ -479,14 +480,14 @@ __device__ __forceinline__ void tile_node_coords(const NodeTables& nt, const int
             X[j] = __ffma2_rn(l2, ytp, f2dup(bx));
             Y[j] = __ffma2_rn(l5, ytp, f2dup(by));
         }
+        // scalar FFMA with the weight as an immediate: 80 instructions; the packed form needs every constant PAIR in a uniform
+        // register first (two UMOV each) and the G values duplicated: 40 FFMA2 + 36 UMOV + 18 MOV
 #pragma unroll
         for (int b = 0; b < NNY; ++b) {
-            const float2 gxb = f2dup(gx[b]), gyb = f2dup(gy[b]);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                const float2 m = f2(NODE_MY[b][2 * j], NODE_MY[b][2 * j + 1]);
-                X[j] = __ffma2_rn(m, gxb, X[j]);
-                Y[j] = __ffma2_rn(m, gyb, Y[j]);
+                X[j].x = fmaf(NODE_MY[b][2 * j], gx[b], X[j].x); X[j].y = fmaf(NODE_MY[b][2 * j + 1], gx[b], X[j].y);
+                Y[j].x = fmaf(NODE_MY[b][2 * j], gy[b], Y[j].x); Y[j].y = fmaf(NODE_MY[b][2 * j + 1], gy[b], Y[j].y);
             }
         }
     }

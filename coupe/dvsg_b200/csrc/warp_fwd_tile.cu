@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
     };
     // coordinates, last part: x / y outputs and the sampler's own coordinate convention
     //   TPS: A4 pixel-space coordinate; others: clipped+1 coordinate in the zero-padded frame
-    auto coords_end = [&](const Tile& T, const float xt, float2 (&X)[TR / 2], float2 (&Y)[TR / 2], float (&rx)[TR], float (&ry)[TR]) {
+    // (XO, YO may alias X, Y: the software pipeline passes the current tile's arrays, free after its gather, so that the next
+    //  tile's coordinates need no register copy at the end of the iteration)
+    auto coords_end = [&](const Tile& T, const float xt, const float2 (&X)[TR / 2], const float2 (&Y)[TR / 2], float2 (&XO)[TR / 2], float2 (&YO)[TR / 2],
+                          float (&rx)[TR], float (&ry)[TR]) {
         if (MODE == TMODE_TPS) {
             if (p.x_out && T.col_ok) {
 #pragma unroll
@@ -293,8 +296,8 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             const float2 wf = f2dup((float)W), hf = f2dup((float)H), half2 = f2dup(0.5f);
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                X[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(X[j], one2), wf), half2);
-                Y[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(Y[j], one2), hf), half2);
+                XO[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(X[j], one2), wf), half2);
+                YO[j] = __fmul2_rn(__fmul2_rn(__fadd2_rn(Y[j], one2), hf), half2);
             }
         } else {
             if (MODE == TMODE_GIVEN || MODE == TMODE_FLOW) {
@@ -326,8 +329,8 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             const float wf = (float)W, hf = (float)H;
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                X[j] = f2(DVSG_ADD(fminf(fmaxf(rx[2 * j], -1.0f), wf), 1.0f), DVSG_ADD(fminf(fmaxf(rx[2 * j + 1], -1.0f), wf), 1.0f));
-                Y[j] = f2(DVSG_ADD(fminf(fmaxf(ry[2 * j], -1.0f), hf), 1.0f), DVSG_ADD(fminf(fmaxf(ry[2 * j + 1], -1.0f), hf), 1.0f));
+                XO[j] = f2(DVSG_ADD(fminf(fmaxf(rx[2 * j], -1.0f), wf), 1.0f), DVSG_ADD(fminf(fmaxf(rx[2 * j + 1], -1.0f), wf), 1.0f));
+                YO[j] = f2(DVSG_ADD(fminf(fmaxf(ry[2 * j], -1.0f), hf), 1.0f), DVSG_ADD(fminf(fmaxf(ry[2 * j + 1], -1.0f), hf), 1.0f));
             }
         }
     };
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
         float2 XC[TR / 2], YC[TR / 2], XN[TR / 2], YN[TR / 2];
         float rx[TR], ry[TR], xt;
         coords_begin(t, cur, xt, XC, YC, rx, ry);
-        coords_end(cur, xt, XC, YC, rx, ry);
+        coords_end(cur, xt, XC, YC, XC, YC, rx, ry);
         footprint_load(XC, YC, cur);
         while (true) {
             const int tn = t + TNW;
@@ -432,11 +435,9 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             out_pending = true;
             if (!has_next) break;
 
-            coords_end(nxt, xt, XN, YN, rx, ry);
-            footprint_load(XN, YN, nxt);   // the staging buffer is free: every lane passed the __syncwarp above
+            coords_end(nxt, xt, XN, YN, XC, YC, rx, ry);      // straight into the current tile's arrays (free after its gather)
+            footprint_load(XC, YC, nxt);   // the staging buffer is free: every lane passed the __syncwarp above
             cur = nxt;
-#pragma unroll
-            for (int j = 0; j < TR / 2; ++j) { XC[j] = XN[j]; YC[j] = YN[j]; }
             t = tn;
         }
     }
