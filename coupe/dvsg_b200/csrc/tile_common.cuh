@@ -374,12 +374,11 @@ __device__ __forceinline__ void node_near_term(const float4 cp, const float xt, 
 }
 // far-field value of one control point at this lane's node (the same expression is added for every control point and
 // subtracted again for the tile's near ones, so the two cancel to the last bit of the running sum's rounding)
-__device__ __forceinline__ void node_far_term(const float4 cp, const float xn, const float yn, const float sign, float& fx, float& fy) {
+__device__ __forceinline__ void node_far_term(const float4 cp, const float xn, const float yn, const float sign, float2& f) {
     const float dx = xn - cp.x, dy = yn - cp.y;
     const float d2 = fmaf(dx, dx, fmaf(dy, dy, TPS_TINY));
     const float r = d2 * lg2_approx(d2) * sign;
-    fx = fmaf(cp.z, r, fx);
-    fy = fmaf(cp.w, r, fy);
+    f = __ffma2_rn(make_float2(cp.z, cp.w), f2dup(r), f);      // (x, y) of the node in one packed FMA, r as a broadcast operand
 }
 // Lagrange weights of this lane's column (li = local column; lanes past the frame edge take the edge pixel's)
 __device__ __forceinline__ void node_load_lx(const int li, float (&lx)[NNX]) {
@@ -421,7 +420,7 @@ __device__ __forceinline__ void tile_node_coords(const NodeTables& nt, const int
         }
     }
     // far field at this lane's node: all control points, then the near ones taken out again
-    float fx = 0.0f, fy = 0.0f;
+    float2 fn = f2dup(0.0f);
     {
         const float xn = fmaf(step_x, (float)col0 + xoff_l, -1.0f);
         const float4* __restrict__ cp = nt.cp;
@@ -440,34 +439,31 @@ __device__ __forceinline__ void tile_node_coords(const NodeTables& nt, const int
                     const float2 c = *reinterpret_cast<const float2*>(&cp[gy * GG + g].z);
                     const float d2 = dx2[g] + dy2;
                     const float r = d2 * lg2_approx(d2);
-                    fx = fmaf(c.x, r, fx);
-                    fy = fmaf(c.y, r, fy);
+                    fn = __ffma2_rn(c, f2dup(r), fn);      // (x, y) in one packed FMA, r as a broadcast operand
                 }
             }
         } else {
             for (int k = 0; k < pn4; k += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) node_far_term(cp[k + u], xn, yn, 1.0f, fx, fy);
+                for (int u = 0; u < 4; ++u) node_far_term(cp[k + u], xn, yn, 1.0f, fn);
             }
         }
-        for (unsigned m = near; m; m &= m - 1) node_far_term(cp[nt.near_idx[__ffs(m) - 1]], xn, yn, -1.0f, fx, fy);
+        for (unsigned m = near; m; m &= m - 1) node_far_term(cp[nt.near_idx[__ffs(m) - 1]], xn, yn, -1.0f, fn);
     }
-    w_nodes[lane] = make_float2(fx, fy);
+    w_nodes[lane] = fn;
     __syncwarp();
-    // interpolation, x direction: G[b] = sum_a Lx[a](column) * F[a + NNX b]
-    float gx[NNY], gy[NNY];
+    // interpolation, x direction: G[b] = sum_a Lx[a](column) * F[a + NNX b], (x, y) packed
+    float2 gxy[NNY];
     {
         const float4* __restrict__ f4 = reinterpret_cast<const float4*>(w_nodes);      // two nodes per 16-byte load
 #pragma unroll
-        for (int b = 0; b < NNY; ++b) { gx[b] = 0.0f; gy[b] = 0.0f; }
+        for (int b = 0; b < NNY; ++b) gxy[b] = f2dup(0.0f);
 #pragma unroll
         for (int q = 0; q < NNX * NNY / 2; ++q) {
             const float4 v = f4[q];
             const int n0 = 2 * q, n1 = 2 * q + 1;
-            gx[n0 / NNX] = fmaf(lx[n0 % NNX], v.x, gx[n0 / NNX]);
-            gy[n0 / NNX] = fmaf(lx[n0 % NNX], v.y, gy[n0 / NNX]);
-            gx[n1 / NNX] = fmaf(lx[n1 % NNX], v.z, gx[n1 / NNX]);
-            gy[n1 / NNX] = fmaf(lx[n1 % NNX], v.w, gy[n1 / NNX]);
+            gxy[n0 / NNX] = __ffma2_rn(f2(v.x, v.y), f2dup(lx[n0 % NNX]), gxy[n0 / NNX]);
+            gxy[n1 / NNX] = __ffma2_rn(f2(v.z, v.w), f2dup(lx[n1 % NNX]), gxy[n1 / NNX]);
         }
     }
     // affine part + y direction onto the lane's 8 rows (row weights are compile-time constants)
@@ -486,8 +482,8 @@ __device__ __forceinline__ void tile_node_coords(const NodeTables& nt, const int
         for (int b = 0; b < NNY; ++b) {
 #pragma unroll
             for (int j = 0; j < TR / 2; ++j) {
-                X[j].x = fmaf(NODE_MY[b][2 * j], gx[b], X[j].x); X[j].y = fmaf(NODE_MY[b][2 * j + 1], gx[b], X[j].y);
-                Y[j].x = fmaf(NODE_MY[b][2 * j], gy[b], Y[j].x); Y[j].y = fmaf(NODE_MY[b][2 * j + 1], gy[b], Y[j].y);
+                X[j].x = fmaf(NODE_MY[b][2 * j], gxy[b].x, X[j].x); X[j].y = fmaf(NODE_MY[b][2 * j + 1], gxy[b].x, X[j].y);
+                Y[j].x = fmaf(NODE_MY[b][2 * j], gxy[b].y, Y[j].x); Y[j].y = fmaf(NODE_MY[b][2 * j + 1], gxy[b].y, Y[j].y);
             }
         }
     }
