@@ -39,7 +39,34 @@ namespace dvsg {
 // ---- per-pixel general gather: full reference semantics --------------------------------------------
 // xp, yp: TPS -> pixel-space coordinate of the A4 sampler; other modes -> clipped+1 coordinate in the
 // zero-padded frame.  Corners come straight from global memory.
-template <int MODE>
+// Wide corner loads: the two corners of one source row are 24 contiguous bytes at a 4-byte alignment (12 x0 mod 16 is 0, 12,
+// 8 or 4).  Twelve scalar loads per pixel made this path bound by L1 tag lookups (each LDG.32 of a scattered warp is 32
+// lookups); here a row is fetched with two 16-byte aligned LDG.128 (plus one LDG.32 for the word that spills over when
+// x0 = 1 mod 4) and the six floats are rotated into place with selects: 4-5 lookups per pixel instead of 12.  The tile
+// path guarantees W % 4 == 0 and a 16-byte aligned frame, so every row starts on a 16-byte boundary and no load that is
+// issued reaches past the frame (each is predicated on containing a needed word).
+__device__ __forceinline__ void row_corners(const float* __restrict__ srcb, int y, int x0, int x1, int W, float (&c0)[3], float (&c1)[3]) {
+    const size_t e = ((size_t)y * W + x0) * 3;
+    const int k = (int)(e & 3);
+    const float* g = srcb + (e - k);
+    const bool two = x1 != x0;
+    const int last = k + (two ? 5 : 2);               // last needed word, relative to g
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(g));
+    float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float q2 = 0.f;
+    if (last >= 4) q1 = __ldg(reinterpret_cast<const float4*>(g) + 1);
+    if (last >= 8) q2 = __ldg(g + 8);
+    const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2};
+    float t[7], f[6];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) t[j] = (k & 2) ? v[j + 2] : v[j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) f[j] = (k & 1) ? t[j + 1] : t[j];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) { c0[ch] = f[ch]; c1[ch] = two ? f[3 + ch] : f[ch]; }
+}
+
+template <int MODE, bool WIDE_LD = true>
 __device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, const float* __restrict__ srcb, float* __restrict__ optr, float* mask_ptr) {
     int x0, x1, y0, y1;
     float ax0, ax1, ay0, ay1;
@@ -66,7 +93,17 @@ __device__ __noinline__ void general_pixel(float xp, float yp, int W, int H, con
     const float w00 = DVSG_MUL(ax1, ay1), w01 = DVSG_MUL(ax0, ay1), w10 = DVSG_MUL(ax1, ay0), w11 = DVSG_MUL(ax0, ay0);
     if (MODE == TMODE_TPS && mask_ptr) *mask_ptr = DVSG_ADD(DVSG_ADD(DVSG_ADD(w00, w10), w01), w11);   // A4 add_n order
     float i00[3], i01[3], i10[3], i11[3];
-    {
+    if (WIDE_LD && (unsigned)(x1 - x0) <= 1u) {          // always, short of the int32 wrap of a coordinate beyond 2^31
+        row_corners(srcb, y0, x0, x1, W, i00, i01);
+        row_corners(srcb, y1, x0, x1, W, i10, i11);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            if (!v00) i00[ch] = 0.0f;
+            if (!v01) i01[ch] = 0.0f;
+            if (!v10) i10[ch] = 0.0f;
+            if (!v11) i11[ch] = 0.0f;
+        }
+    } else {
         const float* a00 = srcb + ((size_t)y0 * W + x0) * 3;
         const float* a01 = srcb + ((size_t)y0 * W + x1) * 3;
         const float* a10 = srcb + ((size_t)y1 * W + x0) * 3;
@@ -418,10 +455,12 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
                 else
                     gather_tile<MODE, true, MASK>(XC, YC, cur.pitch, cur.sb, ot, wm1, hm1, onex, mask_col, ow, rows_ok);
             } else {
+                // wide corner loads pay for a rough flow field (white-noise +-8 px flow: 60 -> 74 Gpix/s); the neighbouring
+                // lanes of a smooth map already share sectors, where the selects only cost (+-0.3 TPS: 137 -> 128 Gpix/s)
 #pragma unroll
                 for (int q = 0; q < TR; ++q) {
                     const float xq = (q & 1) ? XC[q >> 1].y : XC[q >> 1].x, yq = (q & 1) ? YC[q >> 1].y : YC[q >> 1].x;
-                    general_pixel<MODE>(xq, yq, W, H, srcb, ot + q * TC * 3, (MASK && mask_col && q < rows_ok) ? mask_col + q * ow : nullptr);
+                    general_pixel<MODE, MODE == TMODE_FLOW>(xq, yq, W, H, srcb, ot + q * TC * 3, (MASK && mask_col && q < rows_ok) ? mask_col + q * ow : nullptr);
                 }
             }
 
@@ -532,9 +571,10 @@ static int launch_tile(TileParams p, cudaStream_t st) {
 // 288 x 512 training shape (two waves of short CTAs, latency-bound) the small meshes LOSE 10 % -- hence the pixel floor.
 bool tps_nodes_ok(int H, int W, int C, int oh, int ow, int pn, int flags) {
     static const bool env_exact = getenv("DVSG_TPS_EXACT") != nullptr;      // A/B experiments
+    static const bool env_force = getenv("DVSG_TPS_NODES_FORCE") != nullptr;      // experiments: no pixel floor
     (void)H;
     return !(flags & DVSG_FLAG_TPS_EXACT) && !env_exact && C == 3 && W % 4 == 0 && ow % 4 == 0 && pn >= 8 && pn <= TKC && ow >= 400 && oh >= 200 &&
-           (pn >= 64 || (long long)oh * ow >= 500000);
+           (env_force || pn >= 64 || (long long)oh * ow >= 500000);
 }
 
 int tile_tps(const float* U, const float* coord, long long cstride, const float* T, float* out, float* x_out, float* y_out,
