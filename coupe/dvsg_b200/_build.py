@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libdvsg_warp.so')
-SOURCES = ['api.cu', 'tps_solve.cu', 'warp_fwd.cu', 'warp_fwd_tile.cu', 'warp_bwd.cu', 'warp_bwd_tile.cu', 'frames_u8.cu', 'losses.cu', 'elastic.cu']
+SOURCES = ['api.cu', 'tps_solve.cu', 'warp_fwd.cu', 'warp_fwd_tile.cu', 'warp_bwd.cu', 'warp_bwd_tile.cu', 'frames_u8.cu', 'losses.cu', 'elastic.cu', 'homography.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--fmad=true', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--threads', '4']
 

@@ -43,6 +43,7 @@ PROTOTYPES = {
     'dvsg_flow_warp_bwd': (c_int, [_P, _P, _P, _P, _P] + [c_int] * 4 + [_P]),
     'dvsg_st_meshgrid': (c_int, [_P, c_int, c_int, _P]),
     'dvsg_homography_warp_fwd': (c_int, [_P, _P, c_int, _P, _P, _P] + [c_int] * 6 + [_P]),
+    'dvsg_homography_grid_bwd': (c_int, [_P, _P, _P, c_int, _P] + [c_int] * 3 + [_P]),
     'dvsg_host_pipeline_create': (c_int, [ctypes.POINTER(c_void_p)] + [c_int] * 7),
     'dvsg_host_pipeline_destroy': (None, [_P]),
     'dvsg_host_tps_warp': (c_int, [_P, _P, _P, _P, _P, c_int]),

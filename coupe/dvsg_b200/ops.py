@@ -365,20 +365,68 @@ def st_meshgrid(out_size, device=None):
     return grid
 
 
+class _HomographyWarp(torch.autograd.Function):
+    """(inp, theta) -> (out, x_s, y_s) of ProjectiveTransformer / AffineTransformer (spatial_transformer.py:384-452, 31-91).
+    Backward: the sampler's (dvsg_bilinear_bwd) chained through the grid stage (dvsg_homography_grid_bwd)."""
+
+    @staticmethod
+    def forward(ctx, inp, theta, out_size, projective, want_grid):
+        lib = _lib.load()
+        B, H, W, C = inp.shape
+        oh, ow = out_size
+        need_bwd = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        out = torch.empty((B, oh, ow, C), dtype=torch.float32, device=inp.device)
+        keep = want_grid or need_bwd
+        x = torch.empty(B * oh * ow, dtype=torch.float32, device=inp.device) if keep else None
+        y = torch.empty(B * oh * ow, dtype=torch.float32, device=inp.device) if keep else None
+        with torch.cuda.device(inp.device):
+            rc = lib.dvsg_homography_warp_fwd(ptr(inp), ptr(theta), 1 if projective else 0, ptr(out), ptr(x), ptr(y),
+                                              B, H, W, C, oh, ow, stream_ptr(inp.device))
+        _lib.check(rc, 'dvsg_homography_warp_fwd')
+        ctx.out_size, ctx.projective = out_size, projective
+        if need_bwd:
+            ctx.save_for_backward(inp, theta, x, y)
+        if not keep:
+            x, y = out.new_empty(0), out.new_empty(0)
+            ctx.mark_non_differentiable(x, y)
+        return out, x, y
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_x, grad_y):
+        lib = _lib.load()
+        inp, theta, x, y = ctx.saved_tensors
+        B, H, W, C = inp.shape
+        oh, ow = ctx.out_size
+        dev = inp.device
+        grad_out = grad_out.contiguous()
+        g_im = torch.zeros_like(inp) if ctx.needs_input_grad[0] else None
+        g_theta = None
+        need_theta = ctx.needs_input_grad[1]
+        gx = torch.empty_like(x) if need_theta else None
+        gy = torch.empty_like(y) if need_theta else None
+        with torch.cuda.device(dev):
+            rc = lib.dvsg_bilinear_bwd(ptr(inp), ptr(x), ptr(y), ptr(grad_out), ptr(g_im), ptr(gx), ptr(gy), B, H, W, C, oh, ow, stream_ptr(dev))
+            _lib.check(rc, 'dvsg_bilinear_bwd')
+            if need_theta:
+                if grad_x is not None and grad_x.numel():          # x_s / y_s consumed directly (_transform)
+                    gx = gx + grad_x.reshape(-1)
+                if grad_y is not None and grad_y.numel():
+                    gy = gy + grad_y.reshape(-1)
+                g_theta = torch.empty_like(theta)
+                rc = lib.dvsg_homography_grid_bwd(ptr(theta), ptr(gx), ptr(gy), 1 if ctx.projective else 0, ptr(g_theta), B, oh, ow,
+                                                  stream_ptr(dev))
+                _lib.check(rc, 'dvsg_homography_grid_bwd')
+        return g_im, g_theta, None, None, None
+
+
 def homography_warp(inp, theta, out_size, projective, want_grid=False):
-    lib = _lib.load()
     inp = as_cuda_f32(inp, 'inp')
-    B, H, W, C = inp.shape
+    if inp.dim() != 4:
+        raise ValueError('inp must have shape [batch, height, width, channels], got %s' % (tuple(inp.shape),))
+    B = inp.shape[0]
     nt = 8 if projective else 6
     theta = as_cuda_f32(theta, 'theta', like=inp).reshape(B, nt)
-    oh, ow = out_hw(out_size)
-    out = torch.empty((B, oh, ow, C), dtype=torch.float32, device=inp.device)
-    x = torch.empty(B * oh * ow, dtype=torch.float32, device=inp.device) if want_grid else None
-    y = torch.empty(B * oh * ow, dtype=torch.float32, device=inp.device) if want_grid else None
-    with torch.cuda.device(inp.device):
-        rc = lib.dvsg_homography_warp_fwd(ptr(inp), ptr(theta), 1 if projective else 0, ptr(out), ptr(x), ptr(y),
-                                          B, H, W, C, oh, ow, stream_ptr(inp.device))
-    _lib.check(rc, 'dvsg_homography_warp_fwd')
+    out, x, y = _HomographyWarp.apply(inp, theta, out_hw(out_size), bool(projective), bool(want_grid))
     return (out, x, y) if want_grid else out
 
 

@@ -68,8 +68,9 @@ class _HomographyTransformer(object):
 
     def transform(self, inp, theta):
         """inp [B,H,W,C], theta [B, param_dim] -> [B, out_h, out_w, C].  Grid generation and
-        sampling are fused in one kernel; differentiation is not provided (the only reference
-        caller feeds random constants, model.py:156-167)."""
+        sampling are fused in one kernel; differentiable w.r.t. inp and theta (the only reference
+        caller feeds random constants, model.py:156-167, so the backward is built for completeness:
+        dvsg_bilinear_bwd + dvsg_homography_grid_bwd)."""
         return ops.homography_warp(inp, theta, self.out_size, self._projective)
 
     def _transform(self, inp, theta):

@@ -175,6 +175,13 @@ int dvsg_st_meshgrid(float* grid, int oh, int ow, void* stream);
 int dvsg_homography_warp_fwd(const float* im, const float* theta, int projective, float* out,
                              float* x_out, float* y_out, int B, int H, int W, int C,
                              int oh, int ow, void* stream);
+/* Backward of the two transformers' grid stage (no reference caller differentiates them; provided
+ * for completeness): grad_x / grad_y flat [B*oh*ow] w.r.t. x_s / y_s (e.g. from dvsg_bilinear_bwd)
+ * -> grad_theta [B,8] (projective: MatMul :437 and DivNoNan :446-447 gradients, zero where
+ * z_s == 0) or [B,6].  Deterministic (fp64 partial sums, no atomics).                        */
+int dvsg_homography_grid_bwd(const float* theta, const float* grad_x, const float* grad_y,
+                             int projective, float* grad_theta, int B, int oh, int ow,
+                             void* stream);
 
 /* ---- ElasticTransformer (spatial_transformer.py:93-362) ---------------
  * The reference's second TPS formulation: regular mesh fixed at construction, U(r2) = r2 log r2

@@ -221,6 +221,41 @@ def elastic_cases():
     return cases
 
 
+def transformer_grad_cases():
+    """Backward of ProjectiveTransformer / AffineTransformer (spatial_transformer.py:5-91, 364-452) w.r.t. the input and
+    theta: the reference's transform() executed unmodified, gradients by autograd over its op sequence (matmul, div_no_nan,
+    bilinear_interp).  No reference caller differentiates them (model.py:156-167 feeds random constants); built for
+    completeness.  Own generator: the older fixtures stay bit-identical.  `grad_theta_grid` isolates the grid stage
+    (_transform alone, random upstream gradients on x_s and y_s)."""
+    rng = np.random.default_rng(20261021)
+    st = tf.load_reference(os.path.join(REF, 'spatial_transformer.py'), 'ref_spatial_transformer_grad')
+    cases = {}
+    for name, proj, b, h, w, c, osz in [('projective_grad', True, 3, 12, 16, 3, (12, 16)), ('projective_grad_c18', True, 2, 10, 14, 18, (9, 11)),
+                                        ('affine_grad', False, 2, 12, 16, 3, (10, 18))]:
+        im = smooth_image(rng, b, h, w, c)
+        if proj:
+            theta = (rng.uniform(-1, 1, (b, 8)) * np.array([0.1, 0.1, 0.5, 0.1, 0.1, 0.5, 0.1, 0.1])
+                     + np.array([1.0, 0, 0, 0, 1.0, 0, 0, 0])).astype(np.float32)      # model.py:161-163
+            tr = st.ProjectiveTransformer(list(osz))
+        else:
+            theta = (rng.uniform(-0.2, 0.2, (b, 6)) + np.array([1.0, 0, 0, 0, 1.0, 0])).astype(np.float32)
+            tr = st.AffineTransformer(list(osz))
+        g_out = rng.standard_normal((b, osz[0], osz[1], c)).astype(np.float32)
+        im_t, th_t = tt(im).requires_grad_(True), tt(theta).requires_grad_(True)
+        out = tr.transform(im_t, th_t)
+        (out * tt(g_out)).sum().backward()
+        x_s, y_s = tr._transform(tt(im), tt(theta))
+        # the grid stage alone: gradient of sum(x_s * g_x + y_s * g_y) w.r.t. theta
+        g_x = rng.standard_normal(x_s.shape).astype(np.float32)
+        g_y = rng.standard_normal(y_s.shape).astype(np.float32)
+        th2 = tt(theta).requires_grad_(True)
+        x2, y2 = tr._transform(tt(im), th2)
+        ((x2 * tt(g_x)).sum() + (y2 * tt(g_y)).sum()).backward()
+        cases[name] = dict(im=im, theta=theta, out_size=np.array(osz), g_out=g_out, out=out.detach().numpy(), x=x_s.numpy(), y=y_s.numpy(),
+                           grad_im=im_t.grad.numpy(), grad_theta=th_t.grad.numpy(), g_x=g_x, g_y=g_y, grad_theta_grid=th2.grad.numpy())
+    return cases
+
+
 def main():
     rng = np.random.default_rng(20261018)
     allc = {}
@@ -228,6 +263,7 @@ def main():
     allc.update(sampler_cases(rng))
     allc.update(loss_cases())
     allc.update(elastic_cases())
+    allc.update(transformer_grad_cases())
     for name, arrays in allc.items():
         path = os.path.join(OUT, name + '.npz')
         np.savez_compressed(path, **arrays)

@@ -435,3 +435,64 @@ def test_tps_backward_in_node_mode_vs_oracle(shape):
     _, e_gx, e_gy = O.tps_interpolate_bwd(u, xe.cpu().numpy(), ye.cpu().numpy(), h, w, g_out)
     assert rel(gxe.cpu().numpy(), e_gx.reshape(-1) + gx_in) <= 1e-4 and rel(gye.cpu().numpy(), e_gy.reshape(-1) + gy_in) <= 1e-4
     print('   node vs per-pixel evaluation: grad_T differs by %.2e (corner flips)' % rel(gT.cpu().numpy(), gTe.cpu().numpy()))
+
+
+# ---- backward of ProjectiveTransformer / AffineTransformer (VERDICT r1 "missing" 6; no reference caller differentiates them) ----
+@pytest.mark.parametrize('name', ['projective_grad', 'projective_grad_c18', 'affine_grad'])
+def test_transformer_backward_vs_reference_golden(name):
+    """Fixtures: the reference's transform() executed unmodified with autograd over its op sequence
+    (make_golden.transformer_grad_cases).  Grid stage through the raw C ABI: rel <= 1e-5 (fp64 partial sums); end to end
+    through the drop-in classes: max-norm rel <= 1e-4 and element-wise |a-b| <= 1e-4|b| + 2e-5 max|b|."""
+    from coupe.dvsg_b200 import _lib
+    from coupe.dvsg_b200.spatial_transformer import AffineTransformer, ProjectiveTransformer
+    lib = _lib.load()
+    g = load_golden(name)
+    proj = name.startswith('projective')
+    osz = [int(v) for v in g['out_size']]
+    b = g['im'].shape[0]
+    th, gx, gy = cu(g['theta']), cu(g['g_x']), cu(g['g_y'])
+    gt = torch.full_like(th, float('nan'))
+    rc = lib.dvsg_homography_grid_bwd(th.data_ptr(), gx.data_ptr(), gy.data_ptr(), 1 if proj else 0, gt.data_ptr(), b, osz[0], osz[1], 0)
+    assert rc == 0, lib.dvsg_last_error()
+    torch.cuda.synchronize()
+    assert rel(gt.cpu().numpy(), g['grad_theta_grid']) <= 1e-5
+    tr = (ProjectiveTransformer if proj else AffineTransformer)(osz)
+    im, theta = cu(g['im']).requires_grad_(True), cu(g['theta']).requires_grad_(True)
+    out = tr.transform(im, theta)
+    assert np.abs(out.detach().cpu().numpy() - g['out']).max() <= 1e-5
+    (out * cu(g['g_out'])).sum().backward()
+    for nm, got, want in (('grad_im', im.grad, g['grad_im']), ('grad_theta', theta.grad, g['grad_theta'])):
+        assert rel(got.cpu().numpy(), want) <= 1e-4, nm
+        ok, worst, at = close_elementwise(got.cpu().numpy(), want)
+        assert ok, (nm, worst, at)
+    # the coordinates themselves are differentiable too (_transform)
+    theta2 = cu(g['theta']).requires_grad_(True)
+    xs, ys = tr._transform(cu(g['im']), theta2)
+    ((xs * gx).sum() + (ys * gy).sum()).backward()
+    assert rel(theta2.grad.cpu().numpy(), g['grad_theta_grid']) <= 1e-5
+
+
+@pytest.mark.parametrize('case', [(2, 72, 128, 3, (72, 128), True), (2, 40, 64, 18, (36, 60), True), (3, 50, 70, 3, (64, 96), False)],
+                         ids=['projective_c3_tile_path', 'projective_c18_wide_path', 'affine_resize'])
+def test_transformer_backward_vs_oracle_seeded(case):
+    """Seeded, larger than the fixtures, against oracle.homography_transform_bwd (fp64 grid-stage chain on the oracle's own
+    sampler backward): rel <= 1e-4 of the max-norm; theta as model.py:161-163 draws it."""
+    from coupe.dvsg_b200.spatial_transformer import AffineTransformer, ProjectiveTransformer
+    b, h, w, c, osz, proj = case
+    rng = np.random.default_rng(h * w + c)
+    im = smooth_image(rng, b, h, w, c)
+    if proj:
+        theta = (rng.uniform(-1, 1, (b, 8)) * np.array([0.1, 0.1, 0.5, 0.1, 0.1, 0.5, 0.1, 0.1]) + np.array([1.0, 0, 0, 0, 1.0, 0, 0, 0])).astype(np.float32)
+    else:
+        theta = (rng.uniform(-0.2, 0.2, (b, 6)) + np.array([1.0, 0, 0, 0, 1.0, 0])).astype(np.float32)
+    g_out = rng.standard_normal((b, osz[0], osz[1], c)).astype(np.float32)
+    tr = (ProjectiveTransformer if proj else AffineTransformer)(list(osz))
+    I, TH = cu(im).requires_grad_(True), cu(theta).requires_grad_(True)
+    (tr.transform(I, TH) * cu(g_out)).sum().backward()
+    r_gim, r_gth = O.homography_transform_bwd(im, theta, osz, g_out, proj)
+    assert rel(I.grad.cpu().numpy(), r_gim) <= 1e-4
+    assert rel(TH.grad.cpu().numpy(), r_gth) <= 1e-4
+    # only the input needs a gradient: theta's chain is skipped, the result is the same
+    I2 = cu(im).requires_grad_(True)
+    (tr.transform(I2, cu(theta)) * cu(g_out)).sum().backward()
+    assert rel(I2.grad.cpu().numpy(), I.grad.cpu().numpy()) <= 1e-6      # (float atomics in the generic kernel: the order may differ)

@@ -130,3 +130,21 @@ def test_elastic_transformer_vs_reference_golden(name):
     assert np.abs(l_inv - g['l_inv']).max() <= 1e-5 * np.abs(g['l_inv']).max()
     # the sampler on the golden's own coordinates is bit-exact (bilinear_interp, B2)
     np.testing.assert_array_equal(O.bilinear_interp(g['im'], g['x'], g['y'], osz).reshape(g['out'].shape), g['out'])
+
+
+# ---- backward of the projective / affine transformers (make_golden.transformer_grad_cases) ----
+@pytest.mark.parametrize('name', ['projective_grad', 'projective_grad_c18', 'affine_grad'])
+def test_transformer_backward_vs_reference_golden(name):
+    """The reference's transform() with autograd over its own op sequence: grid-stage gradient rel <= 1e-5 (fp64 oracle
+    against the fp32 graph), end-to-end gradients w.r.t. theta and the input rel <= 1e-4 of the max-norm."""
+    g = load_golden(name)
+    proj = name.startswith('projective')
+    osz = tuple(int(v) for v in g['out_size'])
+    xs, ys = (O.projective_grid if proj else O.affine_grid)(g['theta'], osz)
+    assert max(np.abs(xs - g['x']).max(), np.abs(ys - g['y']).max()) <= 2e-6
+    gt = O.homography_grid_bwd(g['theta'], osz, g['g_x'], g['g_y'], proj)
+    assert gt.shape == g['grad_theta_grid'].shape
+    assert np.abs(gt - g['grad_theta_grid']).max() <= 1e-5 * np.abs(g['grad_theta_grid']).max()
+    g_im, g_theta = O.homography_transform_bwd(g['im'], g['theta'], osz, g['g_out'], proj)
+    assert np.abs(g_im - g['grad_im']).max() <= 1e-4 * np.abs(g['grad_im']).max()
+    assert np.abs(g_theta - g['grad_theta']).max() <= 1e-4 * np.abs(g['grad_theta']).max()
