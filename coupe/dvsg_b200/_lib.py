@@ -31,6 +31,7 @@ PROTOTYPES = {
     'dvsg_tps_solve_prepared': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     'dvsg_tps_solve_offsets_prepared': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     'dvsg_tps_solve_bwd_prepared': (c_int, [_P, c_longlong, _P, _P, c_int, c_int, _P, c_size_t, _P]),
+    'dvsg_tps_coord_bwd': (c_int, [_P, c_longlong, _P, _P, _P, _P, _P] + [c_int] * 4 + [_P, c_size_t, _P]),
     'dvsg_tps_warp_fwd': (c_int, [_P, _P, c_longlong, _P, _P, _P, _P, _P] + [c_int] * 8 + [_P]),
     'dvsg_tps_warp_frames': (c_int, [_P, _P, _P, _P, c_size_t, _P, _P, _P, _P, _P] + [c_int] * 7 + [_P]),
     'dvsg_tps_warp_frames_offsets': (c_int, [_P, _P, _P, _P, c_size_t, _P, _P, _P, _P, _P] + [c_int] * 7 + [_P]),

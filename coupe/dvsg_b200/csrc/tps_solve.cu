@@ -425,9 +425,110 @@ static int solve_impl(const float* coord, long long stride, const float* rhs, fl
     return check_launch("tps_apply_kernel");
 }
 
+// ---- gradient w.r.t. the control-point positions `coord` ------------------------------------------------------------
+// No reference call site differentiates the mesh (model.py:62-68 builds it as a constant); provided for completeness.
+// coord enters ThinPlateSpline.py in three places:
+//   (1) the radial terms of the dense grid, r_k(pix) = f(|pix - c_k|^2), f(d2) = d2 log(d2 + 1e-6)   (:100-105, :129)
+//         d c_k += sum_pix (gx Tx_k + gy Ty_k) f'(d2) * 2 (c_k - pix),   f'(d2) = log(d2 + 1e-6) + d2 / (d2 + 1e-6)
+//   (2) the system matrix W of the solve (:147-159), through  Y = W^-1 tp:   dW = -G Y^T,  G = W^-T dY
+//         d c_k += dW[k][1|2] + dW[pn+1|pn+2][3+k] + sum_j (dW[k][3+j] + dW[j][3+k]) f'(d2_kj) * 2 (c_k - c_j)
+//   (3) the right-hand side coord + vector of ThinPlateSpline (:161) -- that term equals the gradient w.r.t. `vector`
+//       and is added by the caller.
+// One CTA per (control point, frame); fp64 throughout; deterministic.
+constexpr int CB_THREADS = 256;
+
+__device__ __forceinline__ double tps_fprime(double d2) { return log(d2 + 1e-6) + d2 / (d2 + 1e-6); }
+
+__global__ void __launch_bounds__(CB_THREADS) tps_coord_bwd_kernel(const double* __restrict__ work, int shared_sys, const float* __restrict__ coord,
+                                                                  long long coord_stride, const float* __restrict__ T,
+                                                                  const float* __restrict__ grad_T, const float* __restrict__ gx,
+                                                                  const float* __restrict__ gy, float* __restrict__ grad_coord, int oh, int ow, int pn,
+                                                                  float step_x, float step_y) {
+    extern __shared__ double s_g[];                       // G [N][2]
+    __shared__ double s_rx[CB_THREADS / 32], s_ry[CB_THREADS / 32];
+    const int k = blockIdx.x, b = blockIdx.y, N = pn + 3, M = 2 * N, tid = threadIdx.x;
+    const float* cb = coord + (size_t)b * coord_stride;
+    const float* Tb = T + (size_t)b * 2 * N;
+    const float* gTb = grad_T + (size_t)b * 2 * N;
+    const double* winv = work + (size_t)(shared_sys ? 0 : b) * N * M + N;
+    const double ckx = (double)cb[2 * k], cky = (double)cb[2 * k + 1];
+    double ax = 0.0, ay = 0.0;
+    // (2) G[i][c] = sum_m Winv[m][i] * grad_T[c][m]
+    for (int i = tid; i < N; i += CB_THREADS) {
+        double g0 = 0.0, g1 = 0.0;
+        for (int m = 0; m < N; ++m) {
+            const double w = winv[(size_t)m * M + i];
+            g0 += w * (double)gTb[m];
+            g1 += w * (double)gTb[N + m];
+        }
+        s_g[2 * i] = g0; s_g[2 * i + 1] = g1;
+    }
+    __syncthreads();
+    // dW[i][j] = -(G[i][0] Y[j][0] + G[i][1] Y[j][1]),  Y[j][c] = T[c][j]
+    auto dW = [&](int i, int j) { return -(s_g[2 * i] * (double)Tb[j] + s_g[2 * i + 1] * (double)Tb[N + j]); };
+    if (tid == 0) {
+        ax += dW(k, 1) + dW(pn + 1, 3 + k);
+        ay += dW(k, 2) + dW(pn + 2, 3 + k);
+    }
+    for (int j = tid; j < pn; j += CB_THREADS) {
+        if (j == k) continue;                             // 2 (c_k - c_k) = 0
+        const double dx = ckx - (double)cb[2 * j], dy = cky - (double)cb[2 * j + 1];
+        // the reference forms d2 in fp32 (:152); the gradient is taken at that value
+        const double d2 = (double)tps_d2(cb[2 * k], cb[2 * k + 1], cb[2 * j], cb[2 * j + 1]);
+        const double f = (dW(k, 3 + j) + dW(j, 3 + k)) * tps_fprime(d2) * 2.0;
+        ax += f * dx; ay += f * dy;
+    }
+    // (1) the dense grid
+    if (gx != nullptr) {
+        const double tx = (double)Tb[3 + k], ty = (double)Tb[N + 3 + k];
+        const long long n = (long long)oh * ow;
+        const float* gxb = gx + (size_t)b * n;
+        const float* gyb = gy + (size_t)b * n;
+        for (long long pix = tid; pix < n; pix += CB_THREADS) {
+            const int row = (int)(pix / ow), col = (int)(pix % ow);
+            const float xt = lin_coord(col, step_x), yt = lin_coord(row, step_y);
+            const double w = (double)__ldg(gxb + pix) * tx + (double)__ldg(gyb + pix) * ty;
+            const double d2 = (double)tps_d2(xt, yt, cb[2 * k], cb[2 * k + 1]);
+            const double f = w * tps_fprime(d2) * 2.0;
+            ax += f * (ckx - (double)xt); ay += f * (cky - (double)yt);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o); }
+    if ((tid & 31) == 0) { s_rx[tid >> 5] = ax; s_ry[tid >> 5] = ay; }
+    __syncthreads();
+    if (tid == 0) {
+        double sx = 0.0, sy = 0.0;
+        for (int w = 0; w < CB_THREADS / 32; ++w) { sx += s_rx[w]; sy += s_ry[w]; }
+        grad_coord[((size_t)b * pn + k) * 2] = (float)sx;
+        grad_coord[((size_t)b * pn + k) * 2 + 1] = (float)sy;
+    }
+}
+
 }  // namespace dvsg
 
 using namespace dvsg;
+
+extern "C" int dvsg_tps_coord_bwd(const float* coord, long long coord_batch_stride, const float* T, const float* grad_T, const float* grad_x,
+                                  const float* grad_y, float* grad_coord, int B, int oh, int ow, int pn, const void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    DVSG_REQUIRE(B >= 0 && pn >= 3 && oh >= 0 && ow >= 0, "tps_coord_bwd: bad shape");
+    if (B == 0) return DVSG_OK;
+    DVSG_REQUIRE(coord && T && grad_T && grad_coord && workspace, "tps_coord_bwd: null pointer");
+    DVSG_REQUIRE((grad_x == nullptr) == (grad_y == nullptr), "tps_coord_bwd: grad_x and grad_y must be given together");
+    DVSG_REQUIRE(coord_batch_stride == 0 || coord_batch_stride >= 2LL * pn, "tps_coord_bwd: coord stride %lld < 2*pn", coord_batch_stride);
+    DVSG_REQUIRE(B <= 65535 && pn + 3 <= 2048 && (long long)oh * ow < (1LL << 31), "tps_coord_bwd: batch / mesh / frame too large");
+    const size_t need = big_workspace_bytes(B, pn, coord_batch_stride);
+    DVSG_REQUIRE(workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 7u) == 0,
+                 "tps_coord_bwd: the workspace dvsg_tps_prepare filled for this mesh is required (%zu bytes, 8-byte aligned; %zu given)", need,
+                 workspace_bytes);
+    const bool grid = grad_x != nullptr && oh > 0 && ow > 0;
+    tps_coord_bwd_kernel<<<dim3((unsigned)pn, (unsigned)B), CB_THREADS, (size_t)2 * (pn + 3) * sizeof(double), (cudaStream_t)stream>>>(
+        reinterpret_cast<const double*>(workspace), coord_batch_stride == 0, coord, coord_batch_stride, T, grad_T, grid ? grad_x : nullptr,
+        grid ? grad_y : nullptr, grad_coord, oh, ow, pn, ow > 1 ? 2.0f / (float)(ow - 1) : 0.0f, oh > 1 ? 2.0f / (float)(oh - 1) : 0.0f);
+    count_launch();
+    return check_launch("tps_coord_bwd_kernel");
+}
 
 extern "C" size_t dvsg_tps_solve_workspace_bytes(int B, int pn, long long coord_batch_stride) {
     if (pn + 3 <= SMALL_N || B <= 0) return 0;

@@ -154,6 +154,25 @@ def tps_solve_bwd(coord, grad_T, cache_mesh=True):
     return g
 
 
+def tps_coord_bwd(coord, T, grad_T, grad_x, grad_y, out_size):
+    """Gradient w.r.t. the control points through the dense grid and the system matrix (dvsg_tps_coord_bwd; the right-hand
+    side's share is the caller's).  Returns [B, pn, 2]; the mesh's inverse is computed here, uncached."""
+    lib = _lib.load()
+    B, _, N = T.shape
+    oh, ow = out_hw(out_size)
+    cbuf, cstride, pn = _mesh_args(coord.detach(), B, N - 3)
+    dev = T.device
+    nbytes = lib.dvsg_tps_prepare_workspace_bytes(B, pn, cstride)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    g = torch.empty((B, pn, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        sp = stream_ptr(dev)
+        _lib.check(lib.dvsg_tps_prepare(ptr(cbuf), cstride, B, pn, ptr(ws), nbytes, sp), 'dvsg_tps_prepare')
+        rc = lib.dvsg_tps_coord_bwd(ptr(cbuf), cstride, ptr(T), ptr(grad_T), ptr(grad_x), ptr(grad_y), ptr(g), B, oh, ow, pn, ptr(ws), nbytes, sp)
+    _lib.check(rc, 'dvsg_tps_coord_bwd')
+    return g
+
+
 # ---- K2+K3 / K4 ------------------------------------------------------------------------------
 def tps_warp_fwd(U, coord, T, out_size, want_grid=True, want_mask=False, flags=0):
     lib = _lib.load()
@@ -210,6 +229,7 @@ class _TpsWarp(torch.autograd.Function):
         ctx.out_size = out_size
         ctx.want_grid = want_grid
         ctx.cache_mesh = cache_mesh
+        ctx.offsets = offsets
         if not want_grid:
             x, y = out.new_empty(0), out.new_empty(0)
             ctx.mark_non_differentiable(x, y)
@@ -226,10 +246,20 @@ class _TpsWarp(torch.autograd.Function):
         if not ctx.want_grid:
             grad_x = grad_y = None
         need_U = ctx.needs_input_grad[0]
+        need_c = ctx.needs_input_grad[1]
         need_t = ctx.needs_input_grad[2]
-        gU, gT, _, _ = tps_warp_bwd(U, coord, T, ctx.out_size, grad_out.contiguous(), grad_x, grad_y, need_grad_U=need_U)
-        g_target = tps_solve_bwd(coord, gT, cache_mesh=ctx.cache_mesh) if need_t else None
-        return gU, None, g_target, None, None, None, None, None
+        gU, gT, gxs, gys = tps_warp_bwd(U, coord, T, ctx.out_size, grad_out.contiguous(), grad_x, grad_y, need_grad_U=need_U,
+                                        want_grid_grad=need_c)
+        g_target = tps_solve_bwd(coord, gT, cache_mesh=ctx.cache_mesh) if (need_t or (need_c and ctx.offsets)) else None
+        g_coord = None
+        if need_c:
+            # no reference caller differentiates the mesh (model.py:62-68): built for completeness (dvsg_tps_coord_bwd)
+            g_coord = tps_coord_bwd(coord, T, gT, gxs, gys, ctx.out_size)
+            if ctx.offsets:                       # coord also sits in the right-hand side coord + vector (ThinPlateSpline.py:161)
+                g_coord = g_coord + g_target
+            if coord.dim() == 2:
+                g_coord = g_coord.sum(dim=0)
+        return gU, g_coord, (g_target if need_t else None), None, None, None, None, None
 
 
 def _tps_args(U, coord, target):
@@ -240,8 +270,7 @@ def _tps_args(U, coord, target):
     coord = _as_mesh(coord, U)
     target = as_cuda_f32(target, 'target', like=U)
     if coord.requires_grad:
-        raise NotImplementedError('gradient w.r.t. the control-point positions is not implemented: every reference '
-                                  'call site passes a constant mesh (model.py:62-68)')
+        cache_mesh = False        # a mesh that is being optimised changes between calls: never reuse a cached inverse
     return U, coord, target, cache_mesh
 
 

@@ -73,6 +73,18 @@ int dvsg_tps_solve(const float* coord, long long coord_batch_stride, const float
 int dvsg_tps_solve_bwd(const float* coord, long long coord_batch_stride, const float* grad_T,
                        float* grad_target, int B, int pn, void* workspace,
                        size_t workspace_bytes, void* stream);
+/* Gradient w.r.t. the control-point positions themselves (no reference caller needs it: the
+ * mesh is a constant, model.py:62-68; provided for completeness).  coord enters through the
+ * radial terms of the dense grid (ThinPlateSpline.py:100-105) and through the system matrix of
+ * the solve (:147-159):  grad_coord [B,pn,2] = both contributions, given T, grad_T [B,2,pn+3]
+ * and the gradients grad_x / grad_y flat [B*oh*ow] w.r.t. the normalised sampling coordinates
+ * (as dvsg_tps_warp_bwd writes them; null = solve part only).  `workspace` must hold W^-1 of
+ * this mesh (dvsg_tps_prepare with the same coord / stride).  The right-hand side coord + vector
+ * of ThinPlateSpline (:161) contributes grad_target, which the caller adds.  fp64, deterministic. */
+int dvsg_tps_coord_bwd(const float* coord, long long coord_batch_stride, const float* T,
+                       const float* grad_T, const float* grad_x, const float* grad_y,
+                       float* grad_coord, int B, int oh, int ow, int pn, const void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* Constant meshes (every reference call site, model.py:62-68): invert the system(s) into the
  * workspace once with dvsg_tps_prepare (fp64 Gauss-Jordan, any mesh size), then only apply

@@ -256,6 +256,40 @@ def transformer_grad_cases():
     return cases
 
 
+def coord_grad_cases():
+    """Gradient w.r.t. the control-point positions `coord` of ThinPlateSpline / ThinPlateSpline2 (no reference caller takes
+    it: model.py:62-68 builds the mesh as a constant): the reference executed unmodified with coord.requires_grad, fp32 and
+    fp64.  Irregular meshes (a regular mesh + jitter), one per frame.  Own generator: the older fixtures stay bit-identical."""
+    rng = np.random.default_rng(20261022)
+    ref_tps = tf.load_reference(os.path.join(REF, 'ThinPlateSpline.py'), 'ref_ThinPlateSpline_cg')
+    ref_tps2 = tf.load_reference(os.path.join(REF, 'ThinPlateSpline2.py'), 'ref_ThinPlateSpline2_cg')
+    cases = {}
+    for name, b, h, w, c, (mr, mc), osz, amp, variant in [('tps_coord_grad', 2, 20, 28, 3, (4, 4), (20, 28), 0.10, 1),
+                                                           ('tps2_coord_grad', 2, 18, 24, 3, (3, 4), (16, 20), 0.08, 2)]:
+        u = smooth_image(rng, b, h, w, c)
+        coord = (mesh(mr, mc, b) + rng.uniform(-0.06, 0.06, (b, mr * mc, 2))).astype(np.float32)
+        vec = rng.uniform(-amp, amp, coord.shape).astype(np.float32)
+        second = vec if variant == 1 else (coord + vec).astype(np.float32)
+        fn = ref_tps.ThinPlateSpline if variant == 1 else ref_tps2.ThinPlateSpline2
+        n_out = b * osz[0] * osz[1]
+        g_out = rng.standard_normal((b, osz[0], osz[1], c)).astype(np.float32)
+        g_x = (rng.standard_normal(n_out) * 0.1).astype(np.float32)
+        g_y = (rng.standard_normal(n_out) * 0.1).astype(np.float32)
+        res = {}
+        for tag, dtype in (('', torch.float32), ('64', torch.float64)):
+            tf.set_float(dtype)
+            u_t = tt(u).to(dtype).requires_grad_(True)
+            s_t = tt(second).to(dtype).requires_grad_(True)
+            c_t = tt(coord).to(dtype).requires_grad_(True)
+            out, x, y = fn(u_t, c_t, s_t, list(osz))
+            ((out * tt(g_out).to(dtype)).sum() + (x * tt(g_x).to(dtype)).sum() + (y * tt(g_y).to(dtype)).sum()).backward()
+            tf.set_float(torch.float32)
+            res.update({'out' + tag: out.detach().numpy(), 'x' + tag: x.detach().numpy(), 'y' + tag: y.detach().numpy(),
+                        'grad_u' + tag: u_t.grad.numpy(), 'grad_second' + tag: s_t.grad.numpy(), 'grad_coord' + tag: c_t.grad.numpy()})
+        cases[name] = dict(u=u, coord=coord, second=second, out_size=np.array(osz), variant=np.array(variant), g_out=g_out, g_x=g_x, g_y=g_y, **res)
+    return cases
+
+
 def main():
     rng = np.random.default_rng(20261018)
     allc = {}
@@ -264,6 +298,7 @@ def main():
     allc.update(loss_cases())
     allc.update(elastic_cases())
     allc.update(transformer_grad_cases())
+    allc.update(coord_grad_cases())
     for name, arrays in allc.items():
         path = os.path.join(OUT, name + '.npz')
         np.savez_compressed(path, **arrays)

@@ -496,3 +496,74 @@ def test_transformer_backward_vs_oracle_seeded(case):
     I2 = cu(im).requires_grad_(True)
     (tr.transform(I2, cu(theta)) * cu(g_out)).sum().backward()
     assert rel(I2.grad.cpu().numpy(), I.grad.cpu().numpy()) <= 1e-6      # (float atomics in the generic kernel: the order may differ)
+
+
+# ---- gradient w.r.t. the control-point positions (VERDICT r1 "missing" 6; no reference caller takes it) ----
+@pytest.mark.parametrize('name', ['tps_coord_grad', 'tps2_coord_grad'])
+def test_tps_coord_gradient_vs_reference_golden(name):
+    """Stage-wise through the raw C ABI (dvsg_tps_coord_bwd on the oracle's own T, grad_T and coordinate gradients: no
+    corner can flip): rel <= 1e-5 against oracle.tps_coord_bwd.  End to end through the drop-ins with coord.requires_grad
+    against the reference's own fp64 run: rel <= 1e-4 (max-norm) for coord, the second argument and the image."""
+    from coupe.dvsg_b200 import _lib
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline
+    from coupe.dvsg_b200.ThinPlateSpline2 import ThinPlateSpline2
+    lib = _lib.load()
+    g = load_golden(name)
+    osz = [int(v) for v in g['out_size']]
+    coord, variant = g['coord'], int(g['variant'])
+    b, pn = coord.shape[:2]
+    target = (coord + g['second']).astype(np.float32) if variant == 1 else g['second']
+    t, w_inv = O.tps_solve(coord, target, return_inverse=True)
+    x, y = O.tps_grid(t, coord, osz[0], osz[1])
+    _, gx, gy = O.tps_interpolate_bwd(g['u'], x, y, osz[0], osz[1], g['g_out'])
+    gx, gy = (gx + g['g_x']).astype(np.float32), (gy + g['g_y']).astype(np.float32)
+    g_t = O.tps_grid_bwd(coord, osz[0], osz[1], gx, gy)
+    want = O.tps_coord_bwd(coord, t, w_inv, g_t, osz[0], osz[1], gx, gy)
+    C_ = cu(coord)
+    nbytes = lib.dvsg_tps_prepare_workspace_bytes(b, pn, pn * 2)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    assert lib.dvsg_tps_prepare(C_.data_ptr(), pn * 2, b, pn, ws.data_ptr(), nbytes, 0) == 0, lib.dvsg_last_error()
+    got = torch.full((b, pn, 2), float('nan'), device=DEV)
+    T_, gT_, gx_, gy_ = cu(t), cu(g_t), cu(gx), cu(gy)
+    rc = lib.dvsg_tps_coord_bwd(C_.data_ptr(), pn * 2, T_.data_ptr(), gT_.data_ptr(), gx_.data_ptr(), gy_.data_ptr(), got.data_ptr(),
+                                b, osz[0], osz[1], pn, ws.data_ptr(), nbytes, 0)
+    assert rc == 0, lib.dvsg_last_error()
+    torch.cuda.synchronize()
+    assert rel(got.cpu().numpy(), want) <= 1e-5
+    # solve part alone (grad_x = grad_y = null)
+    rc = lib.dvsg_tps_coord_bwd(C_.data_ptr(), pn * 2, T_.data_ptr(), gT_.data_ptr(), 0, 0, got.data_ptr(), b, osz[0], osz[1], pn, ws.data_ptr(), nbytes, 0)
+    assert rc == 0, lib.dvsg_last_error()
+    assert rel(got.cpu().numpy(), O.tps_coord_bwd(coord, t, w_inv, g_t, osz[0], osz[1], None, None)) <= 1e-5
+    # end to end
+    U = cu(g['u']).requires_grad_(True)
+    Cg = cu(coord).requires_grad_(True)
+    S = cu(g['second']).requires_grad_(True)
+    out, xs, ys = (ThinPlateSpline if variant == 1 else ThinPlateSpline2)(U, Cg, S, osz)
+    ((out * cu(g['g_out'])).sum() + (xs * cu(g['g_x'])).sum() + (ys * cu(g['g_y'])).sum()).backward()
+    print('coord-grad rel vs fp64 reference run:', rel(Cg.grad.cpu().numpy(), g['grad_coord64']))
+    assert rel(Cg.grad.cpu().numpy(), g['grad_coord64']) <= 1e-4
+    assert rel(S.grad.cpu().numpy(), g['grad_second64']) <= 1e-4
+    assert rel(U.grad.cpu().numpy(), g['grad_u64']) <= 1e-4
+
+
+def test_tps_coord_gradient_of_a_mesh_shared_by_the_batch():
+    """coord of shape [pn, 2] (one mesh for every frame, as model.py:68 builds it) with requires_grad: its gradient is the sum
+    over frames of the per-frame gradients (same call with the mesh repeated per frame)."""
+    from coupe.dvsg_b200.ThinPlateSpline import ThinPlateSpline
+    rng = np.random.default_rng(3)
+    b, h, w = 3, 40, 56
+    mesh = (tiled_mesh(4, 4, 1)[0] + rng.uniform(-0.05, 0.05, (16, 2))).astype(np.float32)
+    vec = rng.uniform(-0.1, 0.1, (b, 16, 2)).astype(np.float32)
+    U = cu(smooth_image(rng, b, h, w, 3))
+    g_out = cu(rng.standard_normal((b, h, w, 3)).astype(np.float32))
+    C1 = cu(mesh).requires_grad_(True)
+    out, _, _ = ThinPlateSpline(U, C1, cu(vec), [h, w])
+    (out * g_out).sum().backward()
+    C2 = cu(np.tile(mesh[None], (b, 1, 1))).requires_grad_(True)
+    out2, _, _ = ThinPlateSpline(U, C2, cu(vec), [h, w])
+    (out2 * g_out).sum().backward()
+    assert torch.equal(out, out2) or float((out - out2).abs().max()) <= 1e-5
+    assert rel(C1.grad.cpu().numpy(), C2.grad.sum(dim=0).cpu().numpy()) <= 1e-4
+    # against the oracle
+    _, _, want = O.thin_plate_spline_bwd(U.cpu().numpy(), np.tile(mesh[None], (b, 1, 1)), vec, (h, w), g_out.cpu().numpy(), want_coord=True)
+    assert rel(C2.grad.cpu().numpy(), want) <= 2e-4

@@ -148,3 +148,30 @@ def test_transformer_backward_vs_reference_golden(name):
     g_im, g_theta = O.homography_transform_bwd(g['im'], g['theta'], osz, g['g_out'], proj)
     assert np.abs(g_im - g['grad_im']).max() <= 1e-4 * np.abs(g['grad_im']).max()
     assert np.abs(g_theta - g['grad_theta']).max() <= 1e-4 * np.abs(g['grad_theta']).max()
+
+
+# ---- gradient w.r.t. the control-point positions (make_golden.coord_grad_cases) ----
+def _oracle_coord_grad(g):
+    osz = tuple(int(v) for v in g['out_size'])
+    coord = g['coord']
+    if int(g['variant']) == 1:
+        _, g_second, g_coord = O.thin_plate_spline_bwd(g['u'], coord, g['second'], osz, g['g_out'], g['g_x'], g['g_y'], want_coord=True)
+        return g_second, g_coord
+    t, w_inv = O.tps_solve(coord, g['second'], return_inverse=True)                  # ThinPlateSpline2: the targets are a separate input
+    x, y = O.tps_grid(t, coord, osz[0], osz[1])
+    _, gx, gy = O.tps_interpolate_bwd(g['u'], x, y, osz[0], osz[1], g['g_out'])
+    gx, gy = gx + g['g_x'], gy + g['g_y']
+    g_t = O.tps_grid_bwd(coord, osz[0], osz[1], gx, gy)
+    return O.tps_solve_bwd(w_inv, g_t), O.tps_coord_bwd(coord, t, w_inv, g_t, osz[0], osz[1], gx, gy)
+
+
+@pytest.mark.parametrize('name', ['tps_coord_grad', 'tps2_coord_grad'])
+def test_tps_coord_gradient_vs_reference_golden(name):
+    """ThinPlateSpline / ThinPlateSpline2 executed unmodified with coord.requires_grad: the oracle's restatement of that
+    gradient (grid radial terms + system matrix + right-hand side) is within 2e-5 of the fp64 run of the reference graph
+    and 1e-4 of its fp32 run (max-norm relative)."""
+    g = load_golden(name)
+    g_second, g_coord = _oracle_coord_grad(g)
+    assert np.abs(g_coord - g['grad_coord64']).max() <= 2e-5 * np.abs(g['grad_coord64']).max()
+    assert np.abs(g_coord - g['grad_coord']).max() <= 1e-4 * np.abs(g['grad_coord']).max()
+    assert np.abs(g_second - g['grad_second64']).max() <= 2e-5 * np.abs(g['grad_second64']).max()
