@@ -32,8 +32,8 @@ def tps_case(B, H, W, m, amp=0.2):
     return U, coord, T
 
 
-def smooth_flow(B, H, W, amp=8.0, jitter=0.5):
-    lat = (torch.rand((B, 2, 9, 16), device=dev) - 0.5) * 2 * amp
+def smooth_flow(B, H, W, amp=8.0, jitter=0.5, lattice=(9, 16)):
+    lat = (torch.rand((B, 2) + tuple(lattice), device=dev) - 0.5) * 2 * amp
     f = torch.nn.functional.interpolate(lat, size=(H, W), mode='bilinear', align_corners=True)
     f = f + (torch.rand((B, 2, H, W), device=dev) - 0.5) * 2 * jitter
     return f.permute(0, 2, 3, 1).contiguous()
@@ -160,6 +160,14 @@ def bwd():
         rec('tf_warp bwd %s B=%d smooth flow (grad image only, trainer.py:246-247)' % (tag, B), ms, px, 44)
         ms = timeit(lambda: fb(True))
         rec('tf_warp bwd %s B=%d smooth flow (grad image and flow)' % (tag, B), ms, px, 64)
+        if H < 1080:
+            # the default field (+-8 px on a 9 x 16 lattice) has 32-px cells at this size: slope 0.5, most tiles fit no box.
+            # Same slope as the 1080p case: amplitude and lattice scaled with the frame
+            flow = smooth_flow(B, H, W, amp=8.0 * H / 1080.0, jitter=0.5 * H / 1080.0, lattice=(3, 5))
+            ms = timeit(lambda: fb(False))
+            rec('tf_warp bwd %s B=%d flow scaled to the frame (grad image only)' % (tag, B), ms, px, 44)
+            ms = timeit(lambda: fb(True))
+            rec('tf_warp bwd %s B=%d flow scaled to the frame (grad image and flow)' % (tag, B), ms, px, 64)
         del U, g, gU, flow, gf
 
 
