@@ -773,6 +773,38 @@ def test_node_evaluation_vs_exact_evaluation_and_fp64_oracle(case):
     assert (1.0 - same.mean()) <= 5e-3 + 2e3 * e_o.max()
 
 
+@pytest.mark.parametrize('case', [(2, 300, 500, (722, 1284), 4, True), (3, 724, 1276, (362, 1412), 5, False)],
+                         ids=['upscale_722x1284_per_frame_meshes', 'resize_362x1412_shared_mesh'])
+def test_node_evaluation_with_resize_ragged_edges_batch_and_mask(case):
+    """Node mode away from the square cases above: output size != input size, ow not a multiple of the 32-pixel tile, oh not
+    a multiple of the 8-row strip, several frames (per-frame meshes / one shared mesh), mask output.  Against the fp32 oracle
+    on every pixel: coordinates <= 2e-5 (the bar of the exact path), sampler and mask bit-exact on the kernel's own
+    coordinates; against the per-pixel kernel: coordinates <= 3e-6."""
+    from coupe.dvsg_b200 import _lib, ops
+    b, h, w, (oh, ow), m, per_frame = case
+    rng = np.random.default_rng(oh + ow)
+    u = smooth_image(rng, b, h, w, 3, period=40.0)
+    coord = tiled_mesh(m, m, b)
+    if per_frame:
+        coord = (coord + rng.uniform(-0.2, 0.2, coord.shape) / m).astype(np.float32)
+    vec = rng.uniform(-0.1, 0.1, coord.shape).astype(np.float32)
+    assert _lib.load().dvsg_tps_coords_mode(h, w, 3, oh, ow, m * m, 0) == 1
+    U = cu(u)
+    C_ = cu(coord) if per_frame else cu(coord[0])
+    T = ops.tps_solve(C_, cu(coord + vec))
+    on, xn, yn, mn = ops.tps_warp_fwd(U, C_, T, (oh, ow), want_grid=True, want_mask=True)
+    oe, xe, ye, me = ops.tps_warp_fwd(U, C_, T, (oh, ow), want_grid=True, want_mask=True, flags=TPS_EXACT)
+    torch.cuda.synchronize()
+    on, xn, yn, mn, xe, ye, Tn = (t.cpu().numpy() for t in (on, xn, yn, mn, xe, ye, T))
+    r_x, r_y = O.tps_grid(Tn, coord, oh, ow)
+    e = max(np.abs(xn - r_x).max(), np.abs(yn - r_y).max())
+    d = max(np.abs(xn - xe).max(), np.abs(yn - ye).max())
+    print('%s: |nodes - fp32 oracle| %.2e, |nodes - exact kernel| %.2e' % (case, e, d))
+    assert e <= 2e-5 and d <= 3e-6
+    np.testing.assert_array_equal(on, O.tps_interpolate(u, xn, yn, oh, ow).reshape(on.shape))
+    np.testing.assert_array_equal(mn, O.tps_interpolate(np.ones((b, h, w, 1), np.float32), xn, yn, oh, ow).reshape(mn.shape))
+
+
 @pytest.mark.parametrize('shape', [(1, 288, 512, 4), (3, 288, 512, 5), (2, 720, 1280, 4), (1, 96, 160, 5), (2, 40, 50, 4), (1, 288, 512, 6)],
                          ids=lambda s: 'B%d_%dx%d_m%d' % s)
 def test_online_call_is_one_launch_and_bit_identical_to_solve_then_warp(shape):
