@@ -395,33 +395,35 @@ def test_shared_mesh_solve_equals_per_frame_solve_bitwise_on_the_5x5_mesh():
         assert float((outs[0] - Tw).abs().max()) <= 2e-7 * float(Tw.abs().max())
 
 
-@pytest.mark.parametrize('shape', [(1, 540, 960, 5, 0.1), (1, 720, 1280, 4, 0.1), (2, 288, 512, 8, 0.04)], ids=lambda s: '%dx%dx%d_m%d' % s[:4])
+@pytest.mark.parametrize('shape', [(1, 540, 960, 5, 0.1), (1, 720, 1280, 4, 0.1), (2, 288, 512, 8, 0.04), (2, 300, 500, 4, 0.1, 722, 1284)],
+                         ids=lambda s: '%dx%dx%d_m%d' % s[:4] + ('_to_%dx%d' % s[5:] if len(s) > 5 else ''))
 def test_tps_backward_in_node_mode_vs_oracle(shape):
     """Shapes for which the tile kernels evaluate the spline on tile nodes (>= 0.5 Mpix, or >= 64 control points): forward and
     backward must see the SAME coordinates (the sampler backward is compared on the forward's x, y: one flipped corner would
     show as an O(1) error), and grad_T -- computed as the adjoint of the node interpolation -- must equal the oracle's
     sum_pix grad * basis within rel 1e-4, element-wise too; the chain to the offsets through W^-T likewise."""
     from coupe.dvsg_b200 import _lib, ops
-    b, h, w, m, amp = shape
-    assert _lib.load().dvsg_tps_coords_mode(h, w, 3, h, w, m * m, 0) == 1
+    b, h, w, m, amp = shape[:5]
+    oh, ow = shape[5:] if len(shape) > 5 else (h, w)      # output size != input size, ragged against the 32 x 8 tiles
+    assert _lib.load().dvsg_tps_coords_mode(h, w, 3, oh, ow, m * m, 0) == 1
     rng = np.random.default_rng(h + m)
     u = smooth_image(rng, b, h, w, 3, period=48.0)
     coord = tiled_mesh(m, m, b)
     vec = rng.uniform(-amp, amp, coord.shape).astype(np.float32)
-    g_out = rng.standard_normal((b, h, w, 3)).astype(np.float32)
-    gx_in = rng.standard_normal(b * h * w).astype(np.float32)
-    gy_in = rng.standard_normal(b * h * w).astype(np.float32)
+    g_out = rng.standard_normal((b, oh, ow, 3)).astype(np.float32)
+    gx_in = rng.standard_normal(b * oh * ow).astype(np.float32)
+    gy_in = rng.standard_normal(b * oh * ow).astype(np.float32)
     U, C_ = cu(u), cu(coord)
     T = ops.tps_solve(C_, C_ + cu(vec))
-    _, x, y, _ = ops.tps_warp_fwd(U, C_, T, (h, w))
-    gU, gT, gxs, gys = ops.tps_warp_bwd(U, C_, T, (h, w), cu(g_out), cu(gx_in), cu(gy_in), want_grid_grad=True)
+    _, x, y, _ = ops.tps_warp_fwd(U, C_, T, (oh, ow))
+    gU, gT, gxs, gys = ops.tps_warp_bwd(U, C_, T, (oh, ow), cu(g_out), cu(gx_in), cu(gy_in), want_grid_grad=True)
     gvec = ops.tps_solve_bwd(C_, gT)
     x, y = x.cpu().numpy(), y.cpu().numpy()
-    r_gim, r_gx, r_gy = O.tps_interpolate_bwd(u, x, y, h, w, g_out)
+    r_gim, r_gx, r_gy = O.tps_interpolate_bwd(u, x, y, oh, ow, g_out)
     r_gx, r_gy = r_gx.reshape(-1) + gx_in, r_gy.reshape(-1) + gy_in
     assert rel(gU.cpu().numpy(), r_gim) <= 1e-4
     assert rel(gxs.cpu().numpy(), r_gx) <= 1e-4 and rel(gys.cpu().numpy(), r_gy) <= 1e-4
-    r_gT = O.tps_grid_bwd(coord.astype(np.float64), h, w, gxs.cpu().numpy(), gys.cpu().numpy(), dtype=np.float64)
+    r_gT = O.tps_grid_bwd(coord.astype(np.float64), oh, ow, gxs.cpu().numpy(), gys.cpu().numpy(), dtype=np.float64)
     print('%s: node-mode grad_T rel %.2e' % (shape, rel(gT.cpu().numpy(), r_gT)))
     assert rel(gT.cpu().numpy(), r_gT) <= 1e-4
     ok, worst, at = close_elementwise(gT.cpu().numpy(), r_gT, rtol=1e-4, atol_frac=1e-5)
@@ -430,9 +432,9 @@ def test_tps_backward_in_node_mode_vs_oracle(shape):
     assert rel(gvec.cpu().numpy(), O.tps_solve_bwd(w_inv, gT.cpu().numpy().astype(np.float64))) <= 1e-4
     # the per-pixel evaluation (DVSG_FLAG_TPS_EXACT in both calls) passes the same stage-wise checks on ITS coordinates; the two
     # grad_T differ by the slope jumps of the few pixels whose sampling corner differs (white-noise grad_out: ~1 % here)
-    _, xe, ye, _ = ops.tps_warp_fwd(U, C_, T, (h, w), flags=2)
-    _, gTe, gxe, gye = ops.tps_warp_bwd(U, C_, T, (h, w), cu(g_out), cu(gx_in), cu(gy_in), want_grid_grad=True, flags=2)
-    _, e_gx, e_gy = O.tps_interpolate_bwd(u, xe.cpu().numpy(), ye.cpu().numpy(), h, w, g_out)
+    _, xe, ye, _ = ops.tps_warp_fwd(U, C_, T, (oh, ow), flags=2)
+    _, gTe, gxe, gye = ops.tps_warp_bwd(U, C_, T, (oh, ow), cu(g_out), cu(gx_in), cu(gy_in), want_grid_grad=True, flags=2)
+    _, e_gx, e_gy = O.tps_interpolate_bwd(u, xe.cpu().numpy(), ye.cpu().numpy(), oh, ow, g_out)
     assert rel(gxe.cpu().numpy(), e_gx.reshape(-1) + gx_in) <= 1e-4 and rel(gye.cpu().numpy(), e_gy.reshape(-1) + gy_in) <= 1e-4
     print('   node vs per-pixel evaluation: grad_T differs by %.2e (corner flips)' % rel(gT.cpu().numpy(), gTe.cpu().numpy()))
 
