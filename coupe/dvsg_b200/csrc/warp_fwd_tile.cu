@@ -188,6 +188,57 @@ __device__ __forceinline__ void gather_pair(const float2 xp, const float2 yp, co
     }
 }
 
+// ---- TPS tiles whose footprint fits no staging box: one pixel PAIR per call, straight from global memory ---------------
+// The arithmetic of gather_pair<CLAMP = true> (corners clamped first, weights from the clamped corners, add_n order; packed
+// fp32x2) with global corner addresses: half the instructions per pixel of general_pixel, identical bits.  Coordinates must
+// be "sane" (|x| < 2^22, the footprint code checks it); anything else goes through general_pixel, which also reproduces the
+// int32 wrap of the reference's cast.
+template <bool MASK>
+__device__ __noinline__ void general_pair_tps(const float2 xp, const float2 yp, const int W, const float wm1, const float hm1,
+                                              const float* __restrict__ srcb, float* __restrict__ opair, float* __restrict__ mask0,
+                                              float* __restrict__ mask1, const float2 one) {
+    const float2 one2 = f2dup(1.0f);
+    const float2 fx = floor2_any(xp), fy = floor2_any(yp);
+    const float2 gx = __fadd2_rn(fx, one2), gy = __fadd2_rn(fy, one2);
+    const float2 x0f = f2(fminf(fmaxf(fx.x, 0.0f), wm1), fminf(fmaxf(fx.y, 0.0f), wm1));
+    const float2 x1f = f2(fminf(fmaxf(gx.x, 0.0f), wm1), fminf(fmaxf(gx.y, 0.0f), wm1));
+    const float2 y0f = f2(fminf(fmaxf(fy.x, 0.0f), hm1), fminf(fmaxf(fy.y, 0.0f), hm1));
+    const float2 y1f = f2(fminf(fmaxf(gy.x, 0.0f), hm1), fminf(fmaxf(gy.y, 0.0f), hm1));
+    const float2 ax1 = sub2(x1f, xp), ax0 = sub2(xp, x0f), ay1 = sub2(y1f, yp), ay0 = sub2(yp, y0f);
+    const float2 w00 = __fmul2_rn(ax1, ay1), w01 = __fmul2_rn(ax0, ay1), w10 = __fmul2_rn(ax1, ay0), w11 = __fmul2_rn(ax0, ay0);
+    if (MASK) {
+        const float2 ms = add2x(add2x(add2x(w00, w10, one), w01, one), w11, one);   // A4 add_n order
+        if (mask0) *mask0 = ms.x;
+        if (mask1) *mask1 = ms.y;
+    }
+    // exact small integers: the float -> int conversion is a bit trick (no F2I on the XU pipe)
+    const float2 m23 = f2dup(MAGIC23);
+    const float2 bx0 = __fadd2_rn(x0f, m23), bx1 = __fadd2_rn(x1f, m23), by0 = __fadd2_rn(y0f, m23), by1 = __fadd2_rn(y1f, m23);
+    const int xa0 = __float_as_int(bx0.x) & 0x7fffff, xa1 = __float_as_int(bx1.x) & 0x7fffff, ya0 = __float_as_int(by0.x) & 0x7fffff,
+              ya1 = __float_as_int(by1.x) & 0x7fffff;
+    const int xb0 = __float_as_int(bx0.y) & 0x7fffff, xb1 = __float_as_int(bx1.y) & 0x7fffff, yb0 = __float_as_int(by0.y) & 0x7fffff,
+              yb1 = __float_as_int(by1.y) & 0x7fffff;
+    const float* __restrict__ ra0 = srcb + (size_t)ya0 * W * 3;
+    const float* __restrict__ ra1 = srcb + (size_t)ya1 * W * 3;
+    const float* __restrict__ rb0 = srcb + (size_t)yb0 * W * 3;
+    const float* __restrict__ rb1 = srcb + (size_t)yb1 * W * 3;
+    const float *p00a = ra0 + xa0 * 3, *p01a = ra0 + xa1 * 3, *p10a = ra1 + xa0 * 3, *p11a = ra1 + xa1 * 3;
+    const float *p00b = rb0 + xb0 * 3, *p01b = rb0 + xb1 * 3, *p10b = rb1 + xb0 * 3, *p11b = rb1 + xb1 * 3;
+    float2 i00[3], i01[3], i10[3], i11[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        i00[ch] = f2(__ldg(p00a + ch), __ldg(p00b + ch)); i01[ch] = f2(__ldg(p01a + ch), __ldg(p01b + ch));
+        i10[ch] = f2(__ldg(p10a + ch), __ldg(p10b + ch)); i11[ch] = f2(__ldg(p11a + ch), __ldg(p11b + ch));
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float2 t00 = __fmul2_rn(w00, i00[ch]), t01 = __fmul2_rn(w01, i01[ch]), t10 = __fmul2_rn(w10, i10[ch]), t11 = __fmul2_rn(w11, i11[ch]);
+        const float2 o = add2x(add2x(add2x(t00, t10, one), t01, one), t11, one);   // ThinPlateSpline.py:89
+        opair[ch] = o.x;
+        opair[TC * 3 + ch] = o.y;
+    }
+}
+
 // gather + blend of the thread's 8 pixels from the staged footprint (one variant per tile, warp-uniform)
 template <int MODE, bool CLAMP, bool MASK>
 __device__ __forceinline__ void gather_tile(const float2 (&XC)[TR / 2], const float2 (&YC)[TR / 2], const int pitch,
@@ -277,7 +328,7 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
 
     struct Tile {               // warp-uniform description of a tile whose coordinates are known
         int col0, col;
-        bool col_ok, staged, interior;
+        bool col_ok, staged, interior, sane;
         int pitch;
         const unsigned char* sb;
     };
@@ -402,6 +453,7 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
         T.pitch = (wide ? p.bw[2] : p.bw[0]) * 4;
         // p.bh[] are 0 for frames whose byte offsets would not fit the packed gather's exact fp32 integers (< 2^22)
         T.staged = all_sane && fw <= p.bw[2] && nrows <= box_rows;
+        T.sane = all_sane;
         // sb = staging address of frame pixel (0,0) minus the bit pattern of 2^23 (see gather_pair); padded-frame modes
         // index pixel idx-1: fold the -1 into it
         T.sb = w_stage - (fy_lo * T.pitch + fx0 * 4) - (MODE == TMODE_TPS ? 0 : T.pitch + 12) - 0x4B000000ll;
@@ -454,6 +506,12 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
                     gather_tile<MODE, false, MASK>(XC, YC, cur.pitch, cur.sb, ot, wm1, hm1, onex, mask_col, ow, rows_ok);
                 else
                     gather_tile<MODE, true, MASK>(XC, YC, cur.pitch, cur.sb, ot, wm1, hm1, onex, mask_col, ow, rows_ok);
+            } else if (MODE == TMODE_TPS && cur.sane && !(p.dbg & 8)) {
+                // TPS tile that fits no box (a stretched or sheared neighbourhood): pixel pairs from global memory
+#pragma unroll
+                for (int j = 0; j < TR / 2; ++j)
+                    general_pair_tps<MASK>(XC[j], YC[j], W, wm1, hm1, srcb, ot + 2 * j * TC * 3, (MASK && mask_col && 2 * j < rows_ok) ? mask_col + 2 * j * ow : nullptr,
+                                           (MASK && mask_col && 2 * j + 1 < rows_ok) ? mask_col + (2 * j + 1) * ow : nullptr, onex);
             } else {
                 // wide corner loads pay for a rough flow field (white-noise +-8 px flow: 60 -> 74 Gpix/s); the neighbouring
                 // lanes of a smooth map already share sectors, where the selects only cost (+-0.3 TPS: 137 -> 128 Gpix/s)

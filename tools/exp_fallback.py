@@ -12,7 +12,7 @@ def ab(name, fn, px, bpp, check=None):
     for dbg in (8, 0):
         lib.dvsg_set_tile_tuning(dbg, -1, -1)
         ms = timeit(fn)
-        rec('%s [%s]' % (name, 'per-pixel' if dbg else 'cp.async'), ms, px, bpp)
+        rec('%s [%s]' % (name, 'per-pixel' if dbg else 'pair path'), ms, px, bpp)
         outs.append(check().clone() if check else None)
     lib.dvsg_set_tile_tuning(0, -1, -1)
     if check:
