@@ -135,7 +135,7 @@ def test_masked_mse_vs_reference_golden():
     g = load_golden('loss_masked_mse')
     P, G, M = (cu(g[k]).requires_grad_(True) for k in ('pred', 'gt', 'mask'))
     loss = losses.masked_MSE(P, G, M)
-    assert abs(float(loss) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    assert abs(float(loss.detach()) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
     (loss * float(g['grad_scale'])).backward()
     assert _close(P.grad.cpu().numpy(), g['grad_pred'])
     assert _close(G.grad.cpu().numpy(), g['grad_gt'])
@@ -151,7 +151,7 @@ def test_temporal_loss_vs_reference_golden():
     h, w = g['pred'].shape[1:3]
     P, MP = cu(g['pred']).requires_grad_(True), cu(g['mask_pred']).requires_grad_(True)
     loss = losses.temporal_loss(P, cu(g['gt']), MP, cu(g['mask_gt']), cu(g['flow']), h, w)
-    assert abs(float(loss) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    assert abs(float(loss.detach()) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
     loss.backward()
     assert _close(P.grad.cpu().numpy(), g['grad_pred'], atol_frac=1e-5)
     assert _close(MP.grad.cpu().numpy(), g['grad_mask_pred'], atol_frac=1e-5)
@@ -167,7 +167,7 @@ def test_surf_loss_vs_reference_golden():
     b = g['surf'].shape[0]
     X, Y = cu(g['x']).requires_grad_(True), cu(g['y']).requires_grad_(True)
     loss = losses.get_surf_loss(cu(g['surf']), X, Y, cu(g['max_dim']), b, w, h)
-    assert abs(float(loss) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    assert abs(float(loss.detach()) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
     loss.backward()
     assert _close(X.grad.cpu().numpy(), g['grad_x'])
     assert _close(Y.grad.cpu().numpy(), g['grad_y'])
