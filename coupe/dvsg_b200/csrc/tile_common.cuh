@@ -292,10 +292,11 @@ struct NodeTables {             // per CTA, in dynamic shared memory (all offset
                                 // [1] 1 when the frame's mesh is separable (G x G, control point k = (gx[k % G], gy[k / G]))
     int* near_idx;              // [NODE_MAX_NEAR] their indices, ascending
     float* near_col;            // [NODE_MAX_NEAR] their column position in output pixels
+    float2* cf;                 // [pn4] (cx ln2, cy ln2) alone: the separable node pass reads two control points per 16-byte load
 };
 constexpr int TKS = 16;         // largest separable mesh side with a specialised node pass
 __host__ __device__ inline size_t node_tables_bytes(int pn) {
-    return (size_t)((pn + 3) & ~3) * 16 + 2 * TKS * 4 + 16 + NODE_MAX_NEAR * 8;
+    return (size_t)((pn + 3) & ~3) * 16 + 2 * TKS * 4 + 16 + NODE_MAX_NEAR * 8 + (size_t)((pn + 3) & ~3) * 8;
 }
 __device__ __forceinline__ NodeTables node_tables_at(unsigned char* base, int pn) {
     NodeTables t;
@@ -305,6 +306,7 @@ __device__ __forceinline__ NodeTables node_tables_at(unsigned char* base, int pn
     t.near_cnt = reinterpret_cast<int*>(base + (size_t)pn4 * 16 + 2 * TKS * 4);
     t.near_idx = t.near_cnt + 4;
     t.near_col = reinterpret_cast<float*>(t.near_idx + NODE_MAX_NEAR);
+    t.cf = reinterpret_cast<float2*>(t.near_col + NODE_MAX_NEAR);
     return t;
 }
 // Tables of one strip (rows row0 .. row0+TR-1).  Called by the whole CTA (>= 2 warps) before its barrier; contains one CTA
@@ -333,6 +335,7 @@ __device__ __forceinline__ void tile_node_tables(const float* __restrict__ Tb, c
         const bool real = k < pn;
         nt.cp[k] = real ? make_float4(__ldg(cb + 2 * k), __ldg(cb + 2 * k + 1), Tb[3 + k] * TLN2, Tb[N + 3 + k] * TLN2)
                         : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (G > 0) nt.cf[k] = real ? make_float2(Tb[3 + k] * TLN2, Tb[N + 3 + k] * TLN2) : make_float2(0.0f, 0.0f);
     }
     if (warp == nthreads / 32 - 1) {
         // row-near control points, in index order (ballot compaction: the order fixes the summation order of the near field)
@@ -430,16 +433,37 @@ __device__ __forceinline__ void tile_node_coords(const NodeTables& nt, const int
             float dx2[GG];
 #pragma unroll
             for (int g = 0; g < GG; ++g) { const float d = xn - nt.gxy[g]; dx2[g] = d * d; }
+            const float4* __restrict__ cf4 = reinterpret_cast<const float4*>(nt.cf);      // the coefficients of two control points per load
+            if (GG % 2 == 0) {
 #pragma unroll 1
-            for (int gy = 0; gy < GG; ++gy) {
-                const float d = yn - nt.gxy[TKS + gy];
-                const float dy2 = fmaf(d, d, TPS_TINY);
+                for (int gy = 0; gy < GG; ++gy) {
+                    const float d = yn - nt.gxy[TKS + gy];
+                    const float dy2 = fmaf(d, d, TPS_TINY);
 #pragma unroll
-                for (int g = 0; g < GG; ++g) {
-                    const float2 c = *reinterpret_cast<const float2*>(&cp[gy * GG + g].z);
-                    const float d2 = dx2[g] + dy2;
-                    const float r = d2 * lg2_approx(d2);
-                    fn = __ffma2_rn(c, f2dup(r), fn);      // (x, y) in one packed FMA, r as a broadcast operand
+                    for (int g = 0; g < GG; g += 2) {
+                        const float4 c = cf4[(gy * GG + g) >> 1];
+                        const float d2a = dx2[g] + dy2, d2b = dx2[g + 1] + dy2;
+                        const float ra = d2a * lg2_approx(d2a), rb = d2b * lg2_approx(d2b);
+                        fn = __ffma2_rn(f2(c.x, c.y), f2dup(ra), fn);      // (x, y) in one packed FMA, r as a broadcast operand
+                        fn = __ffma2_rn(f2(c.z, c.w), f2dup(rb), fn);
+                    }
+                }
+            } else {      // odd side (5 x 5): pairs straddle the mesh rows, everything unrolled; same summation order (k ascending)
+                float dy2[GG];
+#pragma unroll
+                for (int gy = 0; gy < GG; ++gy) { const float d = yn - nt.gxy[TKS + gy]; dy2[gy] = fmaf(d, d, TPS_TINY); }
+#pragma unroll
+                for (int k = 0; k + 1 < GG * GG; k += 2) {
+                    const float4 c = cf4[k >> 1];
+                    const float d2a = dx2[k % GG] + dy2[k / GG], d2b = dx2[(k + 1) % GG] + dy2[(k + 1) / GG];
+                    const float ra = d2a * lg2_approx(d2a), rb = d2b * lg2_approx(d2b);
+                    fn = __ffma2_rn(f2(c.x, c.y), f2dup(ra), fn);
+                    fn = __ffma2_rn(f2(c.z, c.w), f2dup(rb), fn);
+                }
+                {
+                    const float2 c = nt.cf[GG * GG - 1];
+                    const float d2 = dx2[GG - 1] + dy2[GG - 1];
+                    fn = __ffma2_rn(c, f2dup(d2 * lg2_approx(d2)), fn);
                 }
             }
         } else {
