@@ -293,10 +293,24 @@ struct NodeTables {             // per CTA, in dynamic shared memory (all offset
     int* near_idx;              // [NODE_MAX_NEAR] their indices, ascending
     float* near_col;            // [NODE_MAX_NEAR] their column position in output pixels
     float2* cf;                 // [pn4] (cx ln2, cy ln2) alone: the separable node pass reads two control points per 16-byte load
+    // two-level evaluation (16 x 16 meshes, near_cnt[2] > 0): the CTA's segment is SNODE_PER_CTA super-tiles of SNODE_TILES tiles
+    float2* f2;                 // [SNODE_PER_CTA][NNY][SNODE_F2_LD] far-far field at the super-nodes (row pitch 17: conflict-free across the y nodes)
+    int* sn_cnt;                // [SNODE_PER_CTA] super-near control points of each super-tile
+    int* sn_idx;                // [SNODE_PER_CTA][SNODE_MAX] control points inside the grown super-tile box ("super-near"), ascending
+    float* sn_col;              // [SNODE_PER_CTA][SNODE_MAX] their column position in output pixels
+    int* sn_rn;                 // [SNODE_PER_CTA][SNODE_MAX] 1 = also row-near (may be tile-near: then the per-pixel term carries it)
 };
+// Super-near box: the super-tile's 512 x 8 pixels grown by these margins.  The x nodes of a super-tile are ~32 px apart, so a
+// control point straight above or below it must be further away than that to look smooth along x (tools/proto_nodes2.py:
+// 2e-4 with the tile's own 24-pixel row margin, 6e-9 with 160).
+constexpr float SNODE_NEAR_X = 128.0f, SNODE_NEAR_Y = 160.0f;
+// One super-tile per CTA made the CTAs too short (16 tiles behind a serial prologue that keeps 80 of 128 threads busy: 32 %
+// fewer instructions, the same time); four amortise the prologue like the 60-tile segments did and fill its thread rounds.
+constexpr int SNODE_MAX = 32, SNODE_F2_LD = SNODE_NX + 1, SNODE_PER_CTA = 4;
 constexpr int TKS = 16;         // largest separable mesh side with a specialised node pass
 __host__ __device__ inline size_t node_tables_bytes(int pn) {
-    return (size_t)((pn + 3) & ~3) * 16 + 2 * TKS * 4 + 16 + NODE_MAX_NEAR * 8 + (size_t)((pn + 3) & ~3) * 8;
+    return (size_t)((pn + 3) & ~3) * 16 + 2 * TKS * 4 + 16 + NODE_MAX_NEAR * 8 + (size_t)((pn + 3) & ~3) * 8 +
+           (pn == TKS * TKS ? (((size_t)SNODE_PER_CTA * (NNY * SNODE_F2_LD * 8 + SNODE_MAX * 12 + 4) + 15) & ~(size_t)15) : 0);      // what follows is read 16 bytes at a time
 }
 __device__ __forceinline__ NodeTables node_tables_at(unsigned char* base, int pn) {
     NodeTables t;
@@ -307,13 +321,77 @@ __device__ __forceinline__ NodeTables node_tables_at(unsigned char* base, int pn
     t.near_idx = t.near_cnt + 4;
     t.near_col = reinterpret_cast<float*>(t.near_idx + NODE_MAX_NEAR);
     t.cf = reinterpret_cast<float2*>(t.near_col + NODE_MAX_NEAR);
+    t.f2 = t.cf + pn4;
+    t.sn_cnt = reinterpret_cast<int*>(t.f2 + SNODE_PER_CTA * NNY * SNODE_F2_LD);
+    t.sn_idx = t.sn_cnt + SNODE_PER_CTA;
+    t.sn_col = reinterpret_cast<float*>(t.sn_idx + SNODE_PER_CTA * SNODE_MAX);
+    t.sn_rn = reinterpret_cast<int*>(t.sn_col + SNODE_PER_CTA * SNODE_MAX);
     return t;
 }
+// far-field value of one control point at this lane's node (the same expression is added for every control point and
+// subtracted again for the tile's near ones, so the two cancel to the last bit of the running sum's rounding)
+__device__ __forceinline__ void node_far_term(const float4 cp, const float xn, const float yn, const float sign, float2& f) {
+    const float dx = xn - cp.x, dy = yn - cp.y;
+    const float d2 = fmaf(dx, dx, fmaf(dy, dy, TPS_TINY));
+    const float r = d2 * lg2_approx(d2) * sign;
+    f = __ffma2_rn(make_float2(cp.z, cp.w), f2dup(r), f);      // (x, y) of the node in one packed FMA, r as a broadcast operand
+}
+// sum over ALL control points of a separable G x G mesh at one node: (x_n - gx)^2 once per mesh column, (y_n - gy)^2 once per
+// mesh row, the coefficients of two control points per 16-byte load; k ascending
+template <int GG>
+__device__ __forceinline__ float2 node_sep_sum(const NodeTables& nt, const float xn, const float yn) {
+    float2 fn = f2dup(0.0f);
+    float dx2[GG];
+#pragma unroll
+    for (int g = 0; g < GG; ++g) { const float d = xn - nt.gxy[g]; dx2[g] = d * d; }
+    const float4* __restrict__ cf4 = reinterpret_cast<const float4*>(nt.cf);
+    if (GG % 2 == 0) {
+#pragma unroll 1
+        for (int gy = 0; gy < GG; ++gy) {
+            const float d = yn - nt.gxy[TKS + gy];
+            const float dy2 = fmaf(d, d, TPS_TINY);
+#pragma unroll
+            for (int g = 0; g < GG; g += 2) {
+                const float4 c = cf4[(gy * GG + g) >> 1];
+                const float d2a = dx2[g] + dy2, d2b = dx2[g + 1] + dy2;
+                const float ra = d2a * lg2_approx(d2a), rb = d2b * lg2_approx(d2b);
+                fn = __ffma2_rn(f2(c.x, c.y), f2dup(ra), fn);      // (x, y) in one packed FMA, r as a broadcast operand
+                fn = __ffma2_rn(f2(c.z, c.w), f2dup(rb), fn);
+            }
+        }
+    } else {      // odd side (5 x 5): pairs straddle the mesh rows, everything unrolled; same summation order (k ascending)
+        float dy2[GG];
+#pragma unroll
+        for (int gy = 0; gy < GG; ++gy) { const float d = yn - nt.gxy[TKS + gy]; dy2[gy] = fmaf(d, d, TPS_TINY); }
+#pragma unroll
+        for (int k = 0; k + 1 < GG * GG; k += 2) {
+            const float4 c = cf4[k >> 1];
+            const float d2a = dx2[k % GG] + dy2[k / GG], d2b = dx2[(k + 1) % GG] + dy2[(k + 1) / GG];
+            const float ra = d2a * lg2_approx(d2a), rb = d2b * lg2_approx(d2b);
+            fn = __ffma2_rn(f2(c.x, c.y), f2dup(ra), fn);
+            fn = __ffma2_rn(f2(c.z, c.w), f2dup(rb), fn);
+        }
+        {
+            const float2 c = nt.cf[GG * GG - 1];
+            const float d2 = dx2[GG - 1] + dy2[GG - 1];
+            fn = __ffma2_rn(c, f2dup(d2 * lg2_approx(d2)), fn);
+        }
+    }
+    return fn;
+}
+// the 16 x 16 sum is 256 terms long and needed at two places of the kernels (super-nodes in the prologue, tile nodes when the
+// two-level evaluation is off): one out-of-line copy, the instruction cache is the scarcer resource there
+static __device__ __noinline__ float2 node_sep_sum16(const NodeTables nt, const float xn, const float yn) { return node_sep_sum<TKS>(nt, xn, yn); }
+
 // Tables of one strip (rows row0 .. row0+TR-1).  Called by the whole CTA (>= 2 warps) before its barrier; contains one CTA
 // barrier of its own when G > 0 (separability test).
+// seg_col0 / two_level: first pixel column of the CTA's segment, and whether that segment is SNODE_PER_CTA whole super-tiles
+// (the launcher's doing, for 16 x 16 meshes) -- then their far-far fields are tabulated here (second barrier; the caller's
+// barrier publishes them).
 template <int G>
 __device__ __forceinline__ void tile_node_tables(const float* __restrict__ Tb, const float* __restrict__ cb, int pn, int row0, int oh,
-                                                 float step_x, float step_y, int tid, int nthreads, float* s_lin, const NodeTables& nt) {
+                                                 float step_x, float step_y, int tid, int nthreads, float* s_lin, const NodeTables& nt,
+                                                 const int seg_col0 = 0, const bool two_level = false) {
     const int N = pn + 3, pn4 = (pn + 3) & ~3, lane = tid & 31, warp = tid >> 5;
     if (G > 0) {
         constexpr int GS = G > 0 ? G : 1;
@@ -358,6 +436,51 @@ __device__ __forceinline__ void tile_node_tables(const float* __restrict__ Tb, c
         }
         if (lane == 0) nt.near_cnt[0] = cnt <= NODE_MAX_NEAR ? cnt : -1;
     }
+    if (G == TKS) {
+        // super-near control points of each super-tile of the segment, in index order (warp w builds the list of super-tile w)
+        for (int st = warp; st < SNODE_PER_CTA; st += nthreads / 32) {
+            const float inv_sy = step_y > 0.0f ? 1.0f / step_y : 0.0f, inv_sx = step_x > 0.0f ? 1.0f / step_x : 0.0f;
+            const float rlo = (float)row0 - SNODE_NEAR_Y, rhi = (float)(row0 + TR - 1) + SNODE_NEAR_Y;
+            const float nlo = (float)row0 - NODE_NEAR_Y, nhi = (float)(row0 + TR - 1) + NODE_NEAR_Y;
+            const int c0 = seg_col0 + st * SNODE_TILES * TC;
+            const float clo = (float)c0 - SNODE_NEAR_X, chi = (float)(c0 + SNODE_TILES * TC - 1) + SNODE_NEAR_X;
+            int cnt = 0;
+            for (int base = 0; base < pn; base += 32) {
+                const int k = base + lane;
+                bool f = false, rn = false;
+                float ccol = 0.0f;
+                if (k < pn) {
+                    const float crow = (__ldg(cb + 2 * k + 1) + 1.0f) * inv_sy;
+                    ccol = (__ldg(cb + 2 * k) + 1.0f) * inv_sx;
+                    f = crow > rlo && crow < rhi && ccol > clo && ccol < chi;
+                    rn = crow > nlo && crow < nhi;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                if (f && pos < SNODE_MAX) {
+                    nt.sn_idx[st * SNODE_MAX + pos] = k; nt.sn_col[st * SNODE_MAX + pos] = ccol; nt.sn_rn[st * SNODE_MAX + pos] = rn ? 1 : 0;
+                }
+                cnt += __popc(m);
+            }
+            if (lane == 0) nt.sn_cnt[st] = cnt;
+        }
+        __syncthreads();      // records, coefficient pairs, mesh lines, separability flag and the super-near lists are complete
+        bool ok2 = two_level && nt.near_cnt[1] != 0;
+#pragma unroll
+        for (int st = 0; st < SNODE_PER_CTA; ++st) ok2 = ok2 && nt.sn_cnt[st] <= SNODE_MAX;
+        if (ok2) {
+            for (int i = tid; i < SNODE_PER_CTA * NNY * SNODE_NX; i += nthreads) {
+                const int st = i / (NNY * SNODE_NX), r = i % (NNY * SNODE_NX), sx = r % SNODE_NX, b = r / SNODE_NX;
+                const float xn = fmaf(step_x, (float)(seg_col0 + st * SNODE_TILES * TC) + SNODE_XOFF[sx], -1.0f);
+                const float yn = fmaf(step_y, (float)row0 + NODE_YOFF[b], -1.0f);
+                float2 f = node_sep_sum16(nt, xn, yn);      // all control points, then the super-near ones taken out again
+                const int n_sn = nt.sn_cnt[st];
+                for (int j = 0; j < n_sn; ++j) node_far_term(nt.cp[nt.sn_idx[st * SNODE_MAX + j]], xn, yn, -1.0f, f);
+                nt.f2[(st * NNY + b) * SNODE_F2_LD + sx] = f;
+            }
+        }
+        if (tid == 0) nt.near_cnt[2] = ok2 ? 1 : 0;
+    }
 }
 // exact contribution of control point cp to the lane's 8 pixels: c * d2 * log(d2 + 1e-6) as the reference writes it
 // (ThinPlateSpline.py:104-105), minus the 1e-6 * c that the affine constant already carries for every control point
@@ -374,14 +497,6 @@ __device__ __forceinline__ void node_near_term(const float4 cp, const float xt, 
         X[j] = __ffma2_rn(cfx, r, X[j]);
         Y[j] = __ffma2_rn(cfy, r, Y[j]);
     }
-}
-// far-field value of one control point at this lane's node (the same expression is added for every control point and
-// subtracted again for the tile's near ones, so the two cancel to the last bit of the running sum's rounding)
-__device__ __forceinline__ void node_far_term(const float4 cp, const float xn, const float yn, const float sign, float2& f) {
-    const float dx = xn - cp.x, dy = yn - cp.y;
-    const float d2 = fmaf(dx, dx, fmaf(dy, dy, TPS_TINY));
-    const float r = d2 * lg2_approx(d2) * sign;
-    f = __ffma2_rn(make_float2(cp.z, cp.w), f2dup(r), f);      // (x, y) of the node in one packed FMA, r as a broadcast operand
 }
 // Lagrange weights of this lane's column (li = local column; lanes past the frame edge take the edge pixel's)
 __device__ __forceinline__ void node_load_lx(const int li, float (&lx)[NNX]) {
@@ -427,52 +542,39 @@ __device__ __forceinline__ void tile_node_coords(const NodeTables& nt, const int
     {
         const float xn = fmaf(step_x, (float)col0 + xoff_l, -1.0f);
         const float4* __restrict__ cp = nt.cp;
-        if (G > 0 && nt.near_cnt[1]) {
-            // separable mesh: (x_n - gx)^2 once per mesh column, (y_n - gy)^2 once per mesh row, 5 instructions per control point
-            constexpr int GG = G > 0 ? G : 1;
-            float dx2[GG];
+        if (G == TKS && nt.near_cnt[2] > 0) {
+            // two-level (16 x 16 mesh): the far-far field from the super-nodes of this tile's super-tile, interpolated in x (the
+            // y nodes are the strip's own), plus the super-near control points that are not tile-near, at the node
+            const int tix = col0 / TC, tl = tix % SNODE_TILES, st = (tix / SNODE_TILES) % SNODE_PER_CTA, nl = min(lane, NNX * NNY - 1);
+            const float4* __restrict__ w4 = reinterpret_cast<const float4*>(&SNODE_W[tl][nl % NNX][0]);
+            const float2* __restrict__ fr = nt.f2 + (st * NNY + nl / NNX) * SNODE_F2_LD;
 #pragma unroll
-            for (int g = 0; g < GG; ++g) { const float d = xn - nt.gxy[g]; dx2[g] = d * d; }
-            const float4* __restrict__ cf4 = reinterpret_cast<const float4*>(nt.cf);      // the coefficients of two control points per load
-            if (GG % 2 == 0) {
-#pragma unroll 1
-                for (int gy = 0; gy < GG; ++gy) {
-                    const float d = yn - nt.gxy[TKS + gy];
-                    const float dy2 = fmaf(d, d, TPS_TINY);
-#pragma unroll
-                    for (int g = 0; g < GG; g += 2) {
-                        const float4 c = cf4[(gy * GG + g) >> 1];
-                        const float d2a = dx2[g] + dy2, d2b = dx2[g + 1] + dy2;
-                        const float ra = d2a * lg2_approx(d2a), rb = d2b * lg2_approx(d2b);
-                        fn = __ffma2_rn(f2(c.x, c.y), f2dup(ra), fn);      // (x, y) in one packed FMA, r as a broadcast operand
-                        fn = __ffma2_rn(f2(c.z, c.w), f2dup(rb), fn);
-                    }
-                }
-            } else {      // odd side (5 x 5): pairs straddle the mesh rows, everything unrolled; same summation order (k ascending)
-                float dy2[GG];
-#pragma unroll
-                for (int gy = 0; gy < GG; ++gy) { const float d = yn - nt.gxy[TKS + gy]; dy2[gy] = fmaf(d, d, TPS_TINY); }
-#pragma unroll
-                for (int k = 0; k + 1 < GG * GG; k += 2) {
-                    const float4 c = cf4[k >> 1];
-                    const float d2a = dx2[k % GG] + dy2[k / GG], d2b = dx2[(k + 1) % GG] + dy2[(k + 1) / GG];
-                    const float ra = d2a * lg2_approx(d2a), rb = d2b * lg2_approx(d2b);
-                    fn = __ffma2_rn(f2(c.x, c.y), f2dup(ra), fn);
-                    fn = __ffma2_rn(f2(c.z, c.w), f2dup(rb), fn);
-                }
-                {
-                    const float2 c = nt.cf[GG * GG - 1];
-                    const float d2 = dx2[GG - 1] + dy2[GG - 1];
-                    fn = __ffma2_rn(c, f2dup(d2 * lg2_approx(d2)), fn);
-                }
+            for (int q = 0; q < SNODE_NX / 4; ++q) {
+                const float4 w = __ldg(w4 + q);
+                fn = __ffma2_rn(fr[4 * q], f2dup(w.x), fn);
+                fn = __ffma2_rn(fr[4 * q + 1], f2dup(w.y), fn);
+                fn = __ffma2_rn(fr[4 * q + 2], f2dup(w.z), fn);
+                fn = __ffma2_rn(fr[4 * q + 3], f2dup(w.w), fn);
+            }
+            const float lo = (float)col0 - NODE_NEAR_X, hi = (float)(col0 + TC - 1) + NODE_NEAR_X;
+            const int n_sn = nt.sn_cnt[st];
+            for (int i = st * SNODE_MAX; i < st * SNODE_MAX + n_sn; ++i) {
+                const float c = nt.sn_col[i];
+                if (!(nt.sn_rn[i] && c > lo && c < hi)) node_far_term(cp[nt.sn_idx[i]], xn, yn, 1.0f, fn);
             }
         } else {
-            for (int k = 0; k < pn4; k += 4) {
+            if (G > 0 && nt.near_cnt[1]) {
+                constexpr int GG = G > 0 ? G : 1;
+                if (GG == TKS) fn = node_sep_sum16(nt, xn, yn);
+                else fn = node_sep_sum<GG>(nt, xn, yn);
+            } else {
+                for (int k = 0; k < pn4; k += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) node_far_term(cp[k + u], xn, yn, 1.0f, fn);
+                    for (int u = 0; u < 4; ++u) node_far_term(cp[k + u], xn, yn, 1.0f, fn);
+                }
             }
+            for (unsigned m = near; m; m &= m - 1) node_far_term(cp[nt.near_idx[__ffs(m) - 1]], xn, yn, -1.0f, fn);
         }
-        for (unsigned m = near; m; m &= m - 1) node_far_term(cp[nt.near_idx[__ffs(m) - 1]], xn, yn, -1.0f, fn);
     }
     w_nodes[lane] = fn;
     __syncwarp();

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(TNT, BWD_MINB) warp_bwd_tile_kernel(const BwdT
     if (MODE == TMODE_TPS) {
         if (NODES) {
             tile_node_tables<NG>(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, row0, oh, p.step_x, p.step_y, tid, TNT,
-                                 s_lin, nt);
+                                 s_lin, nt, t_begin * TC, p.seg_len == SNODE_PER_CTA * SNODE_TILES);
             for (int i = tid; i < TC * 8; i += TNT) s_lxt[i] = NODE_LX[i >> 3][i & 7];
         } else {
             tile_tps_tables(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, pn8, row0, oh, p.step_y, tid, TNT,
@@ -796,6 +796,8 @@ static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
     // the TPS prologue builds the per-strip tables; the field samplers have none and prefer short CTAs (tf_warp backward,
     // 32 x 288 x 512: 16 / 8 / 4 tiles per CTA 156 / 144 / 138 us; 16 x 720p: 40 / 20 / 4 tiles 220 / 199 / 189 us)
     p.seg_len = tile_pick_seg_len(strips, p.n_tx, 148 * BWD_MINB, MODE == TMODE_TPS ? 0.5 : 0.05, "DVSG_BWD_SEGLEN");
+    // 16 x 16 meshes in node mode: SNODE_PER_CTA super-tiles per CTA, as in the forward kernel -- identical coordinates in both
+    if (MODE == TMODE_TPS && p.nodes && p.pn == TKS * TKS && !getenv("DVSG_TPS_ONE_LEVEL")) p.seg_len = SNODE_PER_CTA * SNODE_TILES;
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "bwd tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
     BwdTileMaps maps;

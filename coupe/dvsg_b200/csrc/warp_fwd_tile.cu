@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TNT, 5) warp_fwd_tile_kernel(const TileParams 
             if (blockIdx.x == 0 && blockIdx.y == 0 && tid < 2 * (p.pn + 3)) p.T_out[(size_t)b * 2 * (p.pn + 3) + tid] = s_T[tid];
             Tb = s_T;
         }
-        if (NODES) tile_node_tables<NG>(Tb, cb, p.pn, row0, oh, p.step_x, p.step_y, tid, TNT, s_lin, nt);
+        if (NODES) tile_node_tables<NG>(Tb, cb, p.pn, row0, oh, p.step_x, p.step_y, tid, TNT, s_lin, nt, t_begin * TC, p.seg_len == SNODE_PER_CTA * SNODE_TILES);
         else if (G > 0) sep = tile_tps_tables_sep<(G > 0 ? G : 1)>(Tb, cb, pn8, row0, oh, p.step_y, tid, TNT, s_lin, tab);
         else tile_tps_tables(Tb, cb, p.pn, pn8, row0, oh, p.step_y, tid, TNT, s_lin, reinterpret_cast<TpsRec*>(tab));
     } else if (MODE == TMODE_HOMOG) {
@@ -582,6 +582,8 @@ static int launch_tile(TileParams p, cudaStream_t st) {
     const long long strips = (long long)p.B * p.n_ty;
     // tiles per CTA (tile_pick_seg_len): the TPS prologue builds the per-strip tables, the field samplers have none
     p.seg_len = tile_pick_seg_len(strips, p.n_tx, 148 * 5, MODE == TMODE_TPS ? 0.75 : 0.2, "DVSG_FWD_SEGLEN");
+    // 16 x 16 meshes in node mode: SNODE_PER_CTA super-tiles per CTA (two-level evaluation, tile_common.cuh); DVSG_TPS_ONE_LEVEL: A/B
+    if (MODE == TMODE_TPS && p.nodes && p.pn == TKS * TKS && !getenv("DVSG_TPS_ONE_LEVEL")) p.seg_len = SNODE_PER_CTA * SNODE_TILES;
     p.segs = (p.n_tx + p.seg_len - 1) / p.seg_len;
     DVSG_REQUIRE(p.B <= 65535 && p.n_ty <= 65535, "tile kernel: batch %d / %d strips exceed the grid limits: split the call", p.B, p.n_ty);
     TileMaps maps;
