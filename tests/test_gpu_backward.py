@@ -569,3 +569,34 @@ def test_tps_coord_gradient_of_a_mesh_shared_by_the_batch():
     # against the oracle
     _, _, want = O.thin_plate_spline_bwd(U.cpu().numpy(), np.tile(mesh[None], (b, 1, 1)), vec, (h, w), g_out.cpu().numpy(), want_coord=True)
     assert rel(C2.grad.cpu().numpy(), want) <= 2e-4
+
+
+def test_two_level_node_evaluation_forward_and_backward_see_the_same_coordinates():
+    """16 x 16 mesh at 1080p: both tile kernels take the two-level node evaluation (tile_common.cuh).  The sampler backward is
+    compared on the FORWARD's x, y (one corner seen differently by the two kernels would show as an O(1) error in grad_xs),
+    and grad_T -- the adjoint of the single-level node interpolation applied to the coordinate gradients -- against the
+    oracle's sum over pixels, accumulated in row bands (the full basis would be 4 GB)."""
+    from coupe.dvsg_b200 import _lib, ops
+    b, h, w, m, amp = 1, 1080, 1920, 16, 0.03
+    assert _lib.load().dvsg_tps_coords_mode(h, w, 3, h, w, m * m, 0) == 1
+    rng = np.random.default_rng(16)
+    u = smooth_image(rng, b, h, w, 3, period=48.0)
+    coord = tiled_mesh(m, m, b)
+    vec = rng.uniform(-amp, amp, coord.shape).astype(np.float32)
+    g_out = rng.standard_normal((b, h, w, 3)).astype(np.float32)
+    U, C_ = cu(u), cu(coord)
+    T = ops.tps_solve(C_, C_ + cu(vec))
+    _, x, y, _ = ops.tps_warp_fwd(U, C_, T, (h, w))
+    gU, gT, gxs, gys = ops.tps_warp_bwd(U, C_, T, (h, w), cu(g_out), want_grid_grad=True)
+    x, y = x.cpu().numpy(), y.cpu().numpy()
+    r_gim, r_gx, r_gy = O.tps_interpolate_bwd(u, x, y, h, w, g_out)
+    assert rel(gxs.cpu().numpy(), r_gx.reshape(-1)) <= 1e-4 and rel(gys.cpu().numpy(), r_gy.reshape(-1)) <= 1e-4
+    assert rel(gU.cpu().numpy(), r_gim) <= 1e-4
+    gx, gy = gxs.cpu().numpy().astype(np.float64).reshape(h, w), gys.cpu().numpy().astype(np.float64).reshape(h, w)
+    r_gT = np.zeros((2, m * m + 3))
+    for r0 in range(0, h, 60):
+        basis = O.tps_basis(coord.astype(np.float64), h, w, dtype=np.float64, rows=(r0, r0 + 60))[0]      # [N, 60 * w]
+        r_gT[0] += basis @ gx[r0:r0 + 60].reshape(-1)
+        r_gT[1] += basis @ gy[r0:r0 + 60].reshape(-1)
+    print('two-level shape: grad_T rel %.2e' % rel(gT.cpu().numpy()[0], r_gT))
+    assert rel(gT.cpu().numpy()[0], r_gT) <= 1e-4
