@@ -301,7 +301,6 @@ __global__ void __launch_bounds__(TNT, BWD_MINB) warp_bwd_tile_kernel(const BwdT
     unsigned char* const node_base = smem + (size_t)TNW * (2 * BSTAGE) + rec_bytes + (size_t)TNW * (2 * pn8 + 16) * sizeof(float);
     const NodeTables nt = node_tables_at(node_base, p.pn);
     float2* const w_nodes = reinterpret_cast<float2*>(node_base + node_tables_bytes(p.pn)) + warp * 32;
-    float* const s_lxt = reinterpret_cast<float*>(node_base + node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2));      // [TC][8]
 
     // ---- prologue -----------------------------------------------------------------------------------
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
@@ -310,7 +309,6 @@ __global__ void __launch_bounds__(TNT, BWD_MINB) warp_bwd_tile_kernel(const BwdT
         if (NODES) {
             tile_node_tables<NG>(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, row0, oh, p.step_x, p.step_y, tid, TNT,
                                  s_lin, nt, t_begin * TC, p.seg_len == SNODE_PER_CTA * SNODE_TILES);
-            for (int i = tid; i < TC * 8; i += TNT) s_lxt[i] = NODE_LX[i >> 3][i & 7];
         } else {
             tile_tps_tables(p.T + (size_t)b * 2 * (p.pn + 3), p.coord + (size_t)b * p.coord_stride, p.pn, pn8, row0, oh, p.step_y, tid, TNT,
                             s_lin, reinterpret_cast<TpsRec*>(smem + (size_t)TNW * (2 * BSTAGE)));
@@ -634,7 +632,9 @@ __global__ void __launch_bounds__(TNT, BWD_MINB) warp_bwd_tile_kernel(const BwdT
                 {
                     const int na = node_l % NNX, nb = node_l / NNX;
                     const float* __restrict__ hp = hbuf + 2 * nb;
-                    const float* __restrict__ lp = s_lxt + na;
+                    // Lagrange weights straight from the (L1-resident, 1 KB) table: a copy in shared memory cost the 5 x 5 mesh
+                    // its fourth CTA per SM
+                    const float* __restrict__ lp = &NODE_LX[0][0] + na;
                     float ax = 0.0f, ay = 0.0f;
 #pragma unroll 8
                     for (int c = 0; c < TC; ++c) {
@@ -812,7 +812,7 @@ static int launch_bwd_tile(BwdTileParams p, cudaStream_t st) {
     const int pn8 = MODE == TMODE_TPS ? (p.pn + 7) & ~7 : 0;
     const bool nodes = MODE == TMODE_TPS && p.nodes;
     const size_t smem = (size_t)TNW * 2 * BSTAGE + (nodes ? 0 : (size_t)pn8 * sizeof(TpsRec)) + (size_t)TNW * (2 * pn8 + 16) * sizeof(float) +
-                        (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) + TC * 8 * sizeof(float) : 0);
+                        (nodes ? node_tables_bytes(p.pn) + (size_t)TNW * 32 * sizeof(float2) : 0);
     auto go = [&](auto k) {
         ensure_dynamic_smem(reinterpret_cast<const void*>(k), (int)smem);
         k<<<dim3((unsigned)p.segs, (unsigned)p.n_ty, (unsigned)p.B), TNT, smem, st>>>(p, maps);

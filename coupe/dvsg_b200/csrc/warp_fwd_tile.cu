@@ -628,13 +628,15 @@ static int launch_tile(TileParams p, cudaStream_t st) {
 // coordinates), the mesh large enough for the node pass to pay (9 instructions per control point and tile + ~130 for the
 // interpolation, against 28 per control point), and a tile small against the frame (the error study covers >= 200 x 400).
 // Measured (sustained, B200): 4x4 mesh 64 x 1080p +11 %, 64 x 720p +9 %, 5x5 at 720p +25 %, 16x16 at 4K 3.8x; at the
-// 288 x 512 training shape (two waves of short CTAs, latency-bound) the small meshes LOSE 10 % -- hence the pixel floor.
+// 288 x 512 training shape (two waves of short CTAs, latency-bound) the 4 x 4 mesh LOSES 5 % (forward 43.3 vs 41.2 us,
+// backward 110 vs 104) -- hence the pixel floor -- while the model's 5 x 5 mesh gains there (forward 45.3 vs 51.3 us, backward
+// 142.5 vs 152.7, once the backward kernel's node mode kept its fourth CTA per SM): the floor applies below 25 points.
 bool tps_nodes_ok(int H, int W, int C, int oh, int ow, int pn, int flags) {
     static const bool env_exact = getenv("DVSG_TPS_EXACT") != nullptr;      // A/B experiments
     static const bool env_force = getenv("DVSG_TPS_NODES_FORCE") != nullptr;      // experiments: no pixel floor
     (void)H;
     return !(flags & DVSG_FLAG_TPS_EXACT) && !env_exact && C == 3 && W % 4 == 0 && ow % 4 == 0 && pn >= 8 && pn <= TKC && ow >= 400 && oh >= 200 &&
-           (env_force || pn >= 64 || (long long)oh * ow >= 500000);
+           (env_force || pn >= 25 || (long long)oh * ow >= 500000);
 }
 
 int tile_tps(const float* U, const float* coord, long long cstride, const float* T, float* out, float* x_out, float* y_out,

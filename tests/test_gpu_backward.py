@@ -395,10 +395,10 @@ def test_shared_mesh_solve_equals_per_frame_solve_bitwise_on_the_5x5_mesh():
         assert float((outs[0] - Tw).abs().max()) <= 2e-7 * float(Tw.abs().max())
 
 
-@pytest.mark.parametrize('shape', [(1, 540, 960, 5, 0.1), (1, 720, 1280, 4, 0.1), (2, 288, 512, 8, 0.04), (2, 300, 500, 4, 0.1, 722, 1284)],
+@pytest.mark.parametrize('shape', [(1, 540, 960, 5, 0.1), (1, 720, 1280, 4, 0.1), (2, 288, 512, 8, 0.04), (2, 300, 500, 4, 0.1, 722, 1284), (3, 288, 512, 5, 0.1)],
                          ids=lambda s: '%dx%dx%d_m%d' % s[:4] + ('_to_%dx%d' % s[5:] if len(s) > 5 else ''))
 def test_tps_backward_in_node_mode_vs_oracle(shape):
-    """Shapes for which the tile kernels evaluate the spline on tile nodes (>= 0.5 Mpix, or >= 64 control points): forward and
+    """Shapes for which the tile kernels evaluate the spline on tile nodes (>= 0.5 Mpix, or >= 25 control points): forward and
     backward must see the SAME coordinates (the sampler backward is compared on the forward's x, y: one flipped corner would
     show as an O(1) error), and grad_T -- computed as the adjoint of the node interpolation -- must equal the oracle's
     sum_pix grad * basis within rel 1e-4, element-wise too; the chain to the offsets through W^-T likewise."""

@@ -711,7 +711,7 @@ def test_tps_forward_vs_oracle_one_full_cfg5_frame():
 # ---- tile-node evaluation of the TPS map (the tile kernels' default) against the per-pixel evaluation and the oracle ----
 NODE_CASES = [
     # H, W, mesh, offset amplitude, jittered mesh
-    (288, 512, 16, 0.02, False), (200, 400, 8, 0.05, True), (540, 960, 4, 0.1, False), (540, 960, 5, 0.3, False),
+    (288, 512, 16, 0.02, False), (200, 400, 8, 0.05, True), (288, 512, 5, 0.1, False), (288, 512, 5, 0.1, True), (540, 960, 4, 0.1, False), (540, 960, 5, 0.3, False),
     (720, 1280, 4, 0.1, False), (720, 1280, 5, 0.3, True), (1080, 1920, 5, 0.1, False), (1080, 1920, 8, 0.05, True),
     (1080, 1920, 16, 0.03, False),      # two-level evaluation (16 x 16 mesh, <= 32 super-near control points per super-tile)
 ]
