@@ -94,3 +94,42 @@ def test_tf_warp_is_bit_exact(shape, c, amp, seed):
         flow = np.round(flow)       # integer shifts: exact copies of source pixels (or zeros from the padding)
     out = tf_warp(cu(im), cu(flow), h, w).cpu().numpy()
     np.testing.assert_array_equal(out, O.tf_warp(im, flow, h, w))
+
+
+# ---- the same property at frame sizes where the tile kernels evaluate the spline on tile nodes ----
+node_sizes = st.tuples(st.integers(200, 420), st.integers(100, 330))      # (oh, ow / 4): ow = 4 * k >= 400, any remainder against the 32 x 8 tiles
+
+
+@settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(size=node_sizes, m=st.sampled_from([4, 5, 6, 8, 16]), amp=st.sampled_from([0.02, 0.1, 0.3]), resize=st.booleans(), jitter=st.booleans(),
+       b=st.integers(1, 2), seed=st.integers(0, 2 ** 16))
+def test_node_evaluation_matches_the_per_pixel_kernel_and_the_oracle(size, m, amp, resize, jitter, b, seed):
+    """Random output sizes with oh not a multiple of 8 and ow not a multiple of 32, input size different from the output, regular
+    and jittered meshes from 4x4 to 16x16: wherever the kernels select the node evaluation its coordinates stay within 3e-6
+    (+ the fp32 noise of the coefficient mass) of the per-pixel kernel's and within the oracle bar, and the sampler is bit-exact
+    on the kernel's own coordinates."""
+    from coupe.dvsg_b200 import _lib, ops
+    oh, ow = size[0], 4 * size[1]
+    rng = np.random.default_rng(seed)
+    h, w = (int(rng.integers(40, 200)), 4 * int(rng.integers(10, 60))) if resize else (oh, ow)
+    amp = amp / max(1.0, m / 5.0)                                     # keep the denser meshes from folding
+    u = smooth_image(rng, b, h, w, 3, period=max(16.0, w / 8.0))
+    coord = tiled_mesh(m, m, b)
+    if jitter:
+        coord = (coord + rng.uniform(-0.25, 0.25, coord.shape) / m).astype(np.float32)
+    vec = rng.uniform(-amp, amp, coord.shape).astype(np.float32)
+    mode = _lib.load().dvsg_tps_coords_mode(h, w, 3, oh, ow, m * m, 0)
+    U, C_ = cu(u), cu(coord)
+    T = ops.tps_solve(C_, C_ + cu(vec))
+    on, xn, yn, _ = ops.tps_warp_fwd(U, C_, T, (oh, ow), want_grid=True)
+    _, xe, ye, _ = ops.tps_warp_fwd(U, C_, T, (oh, ow), want_grid=True, flags=2)
+    torch.cuda.synchronize()
+    on, xn, yn, xe, ye, Tn = (t.cpu().numpy() for t in (on, xn, yn, xe, ye, T))
+    mass = float(np.abs(Tn[:, :, 3:]).sum(axis=2).max())
+    d = max(np.abs(xn - xe).max(), np.abs(yn - ye).max())
+    if mode == 0:
+        assert d == 0.0                                              # per-pixel evaluation either way
+    assert d <= 3e-6 + 1.5e-6 * mass, (mode, d, mass)
+    r_x, r_y = O.tps_grid(Tn, coord, oh, ow)
+    assert max(np.abs(xn - r_x).max(), np.abs(yn - r_y).max()) <= max(2e-5, 1e-5 + 1.5e-6 * mass)
+    np.testing.assert_array_equal(on, O.tps_interpolate(u, xn, yn, oh, ow).reshape(on.shape))
