@@ -133,3 +133,44 @@ def test_node_evaluation_matches_the_per_pixel_kernel_and_the_oracle(size, m, am
     r_x, r_y = O.tps_grid(Tn, coord, oh, ow)
     assert max(np.abs(xn - r_x).max(), np.abs(yn - r_y).max()) <= max(2e-5, 1e-5 + 1.5e-6 * mass)
     np.testing.assert_array_equal(on, O.tps_interpolate(u, xn, yn, oh, ow).reshape(on.shape))
+
+
+@settings(max_examples=6, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(size=st.tuples(st.integers(200, 330), st.integers(100, 260)), m=st.sampled_from([4, 5, 8]), upstream=st.booleans(), seed=st.integers(0, 2 ** 16))
+def test_node_mode_backward_matches_the_oracle_on_ragged_sizes(size, m, upstream, seed):
+    """Backward at random sizes where the node evaluation is selected (oh not a multiple of 8, ow not a multiple of 32): the
+    sampler backward on the forward's own x, y and grad_T (the adjoint of the node interpolation) against the oracle's sums,
+    rel <= 1e-4 of the max-norm."""
+    from coupe.dvsg_b200 import _lib, ops
+    oh, ow = size[0], 4 * size[1]
+    if _lib.load().dvsg_tps_coords_mode(oh, ow, 3, oh, ow, m * m, 0) != 1:
+        oh, ow = max(oh, 520), max(ow, 1000)                          # make it a node-mode shape
+    rng = np.random.default_rng(seed)
+    u = smooth_image(rng, 1, oh, ow, 3, period=max(16.0, ow / 8.0))
+    coord = tiled_mesh(m, m, 1)
+    vec = rng.uniform(-0.1, 0.1, coord.shape).astype(np.float32) / max(1.0, m / 5.0)
+    g_out = rng.standard_normal((1, oh, ow, 3)).astype(np.float32)
+    gx_in = rng.standard_normal(oh * ow).astype(np.float32) if upstream else None
+    gy_in = rng.standard_normal(oh * ow).astype(np.float32) if upstream else None
+    U, C_ = cu(u), cu(coord)
+    T = ops.tps_solve(C_, C_ + cu(vec))
+    _, x, y, _ = ops.tps_warp_fwd(U, C_, T, (oh, ow))
+    gU, gT, gxs, gys = ops.tps_warp_bwd(U, C_, T, (oh, ow), cu(g_out), None if gx_in is None else cu(gx_in), None if gy_in is None else cu(gy_in),
+                                        want_grid_grad=True)
+    r_gim, r_gx, r_gy = O.tps_interpolate_bwd(u, x.cpu().numpy(), y.cpu().numpy(), oh, ow, g_out)
+    r_gx, r_gy = r_gx.reshape(-1), r_gy.reshape(-1)
+    if upstream:
+        r_gx, r_gy = r_gx + gx_in, r_gy + gy_in
+
+    def rel(a, b_):
+        return float(np.abs(np.asarray(a, np.float64) - b_).max() / max(np.abs(b_).max(), 1e-30))
+    # grad_U: samples outside the frame scatter pairs of exactly opposite contributions onto the frame's border pixels (A4 clamps
+    # the corners first); the kernel drops such pairs, the oracle's float32 scatter leaves their rounding noise (|distance| *
+    # |g| * 2^-24 per pair, hundreds of pairs per border pixel): the border ring gets the looser bar
+    g_k, g_o = gU.cpu().numpy()[0], np.asarray(r_gim, np.float64).reshape(oh, ow, 3)
+    scale = np.abs(g_o).max()
+    assert np.abs(g_k[1:-1, 1:-1] - g_o[1:-1, 1:-1]).max() <= 1e-4 * scale
+    assert np.abs(g_k - g_o).max() <= 5e-3 * scale
+    assert rel(gxs.cpu().numpy(), r_gx) <= 1e-4 and rel(gys.cpu().numpy(), r_gy) <= 1e-4
+    r_gT = O.tps_grid_bwd(coord.astype(np.float64), oh, ow, gxs.cpu().numpy(), gys.cpu().numpy(), dtype=np.float64)
+    assert rel(gT.cpu().numpy(), r_gT) <= 1e-4
